@@ -1,0 +1,80 @@
+"""ctypes binding of the C ABI declared in include/dispu_b200.h.
+
+There is no fallback: if libdispu_b200.so is missing or a call fails, this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "libdispu_b200.so")
+
+EINVAL, ENULL, EUNSUPPORTED, EWORKSPACE = -1, -2, -3, -4
+
+_i, _p, _sz = C.c_int, C.c_void_p, C.c_size_t
+
+# name -> argtypes, exactly the prototypes of include/dispu_b200.h
+SIGNATURES = {
+    "dispu_abi_version": ([], C.c_int),
+    "dispu_error_string": ([_i], C.c_char_p),
+    "dispu_launch_count": ([], C.c_uint64),
+    "dispu_fps": ([_i, _i, _i, _p, _p, _p, _p], _i),
+    "dispu_fps_onchip_capacity": ([], _i),
+    "dispu_gather_point": ([_i, _i, _i, _p, _p, _p, _p], _i),
+    "dispu_gather_point_grad": ([_i, _i, _i, _p, _p, _p, _p], _i),
+    "dispu_prob_sample": ([_i, _i, _i, _p, _p, _p, _p, _p], _i),
+    "dispu_query_ball_point": ([_i, _i, _i, _p, _i, _p, _p, _p, _p, _p], _i),
+    "dispu_group_point": ([_i, _i, _i, _i, _i, _p, _p, _p, _p], _i),
+    "dispu_group_point_grad": ([_i, _i, _i, _i, _i, _p, _p, _p, _p], _i),
+    "dispu_selection_sort": ([_i, _i, _i, _i, _p, _p, _p, _p], _i),
+    "dispu_knn": ([_i, _i, _i, _i, _p, _p, _p, _p, _p], _i),
+    "dispu_three_nn": ([_i, _i, _i, _p, _p, _p, _p, _p], _i),
+    "dispu_three_interpolate": ([_i, _i, _i, _i, _p, _p, _p, _p, _p], _i),
+    "dispu_three_interpolate_grad": ([_i, _i, _i, _i, _p, _p, _p, _p, _p], _i),
+    "dispu_three_nn_weights": ([_i, _i, _p, _p, _p], _i),
+    "dispu_nn_distance": ([_i, _i, _p, _i, _p, _p, _p, _p, _p, _p], _i),
+    "dispu_nn_distance_grad": ([_i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p], _i),
+    "dispu_chamfer_workspace_bytes": ([_i, _i, _i], _sz),
+    "dispu_chamfer": ([_i, _i, _p, _i, _p, _p, _p, _p, _p, _sz, _p], _i),
+    "dispu_sa_mlp": ([_i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _p], _i),
+}
+
+_lib = None
+
+
+class DispuError(RuntimeError):
+    def __init__(self, fn, rc, msg):
+        super().__init__(f"{fn} failed: {msg} (rc={rc})")
+        self.rc = rc
+
+
+def lib():
+    """Load libdispu_b200.so.  Raises if it has not been built — there is no CPU path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO):
+            raise RuntimeError(
+                f"{SO} is missing: build it with `python -m dispu_b200.build` (nvcc, sm_100a). "
+                "dispu_b200 has no CPU or PyTorch fallback.")
+        l = C.CDLL(SO)
+        for name, (args, res) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.argtypes = args
+            fn.restype = res
+        if l.dispu_abi_version() != 1:
+            raise RuntimeError("libdispu_b200.so ABI version mismatch")
+        _lib = l
+    return _lib
+
+
+def check(fn: str, rc: int):
+    if rc != 0:
+        msg = lib().dispu_error_string(rc).decode()
+        if rc in (EINVAL, ENULL):
+            raise ValueError(f"{fn}: {msg} (rc={rc})")
+        raise DispuError(fn, rc, msg)
+
+
+def launch_count() -> int:
+    return int(lib().dispu_launch_count())

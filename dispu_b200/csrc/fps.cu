@@ -1,0 +1,271 @@
+// Farthest point sampling for sm_100a — replaces farthestpointsamplingKernel
+// (tf_ops/sampling/tf_sampling_g.cu:105-170) behind farthestpointsamplingLauncher (:203).
+//
+// Design (not a translation): the reference keeps the running min-distance in GLOBAL memory
+// and re-reads it (plus xyz beyond 3072 points) on every one of the m-1 dependent steps, with
+// a 10-barrier shared-memory tree per step and at most one CTA per cloud.  Here a cloud lives
+// ON CHIP for the whole run: every thread owns P points (x,y,z and the running min-distance in
+// registers), a float4 copy of the cloud sits in shared memory only to look up the winner's
+// coordinates, the per-step arg-max is two `redux.sync` per warp + one barrier + two more
+// `redux.sync`, and clouds too large for one SM's register file (or too few to fill the GPU)
+// are spread over a thread-block CLUSTER whose CTAs exchange their local winners through
+// distributed shared memory with one cluster barrier per step.
+//
+// Bit-exactness: indices must equal the reference's.  The reference's order among equal maxima
+// is (k mod 512) ascending, then k ascending (strided per-thread scan with strict '>' at :146,
+// tree reduction keeping the lower thread id at :158).  That order is carried explicitly as a
+// 32-bit tie key next to the float's bit pattern, so the thread mapping is free.  Distances use
+// the reference's FMA contraction (d2_ref_gpu).
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace dispu {
+
+__device__ __forceinline__ uint32_t fps_tie_of(uint32_t k) { return ((k & 511u) << 23) | (k >> 9); }
+__device__ __forceinline__ uint32_t fps_k_of_tie(uint32_t t) { return (t >> 23) | ((t & 0x7fffffu) << 9); }
+
+constexpr uint32_t kTieNone = 0xffffffffu;
+
+// (bits desc, tie asc) arg-max over a warp; every lane gets the winner.
+__device__ __forceinline__ void warp_argmax(uint32_t bits, uint32_t tie, uint32_t &wb, uint32_t &wt) {
+    wb = __reduce_max_sync(kFull, bits);
+    wt = __reduce_min_sync(kFull, bits == wb ? tie : kTieNone);
+}
+
+struct __align__(16) ClusterSlot {
+    uint32_t bits, tie;
+    float x, y;
+    float z;
+    uint32_t pad[3];
+};
+
+// T threads, P points per thread, cluster of C CTAs per cloud (C == 1: plain CTA).
+template <int T, int P, int C>
+__global__ void __launch_bounds__(T, 1)
+fps_onchip_kernel(int b, int n, int m, const float *__restrict__ xyz, int *__restrict__ idx) {
+    static_assert(T % 32 == 0 && T >= 64 && T <= 1024, "bad T");
+    static_assert(C == 1 || (T * P) % 512 == 0, "cluster chunks must be 512-aligned for the tie order");
+    constexpr int NW = T / 32;
+    // Per-thread scan order that visits this thread's points in ascending tie order, so a strict
+    // '>' keeps the reference's winner: points are k = base + t + i*T; with T < 512 their
+    // (k mod 512) cycles with period R = 512/T, so visit residue classes in turn.
+    constexpr int R = (T >= 512) ? 1 : 512 / T;
+
+    extern __shared__ float4 s_xyz[];  // T*P local points (winner lookup only)
+    __shared__ uint2 s_slot[2][32];
+    __shared__ ClusterSlot s_cslot[2][C > 1 ? C : 1];
+
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    int cloud, rank;
+    if (C > 1) {
+        cg::cluster_group cluster = cg::this_cluster();
+        rank = (int)cluster.block_rank();
+        cloud = blockIdx.x / C;
+    } else {
+        rank = 0;
+        cloud = blockIdx.x;
+    }
+    const int base = rank * (T * P);
+    const float *p = xyz + (size_t)cloud * n * 3;
+    int *out = idx + (size_t)cloud * m;
+
+    float px[P], py[P], pz[P], md[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        const int k = base + t + i * T;
+        if (k < n) {
+            px[i] = __ldg(p + (size_t)k * 3 + 0);
+            py[i] = __ldg(p + (size_t)k * 3 + 1);
+            pz[i] = __ldg(p + (size_t)k * 3 + 2);
+            md[i] = 1e38f;  // tf_sampling_g.cu:118
+        } else {
+            px[i] = py[i] = pz[i] = 0.f;
+            md[i] = -1.f;  // never wins (reference idle threads hold best=-1, :125)
+        }
+        s_xyz[t + i * T] = make_float4(px[i], py[i], pz[i], 0.f);
+    }
+    float x1 = __ldg(p + 0), y1 = __ldg(p + 1), z1 = __ldg(p + 2);  // old = 0 (:114)
+    if (t == 0 && rank == 0) out[0] = 0;
+    __syncthreads();
+    if (C > 1) cg::this_cluster().sync();
+
+    for (int j = 1; j < m; ++j) {
+        const int buf = j & 1;
+        float best = -1.f;
+        int bi = -1;
+#pragma unroll
+        for (int a = 0; a < R; ++a) {
+#pragma unroll
+            for (int i = a; i < P; i += R) {
+                const float d = d2_ref_gpu(__fsub_rn(px[i], x1), __fsub_rn(py[i], y1), __fsub_rn(pz[i], z1));
+                md[i] = fminf(d, md[i]);
+                if (md[i] > best) {
+                    best = md[i];
+                    bi = i;
+                }
+            }
+        }
+        const uint32_t bits = bi >= 0 ? __float_as_uint(best) : 0u;
+        const uint32_t tie = bi >= 0 ? fps_tie_of((uint32_t)(base + t + bi * T)) : kTieNone;
+        uint32_t wb, wt;
+        warp_argmax(bits, tie, wb, wt);
+        if (lane == 0) s_slot[buf][warp] = make_uint2(wb, wt);
+        __syncthreads();
+        const uint2 v = lane < NW ? s_slot[buf][lane] : make_uint2(0u, kTieNone);
+        uint32_t cb, ct;
+        warp_argmax(v.x, v.y, cb, ct);
+
+        if (C == 1) {
+            const uint32_t kwin = fps_k_of_tie(ct);
+            const float4 w = s_xyz[kwin];
+            x1 = w.x; y1 = w.y; z1 = w.z;
+            if (t == 0) out[j] = (int)kwin;
+        } else {
+            cg::cluster_group cluster = cg::this_cluster();
+            if (warp == 0) {
+                // A CTA whose chunk lies wholly beyond n has no valid point: ct == kTieNone.
+                float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ct != kTieNone) w = s_xyz[fps_k_of_tie(ct) - base];
+                if (lane < C) {
+                    ClusterSlot *dst = cluster.map_shared_rank(&s_cslot[buf][rank], lane);
+                    dst->bits = cb; dst->tie = ct; dst->x = w.x; dst->y = w.y; dst->z = w.z;
+                }
+            }
+            cluster.sync();
+            uint32_t sb = 0u, st = kTieNone;
+            float sx = 0.f, sy = 0.f, sz = 0.f;
+            if (lane < C) {
+                const ClusterSlot s = s_cslot[buf][lane];
+                sb = s.bits; st = s.tie; sx = s.x; sy = s.y; sz = s.z;
+            }
+            uint32_t gb, gt;
+            warp_argmax(sb, st, gb, gt);
+            const int src = __ffs(__ballot_sync(kFull, sb == gb && st == gt)) - 1;
+            x1 = __shfl_sync(kFull, sx, src);
+            y1 = __shfl_sync(kFull, sy, src);
+            z1 = __shfl_sync(kFull, sz, src);
+            if (t == 0 && rank == 0) out[j] = (int)fps_k_of_tie(gt);
+        }
+    }
+    // keep peers' shared memory alive until every CTA of the cluster has read its slots
+    if (C > 1) cg::this_cluster().sync();
+}
+
+// Any n: running min-distance in the caller's scratch (the reference's `temp`, (32,n) floats),
+// xyz streamed from global/L2.  Only used beyond the on-chip capacity.
+__global__ void __launch_bounds__(512, 1)
+fps_global_kernel(int b, int n, int m, const float *__restrict__ xyz, float *__restrict__ temp,
+                  int *__restrict__ idx) {
+    __shared__ uint2 s_slot[2][32];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int cloud = blockIdx.x; cloud < b; cloud += gridDim.x) {
+        const float *p = xyz + (size_t)cloud * n * 3;
+        float *mind = temp + (size_t)blockIdx.x * n;
+        int *out = idx + (size_t)cloud * m;
+        for (int k = t; k < n; k += 512) mind[k] = 1e38f;
+        if (t == 0) out[0] = 0;
+        uint32_t last = 0;
+        __syncthreads();
+        for (int j = 1; j < m; ++j) {
+            const int buf = j & 1;
+            const float x1 = __ldg(p + (size_t)last * 3), y1 = __ldg(p + (size_t)last * 3 + 1),
+                        z1 = __ldg(p + (size_t)last * 3 + 2);
+            float best = -1.f;
+            int bk = -1;
+            for (int k = t; k < n; k += 512) {  // same residue class, k ascending: strict '>' suffices
+                const float d = d2_ref_gpu(__fsub_rn(__ldg(p + (size_t)k * 3), x1),
+                                           __fsub_rn(__ldg(p + (size_t)k * 3 + 1), y1),
+                                           __fsub_rn(__ldg(p + (size_t)k * 3 + 2), z1));
+                const float td = mind[k];
+                const float d2 = fminf(d, td);
+                if (d2 != td) mind[k] = d2;
+                if (d2 > best) {
+                    best = d2;
+                    bk = k;
+                }
+            }
+            const uint32_t bits = bk >= 0 ? __float_as_uint(best) : 0u;
+            const uint32_t tie = bk >= 0 ? fps_tie_of((uint32_t)bk) : kTieNone;
+            uint32_t wb, wt;
+            warp_argmax(bits, tie, wb, wt);
+            if (lane == 0) s_slot[buf][warp] = make_uint2(wb, wt);
+            __syncthreads();
+            const uint2 v = lane < 16 ? s_slot[buf][lane] : make_uint2(0u, kTieNone);
+            uint32_t cb, ct;
+            warp_argmax(v.x, v.y, cb, ct);
+            last = fps_k_of_tie(ct);
+            if (t == 0) out[j] = (int)last;
+        }
+        __syncthreads();
+    }
+}
+
+template <int T, int P, int C>
+static int launch_onchip(int b, int n, int m, const float *inp, int *out, cudaStream_t stream) {
+    auto kern = fps_onchip_kernel<T, P, C>;
+    const size_t smem = sizeof(float4) * (size_t)T * P;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)b * C);
+    cfg.blockDim = dim3(T);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    if (C > 1) {
+        if (C > 8) {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (e != cudaSuccess) return (int)e;
+        }
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = C;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    count_launch();
+    e = cudaLaunchKernelEx(&cfg, kern, b, n, m, inp, out);
+    if (e != cudaSuccess) return (int)e;
+    return finish_launch();
+}
+
+constexpr int kFpsOnchipCapacity = 16 * 1024 * 8;
+
+}  // namespace dispu
+
+using namespace dispu;
+
+extern "C" int dispu_fps_onchip_capacity(void) { return kFpsOnchipCapacity; }
+
+extern "C" int dispu_fps(int b, int n, int m, const float *inp, float *temp, int *out, dispu_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DISPU_REQUIRE(b >= 0 && n > 0, DISPU_EINVAL);
+    DISPU_REQUIRE(m > 0, DISPU_EINVAL);  // attr npoint>0, tf_sampling.cpp:99
+    if (b == 0) return DISPU_OK;
+    DISPU_REQUIRE(inp && out, DISPU_ENULL);
+    // single CTA per cloud: fewest warps that keep <= 8 points per thread
+    if (n <= 128) return launch_onchip<128, 1, 1>(b, n, m, inp, out, stream);
+    if (n <= 256) return launch_onchip<128, 2, 1>(b, n, m, inp, out, stream);
+    if (n <= 512) return launch_onchip<128, 4, 1>(b, n, m, inp, out, stream);
+    if (n <= 1024) return launch_onchip<128, 8, 1>(b, n, m, inp, out, stream);
+    if (n <= 2048) return launch_onchip<256, 8, 1>(b, n, m, inp, out, stream);
+    if (n <= 4096) return launch_onchip<512, 8, 1>(b, n, m, inp, out, stream);
+    if (n <= 8192) return launch_onchip<1024, 8, 1>(b, n, m, inp, out, stream);
+    // one cluster per cloud
+    if (n <= 2 * 8192) return launch_onchip<1024, 8, 2>(b, n, m, inp, out, stream);
+    if (n <= 4 * 8192) return launch_onchip<1024, 8, 4>(b, n, m, inp, out, stream);
+    if (n <= 8 * 8192) return launch_onchip<1024, 8, 8>(b, n, m, inp, out, stream);
+    if (n <= kFpsOnchipCapacity) {
+        int rc = launch_onchip<1024, 8, 16>(b, n, m, inp, out, stream);
+        if (rc == DISPU_OK) return rc;
+        (void)cudaGetLastError();  // 16-CTA clusters unavailable on this part/partition: fall through
+    }
+    DISPU_REQUIRE(temp != nullptr, DISPU_EWORKSPACE);
+    count_launch();
+    fps_global_kernel<<<b < 32 ? b : 32, 512, 0, stream>>>(b, n, m, inp, temp, out);
+    return finish_launch();
+}

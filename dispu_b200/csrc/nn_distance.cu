@@ -1,0 +1,223 @@
+// NnDistance (+Grad) and the fused Chamfer/Hausdorff reduction for sm_100a.
+//
+// Replaces NmDistanceKernel / NmDistanceGradKernel (tf_ops/nn_distance/tf_nndistance_g.cu:5-157)
+// and, for dispu_chamfer, the six TF reduce ops of chamfer()/hausdorff_loss()
+// (Common/loss_utils.py:45-84) that follow them.
+//
+// The reference launches the search twice (once per direction, (32,16) CTAs each, :129-130)
+// with a global-memory read-modify-write of the running result per 512-point tile (:119).
+// Here both directions run in ONE launch (blockIdx.z), a thread keeps its query's running
+// (min, argmin) in registers across all tiles, candidates are staged as float4 tiles so the
+// inner loop is one broadcast LDS.128 + 9 FP32 ops per pair, and the grid covers queries x
+// clouds x directions.  First minimum wins (strict '<' in ascending candidate order), which is
+// what the reference's tile logic amounts to.  FMA contraction = d2_ref_gpu.
+//
+// dispu_chamfer never writes the (b,n)/(b,m) distance tensors: each CTA reduces its queries'
+// minima to (sum, max) in a fixed order and stores one partial; a second tiny kernel reduces the
+// partials in a fixed order -> per-cloud cd/hd and the batch mean / max / sum.  No float atomics,
+// so results are run-to-run deterministic.
+#include "common.cuh"
+
+namespace dispu {
+
+constexpr int kNnThreads = 256;
+constexpr int kNnTile = 1024;  // float4 candidates per tile (16 KB)
+
+// One thread = one query of direction `dir` (0: xyz1 -> xyz2, 1: xyz2 -> xyz1).
+template <bool kReduce>
+__global__ void __launch_bounds__(kNnThreads)
+nn_distance_kernel(int n, int m, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
+                   float *__restrict__ dist1, int *__restrict__ idx1, float *__restrict__ dist2,
+                   int *__restrict__ idx2, float2 *__restrict__ partials, int chunks) {
+    __shared__ float4 s_tile[kNnTile];
+    __shared__ float s_red[2][kNnThreads / 32];
+    const int cloud = blockIdx.y, dir = blockIdx.z;
+    const int nq = dir == 0 ? n : m, nc = dir == 0 ? m : n;
+    if ((int)blockIdx.x * kNnThreads >= nq) {  // this direction has fewer query chunks
+        if (kReduce && threadIdx.x == 0 && (int)blockIdx.x < chunks)
+            partials[((size_t)cloud * 2 + dir) * chunks + blockIdx.x] = make_float2(0.f, -1.f);
+        return;
+    }
+    const float *qs = (dir == 0 ? xyz1 : xyz2) + (size_t)cloud * nq * 3;
+    const float *cs = (dir == 0 ? xyz2 : xyz1) + (size_t)cloud * nc * 3;
+    const int j = blockIdx.x * kNnThreads + threadIdx.x;
+    const bool active = j < nq;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    if (active) {
+        qx = __ldg(qs + (size_t)j * 3); qy = __ldg(qs + (size_t)j * 3 + 1); qz = __ldg(qs + (size_t)j * 3 + 2);
+    }
+    float best = __int_as_float(0x7f800000);
+    int bi = 0;
+    for (int t0 = 0; t0 < nc; t0 += kNnTile) {
+        const int tn = min(kNnTile, nc - t0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < tn; e += kNnThreads) {
+            const float *p = cs + (size_t)(t0 + e) * 3;
+            s_tile[e] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
+        }
+        __syncthreads();
+        if (t0 == 0) {  // k==0 initialises unconditionally (tf_nndistance_g.cu:29), even for NaN/inf
+            const float4 p = s_tile[0];
+            best = d2_ref_gpu(__fsub_rn(p.x, qx), __fsub_rn(p.y, qy), __fsub_rn(p.z, qz));
+            bi = 0;
+        }
+#pragma unroll 8
+        for (int e = 0; e < tn; ++e) {
+            const float4 p = s_tile[e];
+            const float d = d2_ref_gpu(__fsub_rn(p.x, qx), __fsub_rn(p.y, qy), __fsub_rn(p.z, qz));
+            if (d < best) {
+                best = d;
+                bi = t0 + e;
+            }
+        }
+    }
+    if (!kReduce) {
+        if (active) {
+            (dir == 0 ? dist1 : dist2)[(size_t)cloud * nq + j] = best;
+            (dir == 0 ? idx1 : idx2)[(size_t)cloud * nq + j] = bi;
+        }
+    } else {
+        // fixed-order block reduction: lanes by xor-shuffle, then warps 0..7 in order
+        float s = active ? best : 0.f;
+        float mx = active ? best : -1.f;  // distances are >= 0
+        s = warp_sum(s);
+        mx = warp_max(mx);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (lane == 0) {
+            s_red[0][warp] = s;
+            s_red[1][warp] = mx;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float ts = 0.f, tm = -1.f;
+#pragma unroll
+            for (int w = 0; w < kNnThreads / 32; ++w) {
+                ts += s_red[0][w];
+                tm = fmaxf(tm, s_red[1][w]);
+            }
+            partials[((size_t)cloud * 2 + dir) * chunks + blockIdx.x] = make_float2(ts, tm);
+        }
+    }
+}
+
+// partials (b,2,chunks) -> per_cloud (b,2) and out[4]; one CTA, fixed order.
+__global__ void __launch_bounds__(256)
+chamfer_finalize_kernel(int b, int n_gt, int n_pred, int chunks, const float2 *__restrict__ partials,
+                        const float *__restrict__ radius, float *__restrict__ out, float *__restrict__ per_cloud,
+                        float *__restrict__ scratch /* (b,2) */) {
+    for (int i = threadIdx.x; i < b; i += blockDim.x) {
+        float sf = 0.f, sb = 0.f, mf = -1.f, mb = -1.f;
+        for (int c = 0; c < chunks; ++c) {
+            const float2 f = partials[((size_t)i * 2 + 0) * chunks + c];
+            const float2 g = partials[((size_t)i * 2 + 1) * chunks + c];
+            sf += f.x; mf = fmaxf(mf, f.y);
+            sb += g.x; mb = fmaxf(mb, g.y);
+        }
+        const float r = radius ? radius[i] : 1.0f;
+        // loss_utils.py:59-62: (mean fwd + mean bwd) / radius ; :79-82 with max
+        const float cd = __fdiv_rn(__fadd_rn(__fdiv_rn(sf, (float)n_gt), __fdiv_rn(sb, (float)n_pred)), r);
+        const float hd = __fdiv_rn(__fadd_rn(mf, mb), r);
+        scratch[i * 2] = cd;
+        scratch[i * 2 + 1] = hd;
+        if (per_cloud) {
+            per_cloud[i * 2] = cd;
+            per_cloud[i * 2 + 1] = hd;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float sum = 0.f, mx = -__int_as_float(0x7f800000);
+        for (int i = 0; i < b; ++i) {
+            sum += scratch[i * 2];
+            mx = fmaxf(mx, scratch[i * 2 + 1]);
+        }
+        out[0] = __fdiv_rn(sum, (float)b);
+        out[1] = mx;
+        out[2] = sum;
+        out[3] = (float)b;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+nn_distance_grad_kernel(int n, int m, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
+                        const float *__restrict__ grad_dist1, const int *__restrict__ idx1,
+                        const float *__restrict__ grad_dist2, const int *__restrict__ idx2,
+                        float *__restrict__ grad_xyz1, float *__restrict__ grad_xyz2) {
+    const int cloud = blockIdx.y, dir = blockIdx.z;
+    const int na = dir == 0 ? n : m, nb = dir == 0 ? m : n;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= na) return;
+    const float *a = (dir == 0 ? xyz1 : xyz2) + (size_t)cloud * na * 3;
+    const float *bb = (dir == 0 ? xyz2 : xyz1) + (size_t)cloud * nb * 3;
+    float *ga = (dir == 0 ? grad_xyz1 : grad_xyz2) + (size_t)cloud * na * 3;
+    float *gb = (dir == 0 ? grad_xyz2 : grad_xyz1) + (size_t)cloud * nb * 3;
+    const int j2 = (dir == 0 ? idx1 : idx2)[(size_t)cloud * na + j];
+    const float g = __fmul_rn((dir == 0 ? grad_dist1 : grad_dist2)[(size_t)cloud * na + j], 2.0f);
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+        const float t = __fmul_rn(g, __fsub_rn(a[(size_t)j * 3 + l], bb[(size_t)j2 * 3 + l]));
+        atomicAdd(ga + (size_t)j * 3 + l, t);
+        atomicAdd(gb + (size_t)j2 * 3 + l, -t);
+    }
+}
+
+static inline int nn_chunks(int n, int m) { return ceil_div(n > m ? n : m, kNnThreads); }
+
+}  // namespace dispu
+
+using namespace dispu;
+
+extern "C" int dispu_nn_distance(int b, int n, const float *xyz1, int m, const float *xyz2, float *dist1, int *idx1,
+                                 float *dist2, int *idx2, dispu_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DISPU_REQUIRE(b >= 0 && n > 0 && m > 0, DISPU_EINVAL);
+    if (b == 0) return DISPU_OK;
+    DISPU_REQUIRE(xyz1 && xyz2 && dist1 && idx1 && dist2 && idx2, DISPU_ENULL);
+    DISPU_REQUIRE(b <= 65535, DISPU_EUNSUPPORTED);
+    count_launch();
+    nn_distance_kernel<false><<<dim3(nn_chunks(n, m), b, 2), kNnThreads, 0, stream>>>(n, m, xyz1, xyz2, dist1, idx1,
+                                                                                     dist2, idx2, nullptr, 0);
+    return finish_launch();
+}
+
+extern "C" int dispu_nn_distance_grad(int b, int n, const float *xyz1, int m, const float *xyz2,
+                                      const float *grad_dist1, const int *idx1, const float *grad_dist2,
+                                      const int *idx2, float *grad_xyz1, float *grad_xyz2, dispu_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DISPU_REQUIRE(b >= 0 && n > 0 && m > 0, DISPU_EINVAL);
+    if (b == 0) return DISPU_OK;
+    DISPU_REQUIRE(xyz1 && xyz2 && grad_dist1 && idx1 && grad_dist2 && idx2 && grad_xyz1 && grad_xyz2, DISPU_ENULL);
+    DISPU_REQUIRE(b <= 65535, DISPU_EUNSUPPORTED);
+    cudaError_t e = cudaMemsetAsync(grad_xyz1, 0, sizeof(float) * (size_t)b * n * 3, stream);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemsetAsync(grad_xyz2, 0, sizeof(float) * (size_t)b * m * 3, stream);
+    if (e != cudaSuccess) return (int)e;
+    count_launch();
+    nn_distance_grad_kernel<<<dim3(ceil_div(n > m ? n : m, 256), b, 2), 256, 0, stream>>>(
+        n, m, xyz1, xyz2, grad_dist1, idx1, grad_dist2, idx2, grad_xyz1, grad_xyz2);
+    return finish_launch();
+}
+
+extern "C" size_t dispu_chamfer_workspace_bytes(int b, int n_gt, int n_pred) {
+    if (b <= 0 || n_gt <= 0 || n_pred <= 0) return 0;
+    return sizeof(float2) * (size_t)b * 2 * nn_chunks(n_gt, n_pred) + sizeof(float) * 2 * (size_t)b;
+}
+
+extern "C" int dispu_chamfer(int b, int n_gt, const float *gt, int n_pred, const float *pred, const float *radius,
+                             float *out, float *per_cloud, void *workspace, size_t workspace_bytes,
+                             dispu_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DISPU_REQUIRE(b > 0 && n_gt > 0 && n_pred > 0, DISPU_EINVAL);
+    DISPU_REQUIRE(gt && pred && out, DISPU_ENULL);
+    DISPU_REQUIRE(b <= 65535, DISPU_EUNSUPPORTED);
+    DISPU_REQUIRE(workspace && workspace_bytes >= dispu_chamfer_workspace_bytes(b, n_gt, n_pred), DISPU_EWORKSPACE);
+    const int chunks = nn_chunks(n_gt, n_pred);
+    float2 *partials = reinterpret_cast<float2 *>(workspace);
+    float *scratch = reinterpret_cast<float *>(partials + (size_t)b * 2 * chunks);
+    count_launch(2);
+    // nn_distance(gt, pred): dists_forward belongs to gt (loss_utils.py:51)
+    nn_distance_kernel<true><<<dim3(chunks, b, 2), kNnThreads, 0, stream>>>(n_gt, n_pred, gt, pred, nullptr, nullptr,
+                                                                            nullptr, nullptr, partials, chunks);
+    chamfer_finalize_kernel<<<1, 256, 0, stream>>>(b, n_gt, n_pred, chunks, partials, radius, out, per_cloud, scratch);
+    return finish_launch();
+}

@@ -1,0 +1,172 @@
+// Fused set-abstraction body for sm_100a: group -> centre-subtract -> concat -> 1x1-conv MLP
+// (bias, ReLU) -> max over nsample.  Replaces the chain the reference builds out of separate TF
+// ops, each of which round-trips a (b,npoint,nsample,C) tensor through HBM
+// (Common/pointnet_util.py:46-53 group_point x2 / tile / subtract / concat, :117-121
+// tf_util.conv2d per layer = Common/tf_util.py:120-185, :133 reduce_max).  Nothing of shape
+// (b,npoint,nsample,*) is ever written to global memory here: the only HBM traffic is idx, the
+// gathered rows (L2-resident after first touch), the weights and the (b,npoint,C_out) result.
+//
+// This file holds the exact-FP32 path (DISPU_MLP_FP32): one thread owns one grouped row, its
+// activations ping-pong between two private shared-memory rows (odd stride: conflict-free), each
+// layer is a register-tiled FMA chain over C_in in ascending order, and the pool is a column max
+// over the CTA's rows.  The tensor-core path (DISPU_MLP_TF32X3, tcgen05) lives in
+// sa_mlp_tc.cu.
+#include "common.cuh"
+
+namespace dispu {
+
+constexpr int kMlpThreads = 128;
+constexpr int kMlpMaxLayers = 4;
+
+struct MlpParams {
+    int n_layers;
+    int widths[kMlpMaxLayers + 1];
+    const float *w[kMlpMaxLayers];
+    const float *bias[kMlpMaxLayers];
+};
+
+// rows of a CTA pass: kMlpThreads; groups per pass G = kMlpThreads / ns when ns divides 128,
+// else one group per pass processed in chunks of 128 rows.
+__global__ void __launch_bounds__(kMlpThreads)
+sa_mlp_fp32_kernel(int n, int m, int ns, int c_pts, int layout, const float *__restrict__ xyz,
+                   const float *__restrict__ points, const float *__restrict__ new_xyz,
+                   const int *__restrict__ idx, MlpParams prm, float *__restrict__ out, long long n_groups,
+                   int stride /* odd, >= max width */) {
+    extern __shared__ float s_buf[];  // 2 * kMlpThreads * stride
+    float *buf0 = s_buf + (size_t)threadIdx.x * stride;
+    float *buf1 = s_buf + (size_t)(kMlpThreads + threadIdx.x) * stride;
+    const int t = threadIdx.x;
+    const int c_in = 3 + c_pts;
+    const int c_out = prm.widths[prm.n_layers];
+    const bool multi = ns <= kMlpThreads && (kMlpThreads % ns) == 0;
+    const int G = multi ? kMlpThreads / ns : 1;
+    const int chunks = multi ? 1 : ceil_div(ns, kMlpThreads);
+
+    for (long long g0 = (long long)blockIdx.x * G; g0 < n_groups; g0 += (long long)gridDim.x * G) {
+        for (int ch = 0; ch < chunks; ++ch) {
+            // ---- which grouped row is mine
+            const int gi = multi ? t / ns : 0;
+            const int s = multi ? t % ns : ch * kMlpThreads + t;
+            const long long g = g0 + gi;
+            const bool valid = g < n_groups && s < ns;
+            float *x = buf0, *y = buf1;
+            if (valid) {
+                const long long cloud = g / m;
+                const int ii = __ldg(idx + g * ns + s);
+                const float *pxyz = xyz + (cloud * n + ii) * 3;
+                const float *ctr = new_xyz + g * 3;
+                const float gx = __fsub_rn(__ldg(pxyz), __ldg(ctr));
+                const float gy = __fsub_rn(__ldg(pxyz + 1), __ldg(ctr + 1));
+                const float gz = __fsub_rn(__ldg(pxyz + 2), __ldg(ctr + 2));
+                const int xo = layout == 0 ? 0 : c_pts, po = layout == 0 ? 3 : 0;
+                x[xo] = gx; x[xo + 1] = gy; x[xo + 2] = gz;
+                if (c_pts) {
+                    const float *pf = points + (cloud * n + ii) * (long long)c_pts;
+                    for (int l = 0; l < c_pts; ++l) x[po + l] = __ldg(pf + l);
+                }
+                // ---- MLP, private to this thread's row
+                for (int l = 0; l < prm.n_layers; ++l) {
+                    const int ci = prm.widths[l], co = prm.widths[l + 1];
+                    const float *W = prm.w[l];
+                    const float *B = prm.bias[l];
+                    int oc = 0;
+                    for (; oc + 8 <= co; oc += 8) {
+                        float acc[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) acc[u] = 0.f;
+                        for (int ic = 0; ic < ci; ++ic) {
+                            const float xv = x[ic];
+                            const float *wr = W + (size_t)ic * co + oc;
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) acc[u] = __fmaf_rn(xv, __ldg(wr + u), acc[u]);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const float v = B ? __fadd_rn(acc[u], __ldg(B + oc + u)) : acc[u];
+                            y[oc + u] = fmaxf(v, 0.f);
+                        }
+                    }
+                    for (; oc < co; ++oc) {
+                        float acc = 0.f;
+                        for (int ic = 0; ic < ci; ++ic) acc = __fmaf_rn(x[ic], __ldg(W + (size_t)ic * co + oc), acc);
+                        const float v = B ? __fadd_rn(acc, __ldg(B + oc)) : acc;
+                        y[oc] = fmaxf(v, 0.f);
+                    }
+                    float *tmp = x; x = y; y = tmp;
+                }
+            }
+            __syncthreads();
+            // ---- pool: the result rows sit in buffer (n_layers & 1)
+            const float *res = s_buf + (size_t)((prm.n_layers & 1) ? kMlpThreads : 0) * stride;
+            for (int e = t; e < G * c_out; e += kMlpThreads) {
+                const int pg = e / c_out, oc = e - pg * c_out;
+                const long long gg = g0 + pg;
+                if (gg >= n_groups) continue;
+                const int r0 = multi ? pg * ns : 0;
+                const int rows = multi ? ns : min(kMlpThreads, ns - ch * kMlpThreads);
+                float mx = res[(size_t)r0 * stride + oc];
+                for (int r = 1; r < rows; ++r) mx = fmaxf(mx, res[(size_t)(r0 + r) * stride + oc]);
+                float *o = out + gg * c_out + oc;
+                if (ch == 0) *o = mx; else *o = fmaxf(*o, mx);
+            }
+            __syncthreads();
+        }
+    }
+    (void)c_in;
+}
+
+int sa_mlp_tc_launch(int b, int n, int m, int ns, int c_pts, int layout, const float *xyz, const float *points,
+                     const float *new_xyz, const int *idx, const MlpParams &prm, float *out, cudaStream_t stream,
+                     bool *handled);
+
+}  // namespace dispu
+
+using namespace dispu;
+
+extern "C" int dispu_sa_mlp(int b, int n, int m, int nsample, int c_pts, int layout, const float *xyz,
+                            const float *points, const float *new_xyz, const int *idx, int n_layers,
+                            const int *widths, const float *const *weights, const float *const *biases, float *out,
+                            int precision, dispu_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DISPU_REQUIRE(b >= 0 && n > 0 && m >= 0 && nsample > 0 && c_pts >= 0, DISPU_EINVAL);
+    DISPU_REQUIRE(layout == 0 || layout == 1, DISPU_EINVAL);
+    DISPU_REQUIRE(n_layers >= 1 && n_layers <= kMlpMaxLayers, DISPU_EINVAL);
+    DISPU_REQUIRE(widths && weights && biases, DISPU_ENULL);
+    DISPU_REQUIRE(widths[0] == 3 + c_pts, DISPU_EINVAL);
+    DISPU_REQUIRE(precision == DISPU_MLP_FP32 || precision == DISPU_MLP_TF32X3, DISPU_EINVAL);
+    if (b == 0 || m == 0) return DISPU_OK;
+    DISPU_REQUIRE(xyz && new_xyz && idx && out && (c_pts == 0 || points), DISPU_ENULL);
+    MlpParams prm;
+    prm.n_layers = n_layers;
+    int wmax = widths[0];
+    for (int l = 0; l <= n_layers; ++l) {
+        DISPU_REQUIRE(widths[l] > 0, DISPU_EINVAL);
+        prm.widths[l] = widths[l];
+        if (widths[l] > wmax) wmax = widths[l];
+    }
+    for (int l = 0; l < n_layers; ++l) {
+        DISPU_REQUIRE(weights[l], DISPU_ENULL);
+        prm.w[l] = weights[l];
+        prm.bias[l] = biases[l];
+    }
+    if (precision == DISPU_MLP_TF32X3) {
+        bool handled = false;
+        int rc = sa_mlp_tc_launch(b, n, m, nsample, c_pts, layout, xyz, points, new_xyz, idx, prm, out, stream, &handled);
+        if (handled) return rc;
+        return DISPU_EUNSUPPORTED;  // shape outside the tensor-core kernel's instantiations
+    }
+    const int stride = wmax | 1;
+    const size_t smem = sizeof(float) * 2 * kMlpThreads * (size_t)stride;
+    DISPU_REQUIRE(smem <= 200 * 1024, DISPU_EUNSUPPORTED);
+    cudaError_t e = cudaFuncSetAttribute(sa_mlp_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const long long n_groups = (long long)b * m;
+    const bool multi = nsample <= kMlpThreads && (kMlpThreads % nsample) == 0;
+    const int G = multi ? kMlpThreads / nsample : 1;
+    long long grid = ceil_div64(n_groups, G);
+    if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+    count_launch();
+    sa_mlp_fp32_kernel<<<(unsigned)grid, kMlpThreads, smem, stream>>>(n, m, nsample, c_pts, layout, xyz, points, new_xyz,
+                                                                     idx, prm, out, n_groups, stride);
+    return finish_launch();
+}

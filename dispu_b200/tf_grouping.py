@@ -1,0 +1,109 @@
+"""Mirror of tf_ops/grouping/tf_grouping.py on torch CUDA tensors, backed by the sm_100a kernels."""
+from __future__ import annotations
+
+import numbers
+
+import torch
+
+from ._t import call, ptr, req, stream_ptr
+
+
+def query_ball_point(radius, nsample, xyz, new_xyz):
+    """tf_grouping.py:9.  xyz (b,n,3) dataset, new_xyz (b,m,3) queries, radius scalar or (b,) tensor
+    (only element 0 is used, as in tf_grouping_g.cu:25) -> idx (b,m,nsample) i32, pts_cnt (b,m) i32."""
+    xyz = req(xyz, torch.float32, 3, "xyz")
+    new_xyz = req(new_xyz, torch.float32, 3, "new_xyz")
+    b, n, c = xyz.shape
+    if c != 3:
+        raise ValueError("QueryBallPoint expects (batch_size, ndataset, 3) xyz1 shape.")  # tf_grouping.cpp:80
+    if new_xyz.shape[0] != b or new_xyz.shape[2] != 3:
+        raise ValueError("QueryBallPoint expects (batch_size, npoint, 3) xyz2 shape.")  # tf_grouping.cpp:85
+    if nsample <= 0:
+        raise ValueError("QueryBallPoint expects positive nsample")  # tf_grouping.cpp:75
+    m = new_xyz.shape[1]
+    if isinstance(radius, numbers.Real):  # tf_grouping.py:21-26: scalar -> tiled (b,) tensor
+        radius = torch.full((max(b, 1),), float(radius), dtype=torch.float32, device=xyz.device)
+    radius = req(radius, torch.float32, 1, "radius")
+    idx = torch.empty((b, m, nsample), dtype=torch.int32, device=xyz.device)
+    cnt = torch.empty((b, m), dtype=torch.int32, device=xyz.device)
+    call("dispu_query_ball_point", b, n, m, ptr(radius), nsample, ptr(xyz), ptr(new_xyz), ptr(idx), ptr(cnt),
+         stream_ptr())
+    return idx, cnt
+
+
+def select_top_k(k, dist):
+    """tf_grouping.py:33.  dist (b,m,n) -> (idx (b,m,n) i32, dist_out (b,m,n)); first k columns are the k smallest."""
+    dist = req(dist, torch.float32, 3, "dist")
+    if k <= 0:
+        raise ValueError("SelectionSort expects positive k")  # tf_grouping.cpp:119
+    b, m, n = dist.shape
+    outi = torch.empty((b, m, n), dtype=torch.int32, device=dist.device)
+    out = torch.empty((b, m, n), dtype=torch.float32, device=dist.device)
+    call("dispu_selection_sort", b, n, m, k, ptr(dist), ptr(outi), ptr(out), stream_ptr())
+    return outi, out
+
+
+class _GroupPoint(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, idx):
+        b, n, c = points.shape
+        _, m, ns = idx.shape
+        out = torch.empty((b, m, ns, c), dtype=torch.float32, device=points.device)
+        call("dispu_group_point", b, n, c, m, ns, ptr(points), ptr(idx), ptr(out), stream_ptr())
+        ctx.save_for_backward(idx)
+        ctx.shape = (b, n, c)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):  # tf_grouping.py:53-57
+        (idx,) = ctx.saved_tensors
+        b, n, c = ctx.shape
+        _, m, ns = idx.shape
+        grad_out = grad_out.contiguous()
+        g = torch.empty((b, n, c), dtype=torch.float32, device=grad_out.device)
+        call("dispu_group_point_grad", b, n, c, m, ns, ptr(grad_out), ptr(idx), ptr(g), stream_ptr())
+        return g, None
+
+
+def group_point(points, idx):
+    """tf_grouping.py:44.  points (b,n,c), idx (b,m,nsample) i32 -> (b,m,nsample,c); differentiable w.r.t. points."""
+    points = req(points, torch.float32, 3, "points")
+    idx = req(idx, torch.int32, 3, "idx")
+    if idx.shape[0] != points.shape[0]:
+        raise ValueError("GroupPoint expects (batch_size, npoints, nsample) idx shape")  # tf_grouping.cpp:160
+    return _GroupPoint.apply(points, idx)
+
+
+def group_point_grad(points, idx, grad_out):
+    """The GroupPointGrad op (tf_grouping.cpp:56-64)."""
+    points = req(points, torch.float32, 3, "points")
+    idx = req(idx, torch.int32, 3, "idx")
+    grad_out = req(grad_out, torch.float32, 4, "grad_out")
+    b, n, c = points.shape
+    _, m, ns = idx.shape
+    g = torch.empty((b, n, c), dtype=torch.float32, device=points.device)
+    call("dispu_group_point_grad", b, n, c, m, ns, ptr(grad_out), ptr(idx), ptr(g), stream_ptr())
+    return g
+
+
+def knn(k, xyz1, xyz2):
+    """k nearest dataset points xyz1 (b,n,3) of every query xyz2 (b,m,3): (+d2 (b,m,k), idx (b,m,k) i32),
+    ascending, ties to the lower index."""
+    xyz1 = req(xyz1, torch.float32, 3, "xyz1")
+    xyz2 = req(xyz2, torch.float32, 3, "xyz2")
+    b, n, c = xyz1.shape
+    if c != 3 or xyz2.shape[2] != 3:
+        raise NotImplementedError("dispu_knn is the 3-D kernel; feature-space kNN is SURVEY §8(f) rank 3")
+    if xyz2.shape[0] != b:
+        raise ValueError("knn expects xyz1 and xyz2 to share the batch dimension")
+    m = xyz2.shape[1]
+    dist = torch.empty((b, m, k), dtype=torch.float32, device=xyz1.device)
+    idx = torch.empty((b, m, k), dtype=torch.int32, device=xyz1.device)
+    call("dispu_knn", b, n, m, k, ptr(xyz1), ptr(xyz2), ptr(dist), ptr(idx), stream_ptr())
+    return dist, idx
+
+
+def knn_point(k, xyz1, xyz2):
+    """tf_grouping.py:116.  Returns (val, idx) with val = NEGATED squared distances, like top_k(-dist)."""
+    dist, idx = knn(k, xyz1, xyz2)
+    return -dist, idx

@@ -1,0 +1,165 @@
+/*
+ * dispu_b200.h — C ABI of the B200-native (sm_100a) Dis-PU sampling / grouping /
+ * interpolation / Chamfer hot path (libdispu_b200.so).
+ *
+ * Conventions:
+ *   - every pointer is a DEVICE pointer owned by the caller unless the name ends in _host;
+ *     tensors are dense, row-major, contiguous; float32 / int32;
+ *   - the callee never allocates or frees device memory and never synchronises the stream;
+ *   - dims are int32 like the reference launchers, indexing inside is 64-bit;
+ *   - every entry point returns 0 on success, a NEGATIVE DISPU_E* code for a rejected
+ *     argument (the reference wrappers' OP_REQUIRES checks), or a POSITIVE cudaError_t;
+ *   - `stream` is a cudaStream_t (0 = legacy default stream, which is what the reference
+ *     launchers use: e.g. tf_ops/sampling/tf_sampling_g.cu:203-205);
+ *   - there is no CPU fallback anywhere.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the
+ * reference checkout).  The same object also exports the reference's C++-mangled launcher
+ * symbols (csrc/ref_launchers.cu) so the reference's unmodified tf_*.cpp wrappers link
+ * against it — see INTEGRATION.md.
+ */
+#ifndef DISPU_B200_H_
+#define DISPU_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st *dispu_stream_t; /* == cudaStream_t */
+
+#define DISPU_OK 0
+#define DISPU_EINVAL (-1)      /* bad dimension / attribute (OP_REQUIRES InvalidArgument) */
+#define DISPU_ENULL (-2)       /* required pointer is NULL */
+#define DISPU_EUNSUPPORTED (-3) /* size outside what the kernels are instantiated for */
+#define DISPU_EWORKSPACE (-4)  /* scratch buffer missing or too small */
+
+#define DISPU_ABI_VERSION 1
+int dispu_abi_version(void);
+/* Static string for a return code of any entry point (negative: ours, positive: CUDA). */
+const char *dispu_error_string(int rc);
+/* Number of kernel launches issued by this library since load (bench.py "gpu_launches"). */
+uint64_t dispu_launch_count(void);
+
+/* ---- tf_ops/sampling ------------------------------------------------------------------- */
+
+/* FarthestPointSample.  Replaces farthestpointsamplingLauncher (tf_sampling.cpp:94 ->
+ * tf_sampling_g.cu:203) and its kernel (tf_sampling_g.cu:105-170).  inp (b,n,3) -> out (b,m),
+ * out[:,0]=0, bit-exact tie order of the reference.  `temp` is the
+ * reference's (32,n) float scratch (tf_sampling.cpp:115); it is only touched when n exceeds
+ * what fits on chip (n > dispu_fps_onchip_capacity()) and may be NULL otherwise. */
+int dispu_fps(int b, int n, int m, const float *inp, float *temp, int *out, dispu_stream_t stream);
+int dispu_fps_onchip_capacity(void);
+
+/* GatherPoint / GatherPointGrad.  gatherpointLauncher tf_sampling.cpp:125 (kernel
+ * tf_sampling_g.cu:172) and scatteraddpointLauncher :150 (kernel :183; the zero fill the
+ * wrapper does at :174 is done here). */
+int dispu_gather_point(int b, int n, int m, const float *inp, const int *idx, float *out, dispu_stream_t stream);
+int dispu_gather_point_grad(int b, int n, int m, const float *out_g, const int *idx, float *inp_g,
+                            dispu_stream_t stream);
+
+/* ProbSample.  probsampleLauncher tf_sampling.cpp:65 (kernels tf_sampling_g.cu:7,90): inclusive
+ * prefix sum of inp_p (b,n) into temp (b,n), then for every inp_r (b,m) in [0,1) the first
+ * bucket whose cumulative mass reaches r*total.  Registered for API completeness (its only
+ * call site, tf_sampling.py:87, is commented out). */
+int dispu_prob_sample(int b, int n, int m, const float *inp_p, const float *inp_r, float *temp, int *out,
+                      dispu_stream_t stream);
+
+/* ---- tf_ops/grouping ------------------------------------------------------------------- */
+
+/* QueryBallPoint.  queryBallPointLauncher tf_grouping.cpp:67 (kernel tf_grouping_g.cu:3-36).
+ * xyz1 (b,n,3) dataset, xyz2 (b,m,3) queries, radius: DEVICE tensor (b,) of which only
+ * element 0 is read (tf_grouping_g.cu:25) -> idx (b,m,nsample), pts_cnt (b,m).
+ * One documented difference: a row with pts_cnt==0 is written as zeros (the reference leaves
+ * it uninitialised). */
+int dispu_query_ball_point(int b, int n, int m, const float *radius, int nsample, const float *xyz1,
+                           const float *xyz2, int *idx, int *pts_cnt, dispu_stream_t stream);
+
+/* GroupPoint / GroupPointGrad.  groupPointLauncher tf_grouping.cpp:146 (kernel
+ * tf_grouping_g.cu:40) and groupPointGradLauncher :177 (kernel :61; zero fill of
+ * tf_grouping.cpp:208 done here). */
+int dispu_group_point(int b, int n, int c, int m, int nsample, const float *points, const int *idx, float *out,
+                      dispu_stream_t stream);
+int dispu_group_point_grad(int b, int n, int c, int m, int nsample, const float *grad_out, const int *idx,
+                           float *grad_points, dispu_stream_t stream);
+
+/* SelectionSort.  selectionSortLauncher tf_grouping.cpp:112 (kernel tf_grouping_g.cu:83). */
+int dispu_selection_sort(int b, int n, int m, int k, const float *dist, int *outi, float *out,
+                         dispu_stream_t stream);
+
+/* kNN grouping in 3-D: k smallest squared L2 distances from every query xyz2[b,j] into
+ * xyz1[b,:], ascending, ties to the lower index.  Replaces the three reference routes
+ * (SURVEY.md §8 a5): nanoflann cpp_knn_batch_omp (libs/nearest_neighbors/knn_.cxx:104 via
+ * Common/ops.py:110-118,165 — removing its device->host->device round trip), knn_point
+ * (tf_grouping.py:116-141; it returns -dist) and the 3-D use of knn_point_2 (:95-114).
+ * dist (b,m,k) may be NULL.  1 <= k <= 64, k <= n. */
+int dispu_knn(int b, int n, int m, int k, const float *xyz1, const float *xyz2, float *dist, int *idx,
+              dispu_stream_t stream);
+
+/* ---- tf_ops/interpolation (the reference has CPU-only kernels here) --------------------- */
+
+/* ThreeNN.  threenn_cpu tf_interpolate.cpp:60-103 (op :157-187): xyz1 (b,n,3) unknown,
+ * xyz2 (b,m,3) known -> dist (b,n,3) SQUARED distances ascending, idx (b,n,3). */
+int dispu_three_nn(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist, int *idx,
+                   dispu_stream_t stream);
+/* ThreeInterpolate / Grad.  threeinterpolate_cpu :107-127, threeinterpolate_grad_cpu :131-153
+ * (zero fill of :258 done here).  points (b,m,c), idx/weight (b,n,3) -> out (b,n,c). */
+int dispu_three_interpolate(int b, int m, int c, int n, const float *points, const int *idx, const float *weight,
+                            float *out, dispu_stream_t stream);
+int dispu_three_interpolate_grad(int b, int n, int c, int m, const float *grad_out, const int *idx,
+                                 const float *weight, float *grad_points, dispu_stream_t stream);
+/* Inverse-distance weights of pointnet_fp_module (Common/pointnet_util.py:205-208):
+ * d=max(d,1e-10); w=(1/d)/sum_3(1/d).  dist (b,n,3) -> weight (b,n,3). */
+int dispu_three_nn_weights(int b, int n, const float *dist, float *weight, dispu_stream_t stream);
+
+/* ---- tf_ops/nn_distance + Common/loss_utils.py ------------------------------------------ */
+
+/* NnDistance.  NmDistanceKernelLauncher tf_nndistance.cpp:168 (kernel tf_nndistance_g.cu:5-131).
+ * Same argument order as the launcher. */
+int dispu_nn_distance(int b, int n, const float *xyz1, int m, const float *xyz2, float *dist1, int *idx1,
+                      float *dist2, int *idx2, dispu_stream_t stream);
+/* NnDistanceGrad.  NmDistanceGradKernelLauncher tf_nndistance.cpp:208 (tf_nndistance_g.cu:132-157). */
+int dispu_nn_distance_grad(int b, int n, const float *xyz1, int m, const float *xyz2, const float *grad_dist1,
+                           const int *idx1, const float *grad_dist2, const int *idx2, float *grad_xyz1,
+                           float *grad_xyz2, dispu_stream_t stream);
+
+/* Fused NnDistance + chamfer() + hausdorff_loss() (Common/loss_utils.py:45-64, :67-84), called
+ * like the trainer does (DisPU/model.py:75-79): chamfer(pred, gt) -> nn_distance(gt, pred).
+ *   per_cloud (b,2): [cd_b, hd_b] = [(mean fwd + mean bwd)/radius_b, (max fwd + max bwd)/radius_b]
+ *   out (4):  [mean_b cd_b, max_b hd_b, sum_b cd_b, (float)b]
+ * out[2] is the partial a data-parallel rank contributes to the one all-reduce of the path.
+ * radius (b,) may be NULL (= ones, DisPU/dataset.py:68).  per_cloud may be NULL.
+ * workspace: dispu_chamfer_workspace_bytes(b, n_gt, n_pred) bytes, any contents.
+ * Deterministic: fixed-order reductions, no float atomics. */
+size_t dispu_chamfer_workspace_bytes(int b, int n_gt, int n_pred);
+int dispu_chamfer(int b, int n_gt, const float *gt, int n_pred, const float *pred, const float *radius,
+                  float *out, float *per_cloud, void *workspace, size_t workspace_bytes, dispu_stream_t stream);
+
+/* ---- Common/pointnet_util.py set abstraction --------------------------------------------- */
+
+/* Fused group -> centre-subtract -> concat -> 1x1-conv MLP (bias, ReLU) -> max over nsample:
+ * pointnet_sa_module / sample_and_group (pointnet_util.py:41-59, :117-133) and the _msg
+ * channel order (:179), with tf_util.conv2d (Common/tf_util.py:120-185) as the layer.  The
+ * (b,m,nsample,C) tensors of the reference are never materialised.
+ *   xyz (b,n,3); points (b,n,c_pts) or NULL (c_pts=0); new_xyz (b,m,3); idx (b,m,nsample)
+ *   layout 0: channels = [xyz-centre (3), points]   (sample_and_group, :53)
+ *   layout 1: channels = [points, xyz-centre (3)]   (pointnet_sa_module_msg, :179)
+ *   n_layers in 1..4; widths[0] = 3+c_pts, widths[l+1] = C_out of layer l;
+ *   weights[l]: DEVICE (widths[l], widths[l+1]) row-major (= the (1,1,C_in,C_out) kernel);
+ *   biases[l]: DEVICE (widths[l+1]) or NULL;  the arrays `widths/weights/biases` are HOST arrays.
+ *   out (b,m,widths[n_layers]).
+ *   precision: DISPU_MLP_FP32 = exact fp32 FMA chain; DISPU_MLP_TF32X3 = tcgen05 tensor cores
+ *   with 3xTF32 error-compensated splits (fp32-level accuracy). */
+#define DISPU_MLP_FP32 0
+#define DISPU_MLP_TF32X3 1
+int dispu_sa_mlp(int b, int n, int m, int nsample, int c_pts, int layout, const float *xyz, const float *points,
+                 const float *new_xyz, const int *idx, int n_layers, const int *widths_host,
+                 const float *const *weights_host_array, const float *const *biases_host_array, float *out,
+                 int precision, dispu_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DISPU_B200_H_ */

@@ -1,0 +1,338 @@
+"""GPU parity: the sm_100a kernels (through the C ABI / the reference-shaped Python wrappers)
+against the CPU oracle and against the reference's own CUDA kernels recompiled for sm_100a
+(oracle/_ref/libref_gpu.so).  Integer outputs bit-exact; floats bit-exact where the arithmetic
+is pinned, else within the stated tolerance."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import lattice, unit_ball
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as O  # noqa: E402
+from oracle import ref as R  # noqa: E402
+
+import dispu_b200.tf_sampling as S  # noqa: E402
+import dispu_b200.tf_grouping as G  # noqa: E402
+import dispu_b200.tf_interpolate as I  # noqa: E402
+import dispu_b200.tf_nndistance as N  # noqa: E402
+import dispu_b200.loss_utils as LU  # noqa: E402
+import dispu_b200.pointnet_util as PU  # noqa: E402
+
+dev = "cuda"
+HAVE_REF_GPU = R.available("gpu")
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def ref_fps(xyz, m):
+    b, n, _ = xyz.shape
+    x = T(xyz)
+    temp = torch.empty((32, n), dtype=torch.float32, device=dev)
+    out = torch.empty((b, m), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    R.gpu_fps(b, n, m, x.data_ptr(), temp.data_ptr(), out.data_ptr())
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+# ---------------------------------------------------------------- FPS
+@pytest.mark.parametrize("n,m", [(1, 1), (1, 4), (3, 3), (100, 10), (256, 64), (511, 128), (512, 128), (513, 128),
+                                 (1024, 256), (2048, 24), (3071, 100), (3072, 100), (3073, 100), (5000, 64),
+                                 (8192, 33), (100, 150)])
+def test_fps_vs_oracle_and_ref(rng, n, m):
+    xyz = unit_ball(rng, 3, n)
+    got = S.farthest_point_sample(m, T(xyz)).cpu().numpy()
+    want = O.farthest_point_sample(m, xyz)
+    assert np.array_equal(got, want)
+    if HAVE_REF_GPU:
+        assert np.array_equal(got, ref_fps(xyz, m))
+
+
+@pytest.mark.parametrize("n,m", [(600, 200), (1500, 300), (4100, 64)])
+def test_fps_ties(rng, n, m):
+    xyz = lattice(rng, 2, n, q=6)  # heavy exact ties + duplicated points
+    got = S.farthest_point_sample(m, T(xyz)).cpu().numpy()
+    assert np.array_equal(got, O.farthest_point_sample(m, xyz))
+    if HAVE_REF_GPU:
+        assert np.array_equal(got, ref_fps(xyz, m))
+
+
+def test_fps_identical_cloud():
+    xyz = np.full((2, 700, 3), 0.25, np.float32)
+    got = S.farthest_point_sample(16, T(xyz)).cpu().numpy()
+    assert np.array_equal(got, O.farthest_point_sample(16, xyz))
+    assert (got == 0).all()
+
+
+@pytest.mark.parametrize("n,m", [(10000, 40), (20000, 30), (40000, 24), (70000, 20), (131072, 12)])
+def test_fps_cluster_sizes(rng, n, m):
+    xyz = unit_ball(rng, 2, n)
+    got = S.farthest_point_sample(m, T(xyz)).cpu().numpy()
+    assert np.array_equal(got, O.farthest_point_sample(m, xyz))
+    if HAVE_REF_GPU:
+        assert np.array_equal(got, ref_fps(xyz, m))
+
+
+def test_fps_global_fallback(rng):
+    n, m = 140000, 10
+    xyz = unit_ball(rng, 1, n)
+    got = S.farthest_point_sample(m, T(xyz)).cpu().numpy()
+    assert np.array_equal(got, O.farthest_point_sample(m, xyz))
+
+
+# ---------------------------------------------------------------- gather / group
+def test_gather_point_and_grad(rng):
+    xyz = unit_ball(rng, 4, 300)
+    idx = rng.integers(0, 300, (4, 77)).astype(np.int32)
+    x = T(xyz).requires_grad_(True)
+    out = S.gather_point(x, T(idx))
+    assert np.array_equal(out.detach().cpu().numpy(), O.gather_point(xyz, idx))
+    go = rng.standard_normal((4, 77, 3)).astype(np.float32)
+    out.backward(T(go))
+    np.testing.assert_allclose(x.grad.cpu().numpy(), O.gather_point_grad(xyz, idx, go), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("c", [3, 5, 64])
+def test_group_point_and_grad(rng, c):
+    pts = rng.standard_normal((3, 200, c)).astype(np.float32)
+    idx = rng.integers(0, 200, (3, 40, 16)).astype(np.int32)
+    p = T(pts).requires_grad_(True)
+    out = G.group_point(p, T(idx))
+    assert np.array_equal(out.detach().cpu().numpy(), O.group_point(pts, idx))
+    go = rng.standard_normal((3, 40, 16, c)).astype(np.float32)
+    out.backward(T(go))
+    np.testing.assert_allclose(p.grad.cpu().numpy(), O.group_point_grad(pts, idx, go), rtol=1e-4, atol=1e-5)
+
+
+# ---------------------------------------------------------------- ball query
+@pytest.mark.parametrize("n,m,r,ns", [(1024, 256, 0.2, 32), (1024, 1024, 0.07, 20), (4096, 1024, 0.2, 32),
+                                      (5000, 100, 0.15, 64), (100, 7, 0.5, 16), (33, 33, 2.5, 8), (9000, 64, 0.1, 32)])
+def test_query_ball_point(rng, n, m, r, ns):
+    xyz = unit_ball(rng, 3, n)
+    q = xyz[:, rng.permutation(n)[:m]] if m <= n else unit_ball(rng, 3, m)
+    q = np.ascontiguousarray(q)
+    idx, cnt = G.query_ball_point(r, ns, T(xyz), T(q))
+    idx, cnt = idx.cpu().numpy(), cnt.cpu().numpy()
+    oi, oc = O.query_ball_point(r, ns, xyz, q)
+    assert np.array_equal(cnt, oc)
+    assert np.array_equal(idx, oi)
+    if HAVE_REF_GPU:
+        b = xyz.shape[0]
+        ri = torch.zeros((b, m, ns), dtype=torch.int32, device=dev)
+        rc = torch.zeros((b, m), dtype=torch.int32, device=dev)
+        rad = torch.full((b,), r, dtype=torch.float32, device=dev)
+        x1, x2 = T(xyz), T(q)
+        torch.cuda.synchronize()
+        R.gpu_query_ball_point(b, n, m, rad.data_ptr(), ns, x1.data_ptr(), x2.data_ptr(), ri.data_ptr(), rc.data_ptr())
+        torch.cuda.synchronize()
+        assert np.array_equal(cnt, rc.cpu().numpy())
+        assert np.array_equal(idx, ri.cpu().numpy())  # rows with cnt==0 were pre-zeroed above
+
+
+def test_query_ball_point_empty_rows_and_radii(rng):
+    xyz = unit_ball(rng, 2, 500)
+    q = (unit_ball(rng, 2, 20) + np.float32(5.0)).astype(np.float32)  # far away: zero hits
+    idx, cnt = G.query_ball_point(0.1, 8, T(xyz), T(q))
+    assert (cnt.cpu().numpy() == 0).all() and (idx.cpu().numpy() == 0).all()
+    for r in (1e-21, 0.0, -1.0):
+        idx, cnt = G.query_ball_point(r, 8, T(xyz), T(xyz[:, :20].copy()))
+        assert (cnt.cpu().numpy() == 0).all()
+    # radius tensor: only element 0 is used (tf_grouping_g.cu:25)
+    rad = T(np.array([0.3, 0.01], np.float32))
+    idx, cnt = G.query_ball_point(rad, 8, T(xyz), T(xyz[:, :20].copy()))
+    oi, oc = O.query_ball_point(np.array([0.3, 0.01], np.float32), 8, xyz, xyz[:, :20].copy())
+    assert np.array_equal(idx.cpu().numpy(), oi) and np.array_equal(cnt.cpu().numpy(), oc)
+
+
+def test_query_ball_point_boundary_radius(rng):
+    # distances that land exactly on / next to the radius: the sqrt-free test must agree with sqrtf
+    xyz = lattice(rng, 2, 800, q=10)
+    q = np.ascontiguousarray(xyz[:, :64])
+    for r in (0.1, 0.2, 0.3, float(np.float32(np.sqrt(np.float32(0.05)))), 0.5):
+        idx, cnt = G.query_ball_point(r, 16, T(xyz), T(q))
+        oi, oc = O.query_ball_point(r, 16, xyz, q)
+        assert np.array_equal(cnt.cpu().numpy(), oc) and np.array_equal(idx.cpu().numpy(), oi)
+
+
+# ---------------------------------------------------------------- kNN / 3-NN / interpolate
+@pytest.mark.parametrize("n,m,k", [(1024, 1024, 16), (256, 256, 17), (4096, 100, 16), (50, 50, 4), (300, 10, 32),
+                                   (70, 70, 64), (3000, 17, 1), (40, 5, 24)])
+def test_knn(rng, n, m, k):
+    xyz = unit_ball(rng, 2, n)
+    q = np.ascontiguousarray(xyz[:, :m]) if m <= n else unit_ball(rng, 2, m)
+    d, i = G.knn(k, T(xyz), T(q))
+    od, oi = O.knn(k, xyz, q)
+    assert np.array_equal(i.cpu().numpy(), oi)
+    assert np.array_equal(d.cpu().numpy(), od)
+    v, i2 = G.knn_point(k, T(xyz), T(q))
+    assert np.array_equal(v.cpu().numpy(), -od)
+
+
+def test_knn_ties(rng):
+    xyz = lattice(rng, 2, 500, q=5)
+    d, i = G.knn(16, T(xyz), T(xyz))
+    od, oi = O.knn(16, xyz, xyz)
+    assert np.array_equal(i.cpu().numpy(), oi) and np.array_equal(d.cpu().numpy(), od)
+
+
+@pytest.mark.parametrize("n,m", [(512, 128), (1024, 256), (4096, 1024), (10, 2), (7, 1), (100, 3), (300, 2500)])
+def test_three_nn(rng, n, m):
+    x1, x2 = unit_ball(rng, 2, n), unit_ball(rng, 2, m)
+    d, i = I.three_nn(T(x1), T(x2))
+    od, oi = O.three_nn(x1, x2)
+    assert np.array_equal(i.cpu().numpy(), oi)
+    assert np.array_equal(d.cpu().numpy(), od)  # includes +inf slots when m < 3
+
+
+@pytest.mark.parametrize("c", [1, 6, 64, 130])
+def test_three_interpolate_and_grad(rng, c):
+    n, m = 300, 64
+    x1, x2 = unit_ball(rng, 2, n), unit_ball(rng, 2, m)
+    pts = rng.standard_normal((2, m, c)).astype(np.float32)
+    d, i = I.three_nn(T(x1), T(x2))
+    w = I.three_nn_weights(d)
+    ow = O.three_nn_weights(d.cpu().numpy())
+    np.testing.assert_allclose(w.cpu().numpy(), ow, rtol=1e-6, atol=0)
+    p = T(pts).requires_grad_(True)
+    out = I.three_interpolate(p, i, w)
+    want = O.three_interpolate(pts, i.cpu().numpy(), w.cpu().numpy())
+    assert np.array_equal(out.detach().cpu().numpy(), want)  # unfused arithmetic is pinned
+    go = rng.standard_normal((2, n, c)).astype(np.float32)
+    out.backward(T(go))
+    np.testing.assert_allclose(p.grad.cpu().numpy(),
+                               O.three_interpolate_grad(pts, i.cpu().numpy(), w.cpu().numpy(), go), rtol=1e-4, atol=1e-5)
+
+
+# ---------------------------------------------------------------- NnDistance / Chamfer
+@pytest.mark.parametrize("n,m", [(1024, 1024), (256, 1024), (5, 6), (1, 1), (1, 700), (513, 511), (2049, 1025),
+                                 (8192, 100)])
+def test_nn_distance(rng, n, m):
+    b = 3
+    x1 = unit_ball(rng, b, n)
+    x2 = unit_ball(rng, b, m)
+    d1, i1, d2, i2 = [t.cpu().numpy() for t in N.nn_distance(T(x1), T(x2))]
+    o = O.nn_distance(x1, x2)
+    for got, want in zip((d1, i1, d2, i2), o):
+        assert np.array_equal(got, want)
+    if HAVE_REF_GPU:
+        a, c = T(x1), T(x2)
+        r1 = torch.empty((b, n), dtype=torch.float32, device=dev); ri1 = torch.empty((b, n), dtype=torch.int32, device=dev)
+        r2 = torch.empty((b, m), dtype=torch.float32, device=dev); ri2 = torch.empty((b, m), dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        R.gpu_nn_distance(b, n, a.data_ptr(), m, c.data_ptr(), r1.data_ptr(), ri1.data_ptr(), r2.data_ptr(), ri2.data_ptr())
+        torch.cuda.synchronize()
+        assert np.array_equal(d1, r1.cpu().numpy()) and np.array_equal(i1, ri1.cpu().numpy())
+        assert np.array_equal(d2, r2.cpu().numpy()) and np.array_equal(i2, ri2.cpu().numpy())
+
+
+def test_nn_distance_ties_and_grad(rng):
+    x1 = lattice(rng, 2, 600, q=6)
+    x2 = lattice(rng, 2, 500, q=6)
+    a = T(x1).requires_grad_(True)
+    c = T(x2).requires_grad_(True)
+    d1, i1, d2, i2 = N.nn_distance(a, c)
+    o = O.nn_distance(x1, x2)
+    assert np.array_equal(i1.cpu().numpy(), o[1]) and np.array_equal(i2.cpu().numpy(), o[3])
+    g1 = rng.standard_normal(d1.shape).astype(np.float32)
+    g2 = rng.standard_normal(d2.shape).astype(np.float32)
+    (d1 * T(g1)).sum().add((d2 * T(g2)).sum()).backward()
+    w1, w2 = O.nn_distance_grad(x1, x2, g1, o[1], g2, o[3])
+    np.testing.assert_allclose(a.grad.cpu().numpy(), w1, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(c.grad.cpu().numpy(), w2, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("b,n_gt,n_pred", [(1, 1024, 1024), (32, 1024, 1024), (5, 4096, 1024), (3, 100, 333)])
+def test_chamfer(rng, b, n_gt, n_pred):
+    gt = unit_ball(rng, b, n_gt)
+    pred = unit_ball(rng, b, n_pred)
+    radius = rng.uniform(0.5, 2.0, (b,)).astype(np.float32)
+    per = torch.empty((b, 2), dtype=torch.float32, device=dev)
+    out = LU.chamfer_hausdorff(T(pred), T(gt), T(radius), per_cloud=per).cpu().numpy()
+    o = O.chamfer(pred, gt, radius)
+    # tolerance of north_star: 1e-5 (fp32), relative
+    np.testing.assert_allclose(out[0], o["cd"], rtol=1e-5)
+    np.testing.assert_allclose(out[1], o["hd"], rtol=1e-5)
+    np.testing.assert_allclose(out[2], o["per_cd"].astype(np.float64).sum(), rtol=1e-5)
+    np.testing.assert_allclose(per.cpu().numpy()[:, 0], o["per_cd"], rtol=1e-5)
+    np.testing.assert_allclose(per.cpu().numpy()[:, 1], o["per_hd"], rtol=1e-5)
+    assert float(LU.chamfer(T(pred), T(gt))) == pytest.approx(float(O.chamfer(pred, gt)["cd"]), rel=1e-5)
+    # deterministic: bitwise repeatable
+    out2 = LU.chamfer_hausdorff(T(pred), T(gt), T(radius)).cpu().numpy()
+    assert np.array_equal(out, out2)
+
+
+# ---------------------------------------------------------------- set abstraction
+@pytest.mark.parametrize("c_pts,mlp,ns,layout", [(0, [32, 32, 64], 32, 0), (64, [64, 64, 128], 32, 0), (5, [16], 16, 1),
+                                                 (7, [24, 9], 24, 0), (0, [8, 8], 200, 0)])
+def test_sa_mlp_fp32(rng, c_pts, mlp, ns, layout):
+    b, n, m = 2, 600, 50
+    xyz = unit_ball(rng, b, n)
+    pts = rng.standard_normal((b, n, c_pts)).astype(np.float32) if c_pts else None
+    new_xyz = O.gather_point(xyz, O.farthest_point_sample(m, xyz))
+    idx, _ = O.query_ball_point(0.4, ns, xyz, new_xyz)
+    widths = [3 + c_pts] + mlp
+    ws = [(rng.standard_normal((widths[i], widths[i + 1])) / np.sqrt(widths[i])).astype(np.float32) for i in range(len(mlp))]
+    bs = [rng.standard_normal((widths[i + 1],)).astype(np.float32) * np.float32(0.1) for i in range(len(mlp))]
+    want = O.sa_mlp(xyz, pts, new_xyz, idx, ws, bs, layout)
+    got = PU.grouped_mlp_max(T(xyz), None if pts is None else T(pts), T(new_xyz), T(idx),
+                             [(T(w), T(bb)) for w, bb in zip(ws, bs)], layout=layout).cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5)
+
+
+def test_pointnet_sa_module_end_to_end(rng):
+    b, n, npoint, ns = 2, 1024, 128, 32
+    xyz = unit_ball(rng, b, n)
+    widths = [3, 32, 32, 64]
+    ws = [(rng.standard_normal((widths[i], widths[i + 1])) / np.sqrt(widths[i])).astype(np.float32) for i in range(3)]
+    bs = [np.zeros((widths[i + 1],), np.float32) for i in range(3)]
+    new_xyz, new_points, idx = PU.pointnet_sa_module(T(xyz), None, npoint, 0.2, ns, [(T(w), T(bb)) for w, bb in zip(ws, bs)])
+    o_new_xyz, o_new_points, o_idx, _ = O.sample_and_group(npoint, 0.2, ns, xyz, None)
+    assert np.array_equal(new_xyz.cpu().numpy(), o_new_xyz)
+    assert np.array_equal(idx.cpu().numpy(), o_idx)
+    want = O.sa_mlp(xyz, None, o_new_xyz, o_idx, ws, bs, 0)
+    np.testing.assert_allclose(new_points.cpu().numpy(), want, rtol=1e-5, atol=1e-5)
+    # the unfused reference-shaped path gives the same grouped tensor
+    _, grouped, _, _ = PU.sample_and_group(npoint, 0.2, ns, T(xyz), None)
+    assert np.array_equal(grouped.cpu().numpy(), o_new_points)
+
+
+def test_pointnet_fp_module(rng):
+    b, n, m, c = 2, 512, 128, 64
+    x1, x2 = unit_ball(rng, b, n), unit_ball(rng, b, m)
+    p2 = rng.standard_normal((b, m, c)).astype(np.float32)
+    got = PU.pointnet_fp_module(T(x1), T(x2), None, T(p2)).cpu().numpy()
+    d, i = O.three_nn(x1, x2)
+    want = O.three_interpolate(p2, i, O.three_nn_weights(d))
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-6)  # north_star: interpolated features within 1e-5
+
+
+def test_misc_ops(rng):
+    dm = rng.standard_normal((2, 9, 50)).astype(np.float32)
+    oi, od = G.select_top_k(5, T(dm))
+    wi, wd = O.selection_sort(dm, 5)
+    assert np.array_equal(oi.cpu().numpy()[:, :, :5], wi[:, :, :5]) and np.array_equal(od.cpu().numpy()[:, :, :5], wd[:, :, :5])
+    p = rng.uniform(0.1, 1.0, (3, 40)).astype(np.float32)
+    r = rng.uniform(0, 1, (3, 200)).astype(np.float32)
+    got = S.prob_sample(T(p), T(r)).cpu().numpy()
+    cum = np.cumsum(p.astype(np.float64), axis=1)
+    want = np.array([[min(int(np.searchsorted(cum[i], np.float32(r[i, j]) * np.float32(cum[i, -1]), side="left")), 39)
+                      for j in range(200)] for i in range(3)])
+    assert (np.abs(got - want) <= 1).all() and (got == want).mean() > 0.98
+
+
+def test_invalid_arguments_raise(rng):
+    xyz = T(unit_ball(rng, 1, 10))
+    with pytest.raises(ValueError):
+        S.farthest_point_sample(0, xyz)
+    with pytest.raises(ValueError):
+        G.query_ball_point(0.1, 0, xyz, xyz)
+    with pytest.raises(ValueError):
+        G.knn(11, xyz, xyz)
+    with pytest.raises(ValueError):
+        N.nn_distance(xyz, T(np.zeros((2, 4, 3), np.float32)))
+    with pytest.raises(RuntimeError):
+        S.farthest_point_sample(4, xyz.cpu())

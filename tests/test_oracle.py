@@ -1,0 +1,187 @@
+"""CPU tests of the oracle (oracle/dispu_oracle.c): pinned against the committed golden vectors
+that the REAL reference code produced (tests/golden/ref_cpu.npz from the reference host loops,
+tests/golden/ref_gpu.npz from the reference CUDA kernels run on a B200), against the live
+oracle/_ref libraries when they are present, and against independent numpy restatements."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import lattice, unit_ball
+from oracle import oracle as O
+from oracle import ref as R
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def gc():
+    return np.load(os.path.join(GOLD, "ref_cpu.npz"))
+
+
+@pytest.fixture(scope="module")
+def gg():
+    p = os.path.join(GOLD, "ref_gpu.npz")
+    if not os.path.exists(p):
+        pytest.skip("ref_gpu.npz not generated yet")
+    return np.load(p)
+
+
+# ---- golden vectors from the reference host loops -------------------------------------------
+@pytest.mark.parametrize("tag", ["ball", "lat"])
+def test_golden_cpu_nn_distance(gc, tag):
+    a, b = gc[f"{tag}_a"], gc[f"{tag}_b"]
+    d1, i1, d2, i2 = O.nn_distance(a, b, mode=O.CPU)
+    assert np.array_equal(d1, gc[f"{tag}_nn_d1"]) and np.array_equal(i1, gc[f"{tag}_nn_i1"])
+    assert np.array_equal(d2, gc[f"{tag}_nn_d2"]) and np.array_equal(i2, gc[f"{tag}_nn_i2"])
+
+
+@pytest.mark.parametrize("tag", ["ball", "lat"])
+def test_golden_cpu_three_nn(gc, tag):
+    d, i = O.three_nn(gc[f"{tag}_a"], gc[f"{tag}_b"])
+    assert np.array_equal(d, gc[f"{tag}_3nn_d"]) and np.array_equal(i, gc[f"{tag}_3nn_i"])
+
+
+def test_golden_cpu_interpolate_and_weights(gc):
+    w = O.three_nn_weights(gc["ball_3nn_d"])
+    np.testing.assert_allclose(w, gc["ball_3nn_w"], rtol=1e-6)
+    out = O.three_interpolate(gc["feat_b"], gc["ball_3nn_i"], gc["ball_3nn_w"])
+    assert np.array_equal(out, gc["ball_interp"])
+
+
+@pytest.mark.parametrize("tag", ["ball", "lat"])
+def test_golden_cpu_query_ball_point(gc, tag):
+    idx, cnt = O.query_ball_point(0.3, 16, gc[f"{tag}_a"], gc[f"{tag}_b"], mode=O.CPU, fill_empty=False)
+    assert np.array_equal(idx, gc[f"{tag}_qbp_r0.3_ns16"])  # rows without a hit keep the -1 prefill in both
+
+
+def test_golden_cpu_group_point(gc):
+    assert np.array_equal(O.group_point(gc["feat_a"], gc["ball_group_idx"]), gc["ball_group"])
+
+
+def test_golden_cpu_knn_nanoflann(gc):
+    d, i = O.knn(16, gc["ball_a"], gc["ball_a"])
+    assert np.array_equal(i, gc["ball_knn16"])  # distinct distances: identical order, self at slot 0
+    assert (i[:, :, 0] == np.arange(600)[None]).all()
+    # lattice: equal distances are ordered by KD-tree traversal in nanoflann -> compare distances
+    a = gc["lat_a"]
+    d, i = O.knn(16, a, a)
+    gi = gc["lat_knn16"]
+    gd = ((a[:, :, None, :] - np.take_along_axis(a[:, None], gi[..., None].astype(np.int64), 2)) ** 2)
+    gd = (gd[..., 0] + gd[..., 1]) + gd[..., 2]
+    assert np.array_equal(d, gd.astype(np.float32))
+
+
+# ---- golden vectors from the reference CUDA kernels (generated on a B200) ---------------------
+def test_golden_gpu_fps(gc, gg):
+    assert np.array_equal(O.farthest_point_sample(150, gc["ball_a"]), gg["ball_fps150"])
+    assert np.array_equal(O.farthest_point_sample(200, gc["lat_a"]), gg["lat_fps200"])
+    assert np.array_equal(O.farthest_point_sample(64, gc["big"]), gg["big_fps64"])
+    assert np.array_equal(O.farthest_point_sample(200, gc["ball_b"]), gg["ballb_fps200"])
+
+
+@pytest.mark.parametrize("tag", ["ball", "lat"])
+def test_golden_gpu_query_ball_and_nn(gc, gg, tag):
+    a, q = gc[f"{tag}_a"], gc[f"{tag}_b"]
+    for r, ns in ((0.3, 16), (0.12, 8)):
+        idx, cnt = O.query_ball_point(r, ns, a, q, mode=O.GPU, fill_empty=True)
+        assert np.array_equal(cnt, gg[f"{tag}_qbp_r{r}_ns{ns}_cnt"])
+        assert np.array_equal(idx, gg[f"{tag}_qbp_r{r}_ns{ns}_idx"])  # generator pre-zeroed empty rows
+    d1, i1, d2, i2 = O.nn_distance(a, q, mode=O.GPU)
+    assert np.array_equal(d1, gg[f"{tag}_nn_d1"]) and np.array_equal(i1, gg[f"{tag}_nn_i1"])
+    assert np.array_equal(d2, gg[f"{tag}_nn_d2"]) and np.array_equal(i2, gg[f"{tag}_nn_i2"])
+
+
+# ---- live reference host loops (present where oracle/build_ref.sh ran) -----------------------
+needs_ref = pytest.mark.skipif(not (R.available("cpu") and R.available("knn")), reason="oracle/_ref not built")
+
+
+@needs_ref
+@pytest.mark.parametrize("n,m", [(1, 1), (5, 6), (257, 33), (64, 700)])
+def test_live_ref_host_loops(rng, n, m):
+    a, b = unit_ball(rng, 2, n), unit_ball(rng, 2, m)
+    for got, want in zip(O.nn_distance(a, b, mode=O.CPU), R.cpu_nn_distance(a, b)):
+        assert np.array_equal(got, want)
+    for got, want in zip(O.three_nn(a, b), R.cpu_three_nn(a, b)):
+        assert np.array_equal(got, want)
+    idx, _ = O.query_ball_point(0.4, 8, a, b, mode=O.CPU, fill_empty=False)
+    assert np.array_equal(idx, R.cpu_query_ball_point(0.4, 8, a, b))
+    feat = rng.standard_normal((2, m, 7)).astype(np.float32)
+    d, i = O.three_nn(a, b)
+    w = O.three_nn_weights(d) if m >= 3 else np.full((2, n, 3), 1 / 3, np.float32)
+    assert np.array_equal(O.three_interpolate(feat, i, w), R.cpu_three_interpolate(feat, i, w))
+    go = rng.standard_normal((2, n, 7)).astype(np.float32)
+    assert np.array_equal(O.three_interpolate_grad(feat, i, w, go), R.cpu_three_interpolate_grad(feat, i, w, go))
+    if n >= 16:
+        assert np.array_equal(O.knn(16, a, a)[1], R.cpu_knn_batch(a, a, 16).astype(np.int32))
+
+
+# ---- independent numpy restatements -----------------------------------------------------------
+def fps_numpy(xyz, m):
+    """A.1 of SURVEY.md evaluated with numpy float32 ops (FMA emulated in float64 then rounded once)."""
+    b, n, _ = xyz.shape
+    out = np.zeros((b, m), np.int32)
+    for i in range(b):
+        p = xyz[i].astype(np.float32)
+        mind = np.full(n, np.float32(1e38))
+        last = 0
+        lane = np.arange(n) & 511
+        for j in range(1, m):
+            dx, dy, dz = (p[:, c] - p[last, c] for c in range(3))
+            t = (dy * dy).astype(np.float32)
+            t = (dx.astype(np.float64) * dx.astype(np.float64) + t.astype(np.float64)).astype(np.float32)
+            d = (dz.astype(np.float64) * dz.astype(np.float64) + t.astype(np.float64)).astype(np.float32)
+            mind = np.minimum(d, mind)
+            cand = np.flatnonzero(mind == mind.max())
+            last = int(cand[np.lexsort((cand, lane[cand]))[0]])
+            out[i, j] = last
+    return out
+
+
+@pytest.mark.parametrize("n,m,kind", [(300, 40, "ball"), (1300, 50, "lat"), (700, 30, "lat"), (20, 30, "ball")])
+def test_fps_against_numpy_restatement(rng, n, m, kind):
+    xyz = unit_ball(rng, 2, n) if kind == "ball" else lattice(rng, 2, n, q=5)
+    assert np.array_equal(O.farthest_point_sample(m, xyz), fps_numpy(xyz, m))
+
+
+def test_nn_distance_matches_tf_spec(rng):
+    """tf_ops/nn_distance/tf_nndistance_cpu.py:4-25: tile/sub/square/reduce_min/argmin."""
+    a, b = unit_ball(rng, 2, 40), unit_ball(rng, 2, 55)
+    diff = a[:, :, None, :] - b[:, None, :, :]
+    d = (diff ** 2).sum(-1)
+    d1, i1, d2, i2 = O.nn_distance(a, b, mode=O.CPU)
+    np.testing.assert_allclose(d1, d.min(2), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(d2, d.min(1), rtol=1e-5, atol=1e-7)
+    assert np.array_equal(i1, d.argmin(2)) and np.array_equal(i2, d.argmin(1))
+
+
+def test_chamfer_definition(rng):
+    pred, gt = unit_ball(rng, 3, 64), unit_ball(rng, 3, 128)
+    radius = np.array([1.0, 2.0, 0.5], np.float32)
+    o = O.chamfer(pred, gt, radius)
+    df, _, db, _ = O.nn_distance(gt, pred)
+    cd = ((df.mean(1) + db.mean(1)) / radius).mean()
+    hd = ((df.max(1) + db.max(1)) / radius).max()
+    np.testing.assert_allclose(o["cd"], cd, rtol=1e-6)
+    np.testing.assert_allclose(o["hd"], hd, rtol=1e-6)
+
+
+def test_sa_mlp_against_numpy(rng):
+    b, n, m, ns, c = 2, 200, 20, 16, 6
+    xyz = unit_ball(rng, b, n)
+    pts = rng.standard_normal((b, n, c)).astype(np.float32)
+    new_xyz, new_points, idx, _ = O.sample_and_group(m, 0.5, ns, xyz, pts)
+    ws = [rng.standard_normal((3 + c, 12)).astype(np.float32), rng.standard_normal((12, 7)).astype(np.float32)]
+    bs = [rng.standard_normal(12).astype(np.float32), None]
+    x = new_points.astype(np.float64)
+    for w, bb in zip(ws, bs):
+        x = np.maximum(x @ w.astype(np.float64) + (0 if bb is None else bb), 0)
+    np.testing.assert_allclose(O.sa_mlp(xyz, pts, new_xyz, idx, ws, bs, 0), x.max(2), rtol=1e-4, atol=1e-5)
+
+
+def test_selection_sort_known_answer():
+    """tf_ops/grouping/selection_sort.cpp:65-94: k=3 of a 2x2x4 descending ramp -> idx 3 2 1 ..."""
+    dist = np.arange(16, 0, -1, dtype=np.float32).reshape(2, 2, 4)
+    outi, out = O.selection_sort(dist, 3)
+    assert (outi[..., :3] == np.array([3, 2, 1])).all()
+    assert np.array_equal(out[..., :3], np.sort(dist, -1)[..., :3])
