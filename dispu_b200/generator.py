@@ -1,0 +1,197 @@
+"""Torch restatement of the LIVE Dis-PU generator forward (DisPU/generator.py:31-88) used only to
+drive the hot path at the shapes of BASELINE.json configs 2 and 4 (the TF graph itself cannot
+run here).  It is a caller of the path, not the product: the sampling / grouping / Chamfer ops
+it calls are the sm_100a kernels of this package; the stock dense layers (1x1 convs, the
+non-local attention) are plain torch matmuls exactly as the reference leaves them to stock TF.
+
+Shape trace and literals follow Common/ops.py:
+  feature_extraction_GCN ops.py:1437-1486, dense_conv :1897-1915, get_edge_feature :1856-1877,
+  duplicate_up :1152-1199, gen_grid :60-76, coordinate_regressor :1089-1110,
+  PointShuffle2 :1012-1087, grouping :154-179, weight_net_hidden :181-191,
+  PointNonLocalCell :302-346; conv = tf_util.conv2d/conv1d (Common/tf_util.py:52-185): Xavier
+  weights, zero bias, ReLU unless stated, no BN (use_bn=False, generator.py:33) except the
+  weight net (bn=True hard-coded, ops.py:187) which runs with its initial moving statistics.
+
+`ops` is the backend for the path's own operators:
+    ops.knn3d(k, support (b,n,3), query (b,m,3)) -> idx (b,m,k)       Common/ops.py:110-118
+    ops.group(feature (b,n,c), idx (b,m,k))      -> (b,m,k,c)         tf.gather_nd, ops.py:169,174
+    ops.feature_knn(k, feat (b,n,c))             -> idx (b,n,k)       tf_grouping.py:95-114
+The default backend is the CUDA one below; bench.py supplies a CPU backend for the reference arm.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import tf_grouping
+
+BN_EPS = 1e-3  # tf.contrib.layers.batch_norm default epsilon (Common/tf_util.py:527)
+
+
+class DispuOps:
+    """The path's operators on the B200 kernels."""
+
+    def knn3d(self, k, support, query):
+        return tf_grouping.knn(k, support, query)[1]
+
+    def group(self, feature, idx):
+        return tf_grouping.group_point(feature, idx)
+
+    def feature_knn(self, k, feat):
+        # knn_point_2 (tf_grouping.py:95-114): D = |q|^2 - 2 q.p + |p|^2 ; top_k(-D, k)
+        r = (feat * feat).sum(dim=2, keepdim=True)
+        d = r - 2.0 * torch.bmm(feat, feat.transpose(1, 2)) + r.transpose(1, 2)
+        return torch.topk(-d, k, dim=2, sorted=True)[1].to(torch.int32)
+
+
+def _xavier(gen, cin, cout, device, fan_in=None, fan_out=None):
+    fi = cin if fan_in is None else fan_in
+    fo = cout if fan_out is None else fan_out
+    lim = math.sqrt(6.0 / (fi + fo))
+    w = (torch.rand((cin, cout), generator=gen, dtype=torch.float32) * 2 - 1) * lim
+    return w.to(device), torch.zeros((cout,), dtype=torch.float32, device=device)
+
+
+class Generator:
+    """coarse, fine = G(inputs (b,n,3)); up_ratio 4: (b,4n,3) each."""
+
+    def __init__(self, up_ratio=4, device="cuda", seed=7, ops=None):
+        self.up_ratio = up_ratio
+        self.device = torch.device(device)
+        self.ops = ops if ops is not None else DispuOps()
+        g = torch.Generator().manual_seed(seed)
+        d = self.device
+        P = {}
+        P["layer0"] = _xavier(g, 3, 24, d)
+        c_in = 24
+        for blk in range(1, 5):
+            if blk > 1:
+                P[f"layer{blk}_prep"] = _xavier(g, 120 * (blk - 1), 48, d)
+                c_in = 48
+            P[f"layer{blk}_l0"] = _xavier(g, 2 * c_in, 24, d)
+            P[f"layer{blk}_l1"] = _xavier(g, 24 + c_in, 24, d)
+            P[f"layer{blk}_l2"] = _xavier(g, 48 + c_in, 24, d)
+        P["up_conv1"] = _xavier(g, 482, 256, d)
+        P["up_conv2"] = _xavier(g, 256, 128, d)
+        for name, cin in (("coarse", 128), ("fine", 256)):
+            P[f"{name}_fc0"] = _xavier(g, cin, 256, d)
+            P[f"{name}_fc1"] = _xavier(g, 256, 64, d)
+            P[f"{name}_fc2"] = _xavier(g, 64, 3, d)
+        P["nl_kv"] = _xavier(g, 128, 128, d)
+        P["nl_query"] = _xavier(g, 128, 64, d)
+        P["nl_back"] = _xavier(g, 64, 256, d)
+        P["skip"] = _xavier(g, 134, 256, d)
+        P["conv0"] = _xavier(g, 134, 128, d)
+        P["conv1"] = _xavier(g, 128, 128, d)
+        P["wconv0"] = _xavier(g, 3, 16, d)
+        # after_conv kernel (1,128,16,256): rows ordered (c, s) to match the [B,N,C,S] operand
+        P["after_conv"] = _xavier(g, 128 * 16, 256, d, fan_in=128 * 16, fan_out=128 * 256)
+        P["aggregation"] = _xavier(g, 256, 256, d)
+        self.P = P
+        # gen_grid(4): 2x2 mesh of linspace(-0.2,0.2,2), rows = (x,y) pairs in meshgrid order
+        sq = int(math.sqrt(up_ratio)) + 1
+        for i in range(sq, 0, -1):
+            if up_ratio % i == 0:
+                num_x, num_y = i, up_ratio // i
+                break
+        gx = torch.linspace(-0.2, 0.2, num_x)
+        gy = torch.linspace(-0.2, 0.2, num_y)
+        yy, xx = torch.meshgrid(gy, gx, indexing="ij")
+        self.grid = torch.stack([xx, yy], dim=-1).reshape(-1, 2).to(d)
+
+    # -- layers ---------------------------------------------------------------------------------
+    def _fc(self, x, name, act=True):
+        w, b = self.P[name]
+        y = torch.matmul(x, w) + b
+        return torch.relu(y) if act else y
+
+    def _dense_conv(self, feature, blk, k=16):
+        """ops.py:1897-1915 on (b,n,c) -> (b,n,72+c)."""
+        idx = self.ops.feature_knn(k + 1, feature)[:, :, 1:].contiguous()  # drop self, ops.py:1867-1868
+        neigh = self.ops.group(feature, idx)  # (b,n,k,c)
+        central = feature.unsqueeze(2).expand(-1, -1, k, -1)
+        y = torch.cat([central, neigh - central], dim=-1)
+        y = torch.cat([self._fc(y, f"layer{blk}_l0"), central], dim=-1)
+        y = torch.cat([self._fc(y, f"layer{blk}_l1"), y], dim=-1)
+        y = torch.cat([self._fc(y, f"layer{blk}_l2", act=False), y], dim=-1)
+        return y.max(dim=2)[0]
+
+    def feature_extraction(self, inputs):
+        l0 = self._fc(inputs, "layer0", act=False)
+        out = torch.cat([self._dense_conv(l0, 1), l0], dim=-1)  # 120
+        for blk in (2, 3, 4):
+            prep = self._fc(out, f"layer{blk}_prep")
+            out = torch.cat([self._dense_conv(prep, blk), out], dim=-1)
+        return out  # (b,n,480)
+
+    def duplicate_up(self, feat):
+        b, n, c = feat.shape
+        r = self.up_ratio
+        net = feat.repeat(1, r, 1)  # copy j occupies rows j*n..(j+1)*n-1
+        grid = self.grid.view(1, r, 1, 2).expand(b, r, n, 2).reshape(b, r * n, 2)
+        net = torch.cat([net, grid], dim=-1)
+        net = self._fc(net, "up_conv1")
+        return self._fc(net, "up_conv2")
+
+    def regressor(self, feat, name, is_off=False):
+        x = self._fc(self._fc(feat, f"{name}_fc0"), f"{name}_fc1")
+        out = self._fc(x, f"{name}_fc2", act=False)
+        if is_off:
+            out = torch.sigmoid(out) * 1.0 - 0.5
+        return out
+
+    def point_shuffle(self, xyz, feature, nsample=16):
+        """PointShuffle2 ops.py:1012-1087 with mlp=[128,128,256], kNN grouping, NL + Local."""
+        b, m, c = feature.shape
+        idx = self.ops.knn3d(nsample, xyz, xyz)  # ops.py:165 (nanoflann in the reference)
+        grouped_xyz_raw = self.ops.group(xyz, idx)
+        grouped_feature = torch.cat([grouped_xyz_raw, self.ops.group(feature, idx)], dim=-1)  # 131
+        grouped_xyz = grouped_xyz_raw - xyz.unsqueeze(2)
+        grouped_feat = torch.cat([grouped_xyz, grouped_feature], dim=-1)  # 134
+        # non-local cell
+        kv = self._fc(feature, "nl_kv", act=False)
+        key, val = kv[..., :64], kv[..., 64:]
+        q = self._fc(feature, "nl_query", act=False)
+        att = torch.softmax(torch.bmm(q, key.transpose(1, 2)) / math.sqrt(64.0), dim=-1)
+        nonlocal_pt = self._fc(torch.bmm(att, val), "nl_back")
+        # skip
+        skip = self._fc(grouped_feat.max(dim=2)[0], "skip")
+        # local cell
+        gf = self._fc(self._fc(grouped_feat, "conv0"), "conv1")  # (b,m,s,128)
+        w, bias = self.P["wconv0"]
+        wn = torch.relu((torch.matmul(grouped_xyz, w) + bias) / math.sqrt(1.0 + BN_EPS))  # (b,m,s,16)
+        gf = torch.matmul(gf.transpose(2, 3), wn)  # (b,m,128,16)
+        gf = self._fc(gf.reshape(b, m, 128 * nsample), "after_conv")
+        gf = gf + skip + nonlocal_pt
+        return self._fc(gf, "aggregation")
+
+    def forward(self, inputs):
+        feat = self.feature_extraction(inputs)
+        coarse_feat = self.duplicate_up(feat)
+        coarse = self.regressor(coarse_feat, "coarse")
+        fine_feat = self.point_shuffle(coarse, coarse_feat)
+        fine = coarse + self.regressor(fine_feat, "fine", is_off=True)
+        return coarse, fine
+
+    __call__ = forward
+
+    @staticmethod
+    def flops_per_cloud(n_in=256, up_ratio=4, k=16):
+        """Dense-math FLOPs of one forward per cloud (2*MACs), same accounting as SURVEY.md §8d."""
+        n, m = n_in, n_in * up_ratio
+        f = 2 * n * 3 * 24
+        for blk in range(1, 5):
+            c = 24 if blk == 1 else 48
+            if blk > 1:
+                f += 2 * n * 120 * (blk - 1) * 48
+            f += 2 * n * n * c  # feature kNN matmul
+            f += 2 * n * k * (2 * c * 24 + (24 + c) * 24 + (48 + c) * 24)
+        f += 2 * m * (482 * 256 + 256 * 128)
+        f += 2 * m * (128 * 256 + 256 * 64 + 64 * 3)
+        f += 2 * m * (128 * 128 + 128 * 64 + 64 * 256) + 2 * 2 * m * m * 64
+        f += 2 * m * 134 * 256
+        f += 2 * m * k * (134 * 128 + 128 * 128 + 3 * 16) + 2 * m * 128 * k * k
+        f += 2 * m * 2048 * 256 + 2 * m * 256 * 256
+        f += 2 * m * (256 * 256 + 256 * 64 + 64 * 3)
+        return f
