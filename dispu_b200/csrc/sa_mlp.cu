@@ -11,19 +11,11 @@
 // layer is a register-tiled FMA chain over C_in in ascending order, and the pool is a column max
 // over the CTA's rows.  The tensor-core path (DISPU_MLP_TF32X3, tcgen05) lives in
 // sa_mlp_tc.cu.
-#include "common.cuh"
+#include "sa_mlp.cuh"
 
 namespace dispu {
 
 constexpr int kMlpThreads = 128;
-constexpr int kMlpMaxLayers = 4;
-
-struct MlpParams {
-    int n_layers;
-    int widths[kMlpMaxLayers + 1];
-    const float *w[kMlpMaxLayers];
-    const float *bias[kMlpMaxLayers];
-};
 
 // rows of a CTA pass: kMlpThreads; groups per pass G = kMlpThreads / ns when ns divides 128,
 // else one group per pass processed in chunks of 128 rows.
@@ -115,10 +107,6 @@ sa_mlp_fp32_kernel(int n, int m, int ns, int c_pts, int layout, const float *__r
     (void)c_in;
 }
 
-int sa_mlp_tc_launch(int b, int n, int m, int ns, int c_pts, int layout, const float *xyz, const float *points,
-                     const float *new_xyz, const int *idx, const MlpParams &prm, float *out, cudaStream_t stream,
-                     bool *handled);
-
 }  // namespace dispu
 
 using namespace dispu;
@@ -133,7 +121,8 @@ extern "C" int dispu_sa_mlp(int b, int n, int m, int nsample, int c_pts, int lay
     DISPU_REQUIRE(n_layers >= 1 && n_layers <= kMlpMaxLayers, DISPU_EINVAL);
     DISPU_REQUIRE(widths && weights && biases, DISPU_ENULL);
     DISPU_REQUIRE(widths[0] == 3 + c_pts, DISPU_EINVAL);
-    DISPU_REQUIRE(precision == DISPU_MLP_FP32 || precision == DISPU_MLP_TF32X3, DISPU_EINVAL);
+    DISPU_REQUIRE(precision == DISPU_MLP_FP32 || precision == DISPU_MLP_TF32X3 || precision == DISPU_MLP_TF32,
+                  DISPU_EINVAL);
     if (b == 0 || m == 0) return DISPU_OK;
     DISPU_REQUIRE(xyz && new_xyz && idx && out && (c_pts == 0 || points), DISPU_ENULL);
     MlpParams prm;
@@ -149,9 +138,10 @@ extern "C" int dispu_sa_mlp(int b, int n, int m, int nsample, int c_pts, int lay
         prm.w[l] = weights[l];
         prm.bias[l] = biases[l];
     }
-    if (precision == DISPU_MLP_TF32X3) {
+    if (precision != DISPU_MLP_FP32) {
         bool handled = false;
-        int rc = sa_mlp_tc_launch(b, n, m, nsample, c_pts, layout, xyz, points, new_xyz, idx, prm, out, stream, &handled);
+        int rc = sa_mlp_tc_launch(b, n, m, nsample, c_pts, layout, xyz, points, new_xyz, idx, prm, out, precision, stream,
+                                  &handled);
         if (handled) return rc;
         return DISPU_EUNSUPPORTED;  // shape outside the tensor-core kernel's instantiations
     }

@@ -17,7 +17,7 @@ from .tf_grouping import group_point, knn_point, query_ball_point
 from .tf_interpolate import three_interpolate, three_nn, three_nn_weights
 from .tf_sampling import farthest_point_sample, gather_point
 
-MLP_FP32, MLP_TF32X3 = 0, 1
+MLP_FP32, MLP_TF32X3, MLP_TF32 = 0, 1, 2  # exact fp32 | tcgen05 3xTF32 (fp32-level) | tcgen05 single-pass TF32
 
 
 def sample_and_group(npoint, radius, nsample, xyz, points, knn=False, use_xyz=True):

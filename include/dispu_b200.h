@@ -154,6 +154,7 @@ int dispu_chamfer(int b, int n_gt, const float *gt, int n_pred, const float *pre
  *   with 3xTF32 error-compensated splits (fp32-level accuracy). */
 #define DISPU_MLP_FP32 0
 #define DISPU_MLP_TF32X3 1
+#define DISPU_MLP_TF32 2 /* single-pass TF32 tensor cores: ~1e-3 relative, NOT fp32-level; opt-in only */
 int dispu_sa_mlp(int b, int n, int m, int nsample, int c_pts, int layout, const float *xyz, const float *points,
                  const float *new_xyz, const int *idx, int n_layers, const int *widths_host,
                  const float *const *weights_host_array, const float *const *biases_host_array, float *out,

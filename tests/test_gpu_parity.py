@@ -336,3 +336,71 @@ def test_invalid_arguments_raise(rng):
         N.nn_distance(xyz, T(np.zeros((2, 4, 3), np.float32)))
     with pytest.raises(RuntimeError):
         S.farthest_point_sample(4, xyz.cpu())
+
+
+# ---------------------------------------------------------------- tensor-core (tcgen05) path
+def _tc_selftest(K, N, x3, rng):
+    import ctypes
+    from dispu_b200 import _lib
+    l = _lib.lib()
+    fn = l.dispu__tc_gemm_selftest
+    fn.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    A = rng.standard_normal((128, K)).astype(np.float32)
+    W = rng.standard_normal((K, N)).astype(np.float32)
+    a, w = T(A), T(W)
+    d = torch.zeros((128, N), dtype=torch.float32, device=dev)
+    rc = fn(K, N, a.data_ptr(), w.data_ptr(), d.data_ptr(), int(x3), None)
+    assert rc == 0, rc
+    torch.cuda.synchronize()
+    return d.cpu().numpy(), A.astype(np.float64) @ W.astype(np.float64)
+
+
+@pytest.mark.parametrize("K,N", [(8, 16), (8, 32), (32, 32), (32, 64), (72, 64), (64, 128), (72, 128), (64, 256)])
+def test_tc_gemm_selftest(rng, K, N):
+    got, want = _tc_selftest(K, N, True, rng)
+    scale = np.abs(want).max()
+    assert np.abs(got - want).max() <= 2e-6 * scale * np.sqrt(K), "3xTF32 should be fp32-level"
+    got1, want1 = _tc_selftest(K, N, False, rng)
+    assert np.abs(got1 - want1).max() <= 3e-3 * np.abs(want1).max()  # single-pass TF32: ~2^-11 per operand
+
+
+@pytest.mark.parametrize("c_pts,mlp,ns,layout", [(0, [32, 32, 64], 32, 0), (64, [64, 64, 128], 32, 0), (5, [16], 16, 1),
+                                                 (64, [64, 64], 16, 0), (0, [16, 32], 8, 0), (21, [48, 16, 32], 16, 1)])
+@pytest.mark.parametrize("precision,rtol", [(PU.MLP_TF32X3, 1e-5), (PU.MLP_TF32, 1e-2)])
+def test_sa_mlp_tensor_core(rng, c_pts, mlp, ns, layout, precision, rtol):
+    b, n, m = 3, 700, 77  # 77*ns rows per cloud: tiles straddle clouds and the last tile is partial
+    xyz = unit_ball(rng, b, n)
+    pts = rng.standard_normal((b, n, c_pts)).astype(np.float32) if c_pts else None
+    new_xyz = O.gather_point(xyz, O.farthest_point_sample(m, xyz))
+    idx, _ = O.query_ball_point(0.4, ns, xyz, new_xyz)
+    widths = [3 + c_pts] + mlp
+    ws = [(rng.standard_normal((widths[i], widths[i + 1])) / np.sqrt(widths[i])).astype(np.float32) for i in range(len(mlp))]
+    bs = [rng.standard_normal((widths[i + 1],)).astype(np.float32) * np.float32(0.1) for i in range(len(mlp))]
+    want = O.sa_mlp(xyz, pts, new_xyz, idx, ws, bs, layout)
+    got = PU.grouped_mlp_max(T(xyz), None if pts is None else T(pts), T(new_xyz), T(idx),
+                             [(T(w), T(bb)) for w, bb in zip(ws, bs)], layout=layout, precision=precision).cpu().numpy()
+    tol = rtol * max(1.0, float(np.abs(want).max()))
+    np.testing.assert_allclose(got, want, rtol=rtol, atol=tol)
+
+
+def test_sa_mlp_tc_c3_shapes(rng):
+    """BASELINE.json config 3 layer shapes (reduced batch): ns=32, [3->32->32->64] then [67->64->64->128]."""
+    b, n = 4, 4096
+    xyz = unit_ball(rng, b, n)
+    x = T(xyz)
+
+    def layers(widths):
+        return [((rng.standard_normal((widths[i], widths[i + 1])) / np.sqrt(widths[i])).astype(np.float32),
+                 np.zeros((widths[i + 1],), np.float32)) for i in range(len(widths) - 1)]
+    l1 = layers([3, 32, 32, 64])
+    new_xyz, f1, idx1 = PU.pointnet_sa_module(x, None, 1024, 0.2, 32, [(T(w), T(c)) for w, c in l1], precision=PU.MLP_TF32X3)
+    o_new, _, o_idx, _ = O.sample_and_group(1024, 0.2, 32, xyz, None)
+    assert np.array_equal(idx1.cpu().numpy(), o_idx)
+    want1 = O.sa_mlp(xyz, None, o_new, o_idx, [w for w, _ in l1], [c for _, c in l1], 0)
+    np.testing.assert_allclose(f1.cpu().numpy(), want1, rtol=1e-5, atol=1e-5)
+    l2 = layers([67, 64, 64, 128])
+    new_xyz2, f2, idx2 = PU.pointnet_sa_module(new_xyz, f1, 512, 0.4, 32, [(T(w), T(c)) for w, c in l2], precision=PU.MLP_TF32X3)
+    o_new2, _, o_idx2, _ = O.sample_and_group(512, 0.4, 32, o_new, want1)
+    assert np.array_equal(idx2.cpu().numpy(), o_idx2)
+    want2 = O.sa_mlp(o_new, f1.cpu().numpy(), o_new2, o_idx2, [w for w, _ in l2], [c for _, c in l2], 0)
+    np.testing.assert_allclose(f2.cpu().numpy(), want2, rtol=2e-5, atol=2e-5)
