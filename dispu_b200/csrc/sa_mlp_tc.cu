@@ -3,16 +3,18 @@
 // Reference chain replaced: Common/pointnet_util.py:46-53,117-133 + Common/tf_util.py:120-185
 // (see sa_mlp.cu).  The grouped MLP is the one tensor-core-eligible contraction of the path.
 //
-// One persistent CTA per SM (128 threads); a tile is 128 grouped rows = 128/nsample whole groups.
+// One persistent CTA per SM; a tile is 128 grouped rows = 128/nsample whole groups.  The CTA runs
+// up to four warpgroups, each with its own tile stream, TMEM region and mbarrier, so one
+// warpgroup's tensor-core phase overlaps the others' gather / epilogue phases.
 //   setup   every layer's weights are staged ONCE per CTA into shared memory, already split into
-//           TF32 hi / lo planes and laid out as K-major UMMA operands (tc_common.cuh); TMEM
-//           accumulator (<= 256 columns) allocated once.
-//   tile    (1) gather: thread r builds grouped row r (points[idx] | xyz[idx]-centre | 0-pad)
-//               straight into the A operand planes (hi, lo) in shared memory;
-//           (2) per layer: one thread issues K/8 x {3 | 1} tcgen05.mma (M=128, N=C_out, K=8)
-//               and commits to an mbarrier; all threads wait, then thread r reads accumulator
-//               ROW r with tcgen05.ld (lane = row), applies bias + ReLU, re-splits into hi/lo and
-//               writes the next layer's A operand — activations never leave the SM;
+//           TF32 hi / lo planes and laid out as K-major UMMA operands (tc_common.cuh).
+//   tile    (1) gather: thread r builds grouped row r (points[idx] | xyz[idx]-centre | 0-pad) and
+//               writes it as the A operand of layer 0 into TENSOR MEMORY (lane r) with tcgen05.st;
+//           (2) per layer: one thread issues K/8 x {3 | 1} tcgen05.mma (A from TMEM, B from smem,
+//               M=128, N=C_out, K=8) and commits to the warpgroup's mbarrier; thread r then reads
+//               accumulator ROW r with tcgen05.ld, applies bias + ReLU, re-splits into hi/lo and
+//               stores the next layer's A operand back to TMEM — activations never touch shared or
+//               global memory;
 //           (3) last layer: bias + ReLU, then the max over the nsample rows of a group is ONE
 //               `redux.sync.max.u32` per column (rows of a group are lanes of a warp; post-ReLU
 //               floats order like their bit patterns), and lanes store (group, column) coalesced.
@@ -25,7 +27,7 @@ namespace dispu {
 
 using namespace tc;
 
-constexpr int kTcThreads = 128;
+constexpr int kTcThreads = 128;  // self-test kernels
 constexpr int kTcRows = 128;
 constexpr uint32_t kTmemCols = 256;
 constexpr int kTcMaxSmem = 220 * 1024;
@@ -35,40 +37,113 @@ struct TcPlan {
     int K[kMlpMaxLayers];     // padded input width (multiple of 8)
     int N[kMlpMaxLayers];     // output width (multiple of 16, <= 256)
     int cin[kMlpMaxLayers];   // true input width
-    uint32_t offB[kMlpMaxLayers];     // byte offset of the hi plane of layer l's weights; lo follows
-    uint32_t offBias[kMlpMaxLayers];  // byte offset of the bias (N floats)
-    uint32_t offA;            // A hi plane; lo follows at +planeA
-    uint32_t planeA;          // 128 * Kmax * 4
+    int dcol[kMlpMaxLayers];  // TMEM column (inside a warpgroup's region) of the layer's accumulator
+    uint32_t offB[kMlpMaxLayers];     // smem byte offset of the hi plane of layer l's weights; lo follows
+    uint32_t offBias[kMlpMaxLayers];  // smem byte offset of the bias (N floats)
     const float *w[kMlpMaxLayers];
     const float *bias[kMlpMaxLayers];
     int c_pts, c_pts_pad, layout;
+    int wg_cols;  // TMEM columns per warpgroup region
+    int n_wg;     // warpgroups per CTA (each runs its own tile stream)
 };
 
+__device__ __forceinline__ void wg_barrier(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
+
+// Hidden-layer epilogue for COLS accumulator columns starting at c0 of my row: bias + ReLU, TF32 hi/lo
+// split, and the result becomes columns [c0, c0+COLS) of the next layer's A operand in TMEM.
+template <bool kX3, int COLS>
+__device__ __forceinline__ void epilogue_hidden(uint32_t tmem_row, int dcol, int N, int c0, const float *sb) {
+    uint32_t v[32];
+    if (COLS == 32) tmem_ld32(tmem_row + dcol + c0, v); else tmem_ld16(tmem_row + dcol + c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < COLS; j += 8) {
+        const float4 b0 = *reinterpret_cast<const float4 *>(sb + c0 + j);
+        const float4 b1 = *reinterpret_cast<const float4 *>(sb + c0 + j + 4);
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        uint32_t h[8], lo[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float x = fmaxf(__fadd_rn(__uint_as_float(v[j + u]), bb[u]), 0.f);
+            const float hh = tf32_round(x);
+            h[u] = __float_as_uint(hh);
+            lo[u] = __float_as_uint(__fsub_rn(x, hh));
+        }
+        tmem_st8(tmem_row + c0 + j, h);
+        if (kX3) tmem_st8(tmem_row + N + c0 + j, lo);
+    }
+}
+
+// Last-layer epilogue: max over the NS rows (= lanes) of my group for COLS columns, then bias + ReLU on
+// the winner only.  max_rows(relu(x+b)) == relu(max_rows(x)+b) exactly (fp add is monotone in x), so
+// the reduction runs on the RAW accumulator through an order-preserving float->int key and ONE
+// redux.sync.max.s32 per column; lane (c % NS) of the group keeps column c and stores it coalesced.
+template <int NS, int COLS>
+__device__ __forceinline__ void epilogue_pool(uint32_t tmem_d_row, int N, int c0, const float *sb, unsigned gmask,
+                                              int lane, bool gvalid, float *out_row) {
+    uint32_t v[32];
+    if (COLS == 32) tmem_ld32(tmem_d_row + c0, v); else tmem_ld16(tmem_d_row + c0, v);
+    tmem_ld_wait();
+    constexpr int W = COLS / NS > 0 ? COLS / NS : 1;
+    int keep[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) keep[w] = 0;
+    const int lm = lane % NS;
+#pragma unroll
+    for (int j = 0; j < COLS; ++j) {
+        const int b = (int)v[j];
+        const int key = b ^ ((b >> 31) & 0x7fffffff);  // signed-int order == float order
+        const int mx = __reduce_max_sync(gmask, key);
+        if ((j % NS) == lm) keep[j / NS] = mx;
+    }
+    if (gvalid) {
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            const int col = c0 + w * NS + lm;
+            if (w * NS + lm < COLS) {
+                const int key = keep[w];
+                const float x = __int_as_float(key ^ ((key >> 31) & 0x7fffffff));
+                out_row[col] = fmaxf(__fadd_rn(x, sb[col]), 0.f);
+            }
+        }
+    }
+    (void)N;
+}
+
+// NS: rows per group (8, 16, 32).  kX3: 3xTF32 (hi/lo planes) or single-pass TF32.
+//
+// Activations live in TENSOR MEMORY for the whole MLP: a warpgroup's thread r owns TMEM lane r =
+// grouped row r.  The A operand of every layer is read by the tensor core straight from TMEM
+// ("TS" tcgen05.mma), the accumulator is read back with tcgen05.ld, bias/ReLU/TF32-split happen in
+// registers and the next layer's A operand is written back with tcgen05.st; shared memory holds
+// only the weights.  Column plan inside a warpgroup's region for layer l (P = planes):
+//   A_hi [0,K_l)  A_lo [K_l,2K_l)  D [dcol_l, dcol_l+N_l)  with dcol_l >= P*K_l and >= P*N_l (next A).
 template <bool kX3, int NS>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(512, 1)
 sa_mlp_tc_kernel(int n, int m, const float *__restrict__ xyz, const float *__restrict__ points,
                  const float *__restrict__ new_xyz, const int *__restrict__ idx, TcPlan plan,
                  float *__restrict__ out, long long total_rows, int n_tiles) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ __align__(8) uint64_t s_bar[4];
     __shared__ uint32_t s_tmem;
+    constexpr int P = kX3 ? 2 : 1;
 
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int tid = threadIdx.x;
+    const int wg = tid >> 7, t = tid & 127, lane = tid & 31, q = (tid >> 5) & 3;
     const uint32_t smem_base = smem_u32(smem);
 
-    // ---- one-time setup ------------------------------------------------------------------------
-    if (t == 0) {
-        mbar_init(&s_bar, 1);
+    // ---- one-time setup: barriers, TMEM, weights (hi/lo planes, K-major UMMA layout) ------------
+    if (tid == 0) {
+        for (int i = 0; i < 4; ++i) mbar_init(&s_bar[i], 1);
         fence_mbar_init();
     }
-    if (warp == 0) tmem_alloc(&s_tmem, kTmemCols);
-
+    if (tid < 32) tmem_alloc(&s_tmem, 512);
     for (int l = 0; l < plan.n_layers; ++l) {
         const int K = plan.K[l], N = plan.N[l], cin = plan.cin[l];
         uint8_t *bhi = smem + plan.offB[l];
         uint8_t *blo = bhi + (size_t)K * N * 4;
         const float *W = plan.w[l];
-        for (int e = t; e < K * N; e += kTcThreads) {
+        for (int e = tid; e < K * N; e += blockDim.x) {
             const int k = e / N, nn = e - k * N;
             int row = -1;  // reference weight row feeding internal channel k
             if (l == 0) {
@@ -85,36 +160,42 @@ sa_mlp_tc_kernel(int n, int m, const float *__restrict__ xyz, const float *__res
             if (kX3) *reinterpret_cast<float *>(blo + o) = __fsub_rn(w, hi);
         }
         float *sb = reinterpret_cast<float *>(smem + plan.offBias[l]);
-        for (int e = t; e < N; e += kTcThreads) sb[e] = plan.bias[l] ? __ldg(plan.bias[l] + e) : 0.f;
+        for (int e = tid; e < N; e += blockDim.x) sb[e] = plan.bias[l] ? __ldg(plan.bias[l] + e) : 0.f;
     }
     fence_proxy_async_smem();
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
-    const uint32_t tmem_d = s_tmem;
+
+    const uint32_t tmem_wg = s_tmem + (uint32_t)(wg * plan.wg_cols);       // lane 0 of my warpgroup's region
+    const uint32_t tmem_row = tmem_wg + ((uint32_t)(q * 32) << 16);        // my warp's 32 lanes
     uint32_t phase = 0;
-
-    uint8_t *a_hi = smem + plan.offA;
-    uint8_t *a_lo = a_hi + plan.planeA;
-    const uint32_t a_hi_addr = smem_base + plan.offA;
-    const uint32_t a_lo_addr = a_hi_addr + plan.planeA;
-    const uint32_t row_off = (uint32_t)(t >> 3) * 128u + (uint32_t)(t & 7) * 16u;  // my row inside a K-chunk
-    constexpr uint32_t kLboA = (kTcRows / 8) * 128;                               // 2048
-    constexpr int ns = NS;  // rows per group: 8, 16 or 32 (a group never straddles a warp)
     const unsigned gmask = NS == 32 ? 0xffffffffu : (((1u << (NS & 31)) - 1u) << ((lane / NS) * NS));
+    const int c_pts = plan.c_pts, cpp = plan.c_pts_pad, K0 = plan.K[0];
+    const bool vec = (c_pts & 3) == 0 && (reinterpret_cast<uintptr_t>(points) & 15u) == 0;
+    const int tile_stride = gridDim.x * plan.n_wg;
 
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        // ---- (1) gather my grouped row into the A operand of layer 0 ----------------------------
+    int tile = blockIdx.x * plan.n_wg + wg;
+    int ii_next = 0;
+    if (tile < n_tiles) {
+        const long long R = (long long)tile * kTcRows + t;
+        if (R < total_rows) ii_next = __ldg(idx + R);
+    }
+    for (; tile < n_tiles; tile += tile_stride) {
+        // ---- (1) gather my grouped row -> A operand of layer 0 (TMEM) ---------------------------
+        const long long R = (long long)tile * kTcRows + t;
+        const bool valid = R < total_rows;
+        const int ii = ii_next;
         {
-            const long long R = (long long)tile * kTcRows + t;
-            const bool valid = R < total_rows;
-            const int K0 = plan.K[0], c_pts = plan.c_pts, cpp = plan.c_pts_pad;
+            const long long Rn = R + (long long)tile_stride * kTcRows;  // prefetch next tile's index
+            if (tile + tile_stride < n_tiles && Rn < total_rows) ii_next = __ldg(idx + Rn);
+        }
+        {
             float gx = 0.f, gy = 0.f, gz = 0.f;
-            const float *pf = nullptr;
+            const float *pf = points;
             if (valid) {
-                const long long g = R / ns;
+                const long long g = R / NS;
                 const long long cloud = g / m;
-                const int ii = __ldg(idx + R);
                 const float *pxyz = xyz + (cloud * n + ii) * 3;
                 const float *ctr = new_xyz + g * 3;
                 gx = __fsub_rn(__ldg(pxyz), __ldg(ctr));
@@ -122,125 +203,90 @@ sa_mlp_tc_kernel(int n, int m, const float *__restrict__ xyz, const float *__res
                 gz = __fsub_rn(__ldg(pxyz + 2), __ldg(ctr + 2));
                 if (c_pts) pf = points + (cloud * n + ii) * (long long)c_pts;
             }
-            const bool vec = (c_pts & 3) == 0 && (reinterpret_cast<uintptr_t>(points) & 15u) == 0;
-            for (int c = 0; c < K0 / 4; ++c) {
-                const int k0 = c * 4;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (valid) {
-                    if (k0 + 3 < c_pts && vec) {
-                        v = __ldg(reinterpret_cast<const float4 *>(pf + k0));
+            for (int k0 = 0; k0 < K0; k0 += 8) {
+                float x[8];
+#pragma unroll
+                for (int hlf = 0; hlf < 2; ++hlf) {
+                    const int kk = k0 + hlf * 4;
+                    if (valid && vec && kk + 3 < c_pts) {
+                        const float4 v = __ldg(reinterpret_cast<const float4 *>(pf + kk));
+                        x[hlf * 4] = v.x; x[hlf * 4 + 1] = v.y; x[hlf * 4 + 2] = v.z; x[hlf * 4 + 3] = v.w;
                     } else {
-                        float e4[4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            const int k = k0 + u;
-                            float x = 0.f;
-                            if (k < c_pts) x = __ldg(pf + k);
-                            else if (k == cpp) x = gx;
-                            else if (k == cpp + 1) x = gy;
-                            else if (k == cpp + 2) x = gz;
-                            e4[u] = x;
+                            const int k = kk + u;
+                            float e = 0.f;
+                            if (valid) {
+                                if (k < c_pts) e = __ldg(pf + k);
+                                else if (k == cpp) e = gx;
+                                else if (k == cpp + 1) e = gy;
+                                else if (k == cpp + 2) e = gz;
+                            }
+                            x[hlf * 4 + u] = e;
                         }
-                        v = make_float4(e4[0], e4[1], e4[2], e4[3]);
                     }
                 }
-                const float4 h = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
-                const uint32_t o = (uint32_t)c * kLboA + row_off;
-                *reinterpret_cast<float4 *>(a_hi + o) = h;
-                if (kX3)
-                    *reinterpret_cast<float4 *>(a_lo + o) =
-                        make_float4(__fsub_rn(v.x, h.x), __fsub_rn(v.y, h.y), __fsub_rn(v.z, h.z), __fsub_rn(v.w, h.w));
+                uint32_t h[8], lo[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float hh = tf32_round(x[u]);
+                    h[u] = __float_as_uint(hh);
+                    lo[u] = __float_as_uint(__fsub_rn(x[u], hh));
+                }
+                tmem_st8(tmem_row + k0, h);
+                if (kX3) tmem_st8(tmem_row + K0 + k0, lo);
             }
         }
 
         for (int l = 0; l < plan.n_layers; ++l) {
-            const int K = plan.K[l], N = plan.N[l];
-            // operands written by the generic proxy -> visible to the tensor core
-            fence_proxy_async_smem();
+            const int K = plan.K[l], N = plan.N[l], dcol = plan.dcol[l];
+            tmem_st_wait();  // my A-operand stores have landed
             tc_fence_before_sync();
-            __syncthreads();
-            // ---- (2) issue the layer's MMAs -------------------------------------------------------
+            wg_barrier(wg);
+            // ---- (2) one thread of the warpgroup issues the layer's MMAs ------------------------
             if (t == 0) {
                 tc_fence_after_sync();
                 const uint32_t idesc = make_idesc_tf32(kTcRows, N);
                 const uint32_t lboB = (uint32_t)(N / 8) * 128u;
                 const uint32_t b_hi_addr = smem_base + plan.offB[l];
                 const uint32_t b_lo_addr = b_hi_addr + (uint32_t)K * N * 4u;
+                const uint32_t d = tmem_wg + dcol;
                 for (int ks = 0; ks < K / 8; ++ks) {
-                    const uint64_t ah = make_smem_desc(a_hi_addr + ks * 2 * kLboA, kLboA, 128);
                     const uint64_t bh = make_smem_desc(b_hi_addr + ks * 2 * lboB, lboB, 128);
                     if (kX3) {
-                        const uint64_t al = make_smem_desc(a_lo_addr + ks * 2 * kLboA, kLboA, 128);
                         const uint64_t bl = make_smem_desc(b_lo_addr + ks * 2 * lboB, lboB, 128);
-                        mma_tf32_ss(tmem_d, al, bh, idesc, ks > 0);
-                        mma_tf32_ss(tmem_d, ah, bl, idesc, 1);
-                        mma_tf32_ss(tmem_d, ah, bh, idesc, 1);
+                        mma_tf32_ts(d, tmem_wg + K + ks * 8, bh, idesc, ks > 0);  // a_lo * b_hi
+                        mma_tf32_ts(d, tmem_wg + ks * 8, bl, idesc, 1);           // a_hi * b_lo
+                        mma_tf32_ts(d, tmem_wg + ks * 8, bh, idesc, 1);           // a_hi * b_hi
                     } else {
-                        mma_tf32_ss(tmem_d, ah, bh, idesc, ks > 0);
+                        mma_tf32_ts(d, tmem_wg + ks * 8, bh, idesc, ks > 0);
                     }
                 }
-                mma_commit(&s_bar);
+                mma_commit(&s_bar[wg]);
             }
-            mbar_wait(&s_bar, phase);
+            mbar_wait(&s_bar[wg], phase);
             phase ^= 1;
             tc_fence_after_sync();
 
-            // ---- (3) epilogue: my accumulator row ------------------------------------------------
+            // ---- (3) epilogue on my accumulator row -------------------------------------------------
             const float *sb = reinterpret_cast<const float *>(smem + plan.offBias[l]);
-            const uint32_t trow = tmem_d + ((uint32_t)(warp * 32) << 16);
-            const bool last = l == plan.n_layers - 1;
-            for (int c0 = 0; c0 < N; c0 += 32) {
-                uint32_t v[32];
-                const int cols = min(32, N - c0);  // 32 or 16
-                if (cols == 32) tmem_ld32(trow + c0, v); else tmem_ld16(trow + c0, v);
-                tmem_ld_wait();
-                if (!last) {
-                    // bias + ReLU -> hi/lo split -> next layer's A operand (K-chunks of 4 columns)
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        if (j < cols) {
-                            float x[4];
-#pragma unroll
-                            for (int u = 0; u < 4; ++u)
-                                x[u] = fmaxf(__fadd_rn(__uint_as_float(v[j + u]), sb[c0 + j + u]), 0.f);
-                            const float4 h = make_float4(tf32_round(x[0]), tf32_round(x[1]), tf32_round(x[2]), tf32_round(x[3]));
-                            const uint32_t o = (uint32_t)((c0 + j) >> 2) * kLboA + row_off;
-                            *reinterpret_cast<float4 *>(a_hi + o) = h;
-                            if (kX3)
-                                *reinterpret_cast<float4 *>(a_lo + o) = make_float4(
-                                    __fsub_rn(x[0], h.x), __fsub_rn(x[1], h.y), __fsub_rn(x[2], h.z), __fsub_rn(x[3], h.w));
-                        }
-                    }
-                } else {
-                    // bias + ReLU, max over the group's lanes, coalesced store of (group, column)
-                    const long long g = ((long long)tile * kTcRows + t) / ns;
-                    const bool gvalid = (long long)tile * kTcRows + (t / ns) * ns < total_rows;
-                    float keep[32 / NS];  // window w holds column c0 + w*ns + lane%ns
-#pragma unroll
-                    for (int w = 0; w < 32 / NS; ++w) keep[w] = 0.f;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (j < cols) {
-                            const float x = fmaxf(__fadd_rn(__uint_as_float(v[j]), sb[c0 + j]), 0.f);
-                            const uint32_t mx = __reduce_max_sync(gmask, __float_as_uint(x));  // x >= 0: bit order == value order
-                            if ((j % NS) == (lane % NS)) keep[j / NS] = __uint_as_float(mx);
-                        }
-                    }
-                    if (gvalid) {
-#pragma unroll
-                        for (int w = 0; w < 32 / NS; ++w) {
-                            const int col = c0 + w * ns + (lane % ns);
-                            if (col < c0 + cols) out[g * N + col] = keep[w];
-                        }
-                    }
-                }
+            if (l != plan.n_layers - 1) {
+                for (int c0 = 0; c0 + 32 <= N; c0 += 32) epilogue_hidden<kX3, 32>(tmem_row, dcol, N, c0, sb);
+                if (N & 16) epilogue_hidden<kX3, 16>(tmem_row, dcol, N, N - 16, sb);
+            } else {
+                const long long g = R / NS;
+                const bool gvalid = (long long)tile * kTcRows + (t / NS) * NS < total_rows;
+                for (int c0 = 0; c0 + 32 <= N; c0 += 32)
+                    epilogue_pool<NS, 32>(tmem_row + dcol, N, c0, sb, gmask, lane, gvalid, out + g * N);
+                if (N & 16) epilogue_pool<NS, 16>(tmem_row + dcol, N, N - 16, sb, gmask, lane, gvalid, out + g * N);
             }
-            // all TMEM reads / smem writes of this layer done before the next MMA overwrites them
-            tc_fence_before_sync();
         }
+        // the next gather overwrites [0, P*K0): only my own lanes, after my own tcgen05.wait::ld
     }
+    (void)P;
+    tc_fence_before_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_d, kTmemCols);
+    if (tid < 32) tmem_dealloc(s_tmem, 512);
 }
 
 // D (128 x N) = A (128 x K) . W (K x N): descriptor / layout self-test used by tests (not a product op).
@@ -305,6 +351,72 @@ tc_gemm_selftest_kernel(int K, int N, const float *__restrict__ A, const float *
     if (warp == 0) tmem_dealloc(tmem_d, kTmemCols);
 }
 
+// Same product with A held in TMEM ("TS" form): rows are TMEM lanes, K runs along columns.
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_gemm_selftest_ts_kernel(int K, int N, const float *__restrict__ A, const float *__restrict__ W, float *__restrict__ D) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_tmem;
+    const int t = threadIdx.x, warp = t >> 5;
+    uint8_t *b_hi = smem, *b_lo = b_hi + K * N * 4;
+    if (t == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
+    if (warp == 0) tmem_alloc(&s_tmem, 512);
+    for (int e = t; e < K * N; e += kTcThreads) {
+        const int k = e / N, nn = e - k * N;
+        const float x = W[e], h = tf32_round(x);
+        *reinterpret_cast<float *>(b_hi + op_offset(N, nn, k)) = h;
+        *reinterpret_cast<float *>(b_lo + op_offset(N, nn, k)) = x - h;
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_d = s_tmem;
+    const uint32_t lane_base = ((uint32_t)(warp * 32) << 16);
+    const uint32_t a_hi_col = 256, a_lo_col = 256 + K;  // D at [0,N), A planes from column 256
+    for (int k0 = 0; k0 < K; k0 += 8) {
+        uint32_t h[8], l[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float x = A[(size_t)t * K + k0 + u], hh = tf32_round(x);
+            h[u] = __float_as_uint(hh);
+            l[u] = __float_as_uint(x - hh);
+        }
+        tmem_st8(tmem_d + lane_base + a_hi_col + k0, h);
+        tmem_st8(tmem_d + lane_base + a_lo_col + k0, l);
+    }
+    tmem_st_wait();
+    tc_fence_before_sync();
+    __syncthreads();
+    if (t == 0) {
+        tc_fence_after_sync();
+        const uint32_t idesc = make_idesc_tf32(128, N);
+        const uint32_t lboB = (uint32_t)(N / 8) * 128u;
+        const uint32_t bh0 = smem_u32(b_hi), bl0 = smem_u32(b_lo);
+        for (int ks = 0; ks < K / 8; ++ks) {
+            const uint64_t bh = make_smem_desc(bh0 + ks * 2 * lboB, lboB, 128), bl = make_smem_desc(bl0 + ks * 2 * lboB, lboB, 128);
+            mma_tf32_ts(tmem_d, tmem_d + a_lo_col + ks * 8, bh, idesc, ks > 0);
+            mma_tf32_ts(tmem_d, tmem_d + a_hi_col + ks * 8, bl, idesc, 1);
+            mma_tf32_ts(tmem_d, tmem_d + a_hi_col + ks * 8, bh, idesc, 1);
+        }
+        mma_commit(&s_bar);
+    }
+    mbar_wait(&s_bar, 0);
+    tc_fence_after_sync();
+    for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t v[32];
+        const int cols = min(32, N - c0);
+        if (cols == 32) tmem_ld32(tmem_d + lane_base + c0, v); else tmem_ld16(tmem_d + lane_base + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (j < cols) D[(size_t)t * N + c0 + j] = __uint_as_float(v[j]);
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_d, 512);
+}
+
 int sa_mlp_tc_launch(int b, int n, int m, int ns, int c_pts, int layout, const float *xyz, const float *points,
                      const float *new_xyz, const int *idx, const MlpParams &prm, float *out, int precision,
                      cudaStream_t stream, bool *handled) {
@@ -318,30 +430,34 @@ int sa_mlp_tc_launch(int b, int n, int m, int ns, int c_pts, int layout, const f
     const bool x3 = precision == DISPU_MLP_TF32X3;
     const int planes = x3 ? 2 : 1;
     uint32_t off = 0;
-    int kmax = 0;
+    int need = 0;
     for (int l = 0; l < prm.n_layers; ++l) {
         const int cin = prm.widths[l], N = prm.widths[l + 1];
         if (N % 16 != 0 || N > 256) return DISPU_EUNSUPPORTED;
         const int K = l == 0 ? ((plan.c_pts_pad + 3 + 7) & ~7) : cin;  // hidden widths are multiples of 16 already
+        const bool last = l == prm.n_layers - 1;
+        int dcol = planes * K;
+        if (!last && planes * N > dcol) dcol = planes * N;
         plan.K[l] = K;
         plan.N[l] = N;
         plan.cin[l] = cin;
+        plan.dcol[l] = dcol;
         plan.w[l] = prm.w[l];
         plan.bias[l] = prm.bias[l];
         plan.offB[l] = off;
         off += (uint32_t)K * N * 4 * planes;
-        if (K > kmax) kmax = K;
+        if (dcol + N > need) need = dcol + N;
     }
+    if (need > 512) return DISPU_EUNSUPPORTED;
     for (int l = 0; l < prm.n_layers; ++l) {
         plan.offBias[l] = off;
         off += (uint32_t)plan.N[l] * 4;
     }
-    off = (off + 127u) & ~127u;
-    plan.offA = off;
-    plan.planeA = (uint32_t)kTcRows * kmax * 4;
-    off += plan.planeA * planes;
     if (off > (uint32_t)kTcMaxSmem) return DISPU_EUNSUPPORTED;
     *handled = true;
+    plan.wg_cols = (need + 31) & ~31;
+    plan.n_wg = 512 / plan.wg_cols;
+    if (plan.n_wg > 4) plan.n_wg = 4;
     const long long total_rows = (long long)b * m * ns;
     const long long n_tiles_ll = ceil_div64(total_rows, kTcRows);
     if (n_tiles_ll > 0x7fffffffLL) return DISPU_EUNSUPPORTED;
@@ -349,15 +465,17 @@ int sa_mlp_tc_launch(int b, int n, int m, int ns, int c_pts, int layout, const f
     int dev = 0, sms = kNumSMs;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int grid = n_tiles < sms ? n_tiles : sms;
+    long long grid_ll = ceil_div64(n_tiles, plan.n_wg);
+    const int grid = grid_ll < sms ? (int)grid_ll : sms;
+    const int threads = plan.n_wg * 128;
     count_launch();
 #define DISPU_TC_LAUNCH(X3, NSV)                                                                                   \
     do {                                                                                                           \
         cudaError_t e_ = cudaFuncSetAttribute(sa_mlp_tc_kernel<X3, NSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                               (int)off);                                                           \
         if (e_ != cudaSuccess) return (int)e_;                                                                     \
-        sa_mlp_tc_kernel<X3, NSV><<<grid, kTcThreads, off, stream>>>(n, m, xyz, points, new_xyz, idx, plan, out,    \
-                                                                     total_rows, n_tiles);                         \
+        sa_mlp_tc_kernel<X3, NSV><<<grid, threads, off, stream>>>(n, m, xyz, points, new_xyz, idx, plan, out,       \
+                                                                  total_rows, n_tiles);                            \
     } while (0)
     if (x3) {
         if (ns == 8) DISPU_TC_LAUNCH(true, 8); else if (ns == 16) DISPU_TC_LAUNCH(true, 16); else DISPU_TC_LAUNCH(true, 32);
@@ -378,6 +496,13 @@ extern "C" int dispu__tc_gemm_selftest(int K, int N, const float *A, const float
     const size_t smem = (size_t)(128 * K + K * N) * 4 * 2;
     if (smem > (size_t)kTcMaxSmem) return DISPU_EUNSUPPORTED;
     count_launch();
+    if (x3 == 2) {  // TS form (A in TMEM), 3xTF32
+        if (K > 128) return DISPU_EUNSUPPORTED;
+        const size_t sm2 = (size_t)K * N * 4 * 2;
+        cudaFuncSetAttribute(tc_gemm_selftest_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+        tc_gemm_selftest_ts_kernel<<<1, kTcThreads, sm2, (cudaStream_t)stream>>>(K, N, A, W, D);
+        return finish_launch();
+    }
     if (x3) {
         cudaFuncSetAttribute(tc_gemm_selftest_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         tc_gemm_selftest_kernel<true><<<1, kTcThreads, smem, (cudaStream_t)stream>>>(K, N, A, W, D);

@@ -360,6 +360,8 @@ def test_tc_gemm_selftest(rng, K, N):
     got, want = _tc_selftest(K, N, True, rng)
     scale = np.abs(want).max()
     assert np.abs(got - want).max() <= 2e-6 * scale * np.sqrt(K), "3xTF32 should be fp32-level"
+    got2, want2 = _tc_selftest(K, N, 2, rng)  # A operand in TMEM ("TS" form)
+    assert np.abs(got2 - want2).max() <= 2e-6 * np.abs(want2).max() * np.sqrt(K)
     got1, want1 = _tc_selftest(K, N, False, rng)
     assert np.abs(got1 - want1).max() <= 3e-3 * np.abs(want1).max()  # single-pass TF32: ~2^-11 per operand
 
