@@ -9,7 +9,8 @@
 // coordinates, the per-step arg-max is two `redux.sync` per warp + one barrier + two more
 // `redux.sync`, and clouds too large for one SM's register file (or too few to fill the GPU)
 // are spread over a thread-block CLUSTER whose CTAs exchange their local winners through
-// distributed shared memory with one cluster barrier per step.
+// distributed shared memory through asynchronous DSMEM stores that complete transaction bytes on the
+// receiver's mbarrier (no cluster-wide barrier inside the loop).
 //
 // Bit-exactness: indices must equal the reference's.  The reference's order among equal maxima
 // is (k mod 512) ascending, then k ascending (strided per-thread scan with strict '>' at :146,
@@ -17,6 +18,7 @@
 // 32-bit tie key next to the float's bit pattern, so the thread mapping is free.  Distances use
 // the reference's FMA contraction (d2_ref_gpu).
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -33,6 +35,44 @@ constexpr uint32_t kTieNone = 0xffffffffu;
 __device__ __forceinline__ void warp_argmax(uint32_t bits, uint32_t tie, uint32_t &wb, uint32_t &wt) {
     wb = __reduce_max_sync(kFull, bits);
     wt = __reduce_min_sync(kFull, bits == wb ? tie : kTieNone);
+}
+
+// ---- cluster exchange primitives (DSMEM + remote mbarrier arrive) ---------------------------------
+__device__ __forceinline__ uint32_t fps_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fps_mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fps_smem_u32(bar)), "r"(count) : "memory");
+}
+// map a shared::cta address of this CTA to the shared::cluster address of the same variable in CTA `rank`
+__device__ __forceinline__ uint32_t fps_mapa(uint32_t saddr, uint32_t rank) {
+    uint32_t raddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(saddr), "r"(rank));
+    return raddr;
+}
+// Asynchronous remote stores that complete transaction bytes on the DESTINATION CTA's mbarrier: data and
+// "it has arrived" travel together, so no release fence / second round trip is needed.
+__device__ __forceinline__ void fps_st_async_v4(uint32_t raddr, uint32_t rbar, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr),
+                 "r"(a), "r"(b), "r"(c), "r"(d), "r"(rbar)
+                 : "memory");
+}
+__device__ __forceinline__ void fps_st_async_b32(uint32_t raddr, uint32_t rbar, uint32_t a) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(raddr), "r"(a), "r"(rbar)
+                 : "memory");
+}
+__device__ __forceinline__ void fps_mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fps_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fps_mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(fps_smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
 }
 
 struct __align__(16) ClusterSlot {
@@ -57,6 +97,7 @@ fps_onchip_kernel(int b, int n, int m, const float *__restrict__ xyz, int *__res
     extern __shared__ float4 s_xyz[];  // T*P local points (winner lookup only)
     __shared__ uint2 s_slot[2][32];
     __shared__ ClusterSlot s_cslot[2][C > 1 ? C : 1];
+    __shared__ __align__(8) uint64_t s_cbar[2];  // one per slot buffer; 1 local arrival + 20*C transaction bytes per use
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     int cloud, rank;
@@ -89,8 +130,13 @@ fps_onchip_kernel(int b, int n, int m, const float *__restrict__ xyz, int *__res
     }
     float x1 = __ldg(p + 0), y1 = __ldg(p + 1), z1 = __ldg(p + 2);  // old = 0 (:114)
     if (t == 0 && rank == 0) out[0] = 0;
+    if (C > 1 && t == 0) {
+        fps_mbar_init(&s_cbar[0], 1);
+        fps_mbar_init(&s_cbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
-    if (C > 1) cg::this_cluster().sync();
+    if (C > 1) cg::this_cluster().sync();  // barriers initialised cluster-wide before anyone arrives
 
     for (int j = 1; j < m; ++j) {
         const int buf = j & 1;
@@ -124,17 +170,24 @@ fps_onchip_kernel(int b, int n, int m, const float *__restrict__ xyz, int *__res
             x1 = w.x; y1 = w.y; z1 = w.z;
             if (t == 0) out[j] = (int)kwin;
         } else {
-            cg::cluster_group cluster = cg::this_cluster();
             if (warp == 0) {
                 // A CTA whose chunk lies wholly beyond n has no valid point: ct == kTieNone.
                 float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (ct != kTieNone) w = s_xyz[fps_k_of_tie(ct) - base];
+                if (lane == 0) fps_mbar_arrive_expect_tx(&s_cbar[buf], 20u * C);  // what my own barrier will receive
                 if (lane < C) {
-                    ClusterSlot *dst = cluster.map_shared_rank(&s_cslot[buf][rank], lane);
-                    dst->bits = cb; dst->tie = ct; dst->x = w.x; dst->y = w.y; dst->z = w.z;
+                    // publish my CTA's winner into slot [rank] of CTA `lane`; the stores themselves complete
+                    // 20 transaction bytes on that CTA's barrier.
+                    const uint32_t rslot = fps_mapa(fps_smem_u32(&s_cslot[buf][rank]), (uint32_t)lane);
+                    const uint32_t rbar = fps_mapa(fps_smem_u32(&s_cbar[buf]), (uint32_t)lane);
+                    fps_st_async_v4(rslot, rbar, cb, ct, __float_as_uint(w.x), __float_as_uint(w.y));
+                    fps_st_async_b32(rslot + 16, rbar, __float_as_uint(w.z));
                 }
             }
-            cluster.sync();
+            // buffer `buf` is used at steps j = 2u+1 (buf 1) / 2u+2 (buf 0): use number u = (j-1)>>1.
+            // Re-use is safe: a peer can only be two steps ahead after it received my stores for the step in
+            // between, which I issue after all my warps consumed this step's slots.
+            fps_mbar_wait_cluster(&s_cbar[buf], (uint32_t)(((j - 1) >> 1) & 1));
             uint32_t sb = 0u, st = kTieNone;
             float sx = 0.f, sy = 0.f, sz = 0.f;
             if (lane < C) {
@@ -255,14 +308,40 @@ extern "C" int dispu_fps(int b, int n, int m, const float *inp, float *temp, int
     if (n <= 2048) return launch_onchip<256, 8, 1>(b, n, m, inp, out, stream);
     if (n <= 4096) return launch_onchip<512, 8, 1>(b, n, m, inp, out, stream);
     if (n <= 8192) return launch_onchip<1024, 8, 1>(b, n, m, inp, out, stream);
-    // one cluster per cloud
-    if (n <= 2 * 8192) return launch_onchip<1024, 8, 2>(b, n, m, inp, out, stream);
-    if (n <= 4 * 8192) return launch_onchip<1024, 8, 4>(b, n, m, inp, out, stream);
-    if (n <= 8 * 8192) return launch_onchip<1024, 8, 8>(b, n, m, inp, out, stream);
+    // one cluster per cloud: the fewest CTAs that hold the cloud (<= 8 points per thread), then more
+    // CTAs with fewer points each while that still leaves the GPU under-filled (small batches: the
+    // per-step scan shrinks with P, the exchange cost barely grows with C).
     if (n <= kFpsOnchipCapacity) {
-        int rc = launch_onchip<1024, 8, 16>(b, n, m, inp, out, stream);
+        int C = 2;
+        while (C * 8192 < n) C *= 2;
+        int P = ceil_div(n, C * 1024);
+        while (C < 16 && P > 1 && (long long)b * C * 2 <= kNumSMs) {
+            C *= 2;
+            P = ceil_div(n, C * 1024);
+        }
+        if (const char *force = getenv("DISPU_FPS_FORCE_C")) {  // tuning hook (tools/), not a product knob
+            const int fc = atoi(force);
+            if ((fc == 2 || fc == 4 || fc == 8 || fc == 16) && (long long)fc * 8192 >= n) {
+                C = fc;
+                P = ceil_div(n, C * 1024);
+            }
+        }
+        P = P <= 1 ? 1 : P <= 2 ? 2 : P <= 4 ? 4 : 8;
+        int rc = DISPU_EUNSUPPORTED;
+#define DISPU_FPS_CASE(CC, PP) \
+    if (C == CC && P == PP) rc = launch_onchip<1024, PP, CC>(b, n, m, inp, out, stream);
+        DISPU_FPS_CASE(2, 1) DISPU_FPS_CASE(2, 2) DISPU_FPS_CASE(2, 4) DISPU_FPS_CASE(2, 8)
+        DISPU_FPS_CASE(4, 1) DISPU_FPS_CASE(4, 2) DISPU_FPS_CASE(4, 4) DISPU_FPS_CASE(4, 8)
+        DISPU_FPS_CASE(8, 1) DISPU_FPS_CASE(8, 2) DISPU_FPS_CASE(8, 4) DISPU_FPS_CASE(8, 8)
+        DISPU_FPS_CASE(16, 1) DISPU_FPS_CASE(16, 2) DISPU_FPS_CASE(16, 4) DISPU_FPS_CASE(16, 8)
+#undef DISPU_FPS_CASE
         if (rc == DISPU_OK) return rc;
-        (void)cudaGetLastError();  // 16-CTA clusters unavailable on this part/partition: fall through
+        if (C == 16) {  // 16-CTA clusters unavailable on this part/partition: retry with 8 if it fits
+            (void)cudaGetLastError();
+            if (n <= 8 * 8192) return launch_onchip<1024, 8, 8>(b, n, m, inp, out, stream);
+        } else {
+            return rc;
+        }
     }
     DISPU_REQUIRE(temp != nullptr, DISPU_EWORKSPACE);
     count_launch();
