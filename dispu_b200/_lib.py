@@ -25,6 +25,8 @@ SIGNATURES = {
     "dispu_gather_point_grad": ([_i, _i, _i, _p, _p, _p, _p], _i),
     "dispu_prob_sample": ([_i, _i, _i, _p, _p, _p, _p, _p], _i),
     "dispu_query_ball_point": ([_i, _i, _i, _p, _i, _p, _p, _p, _p, _p], _i),
+    "dispu_query_ball_point_workspace_bytes": ([_i, _i, _i], _sz),
+    "dispu_query_ball_point_ws": ([_i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _sz, _p], _i),
     "dispu_group_point": ([_i, _i, _i, _i, _i, _p, _p, _p, _p], _i),
     "dispu_group_point_grad": ([_i, _i, _i, _i, _i, _p, _p, _p, _p], _i),
     "dispu_selection_sort": ([_i, _i, _i, _i, _p, _p, _p, _p], _i),

@@ -102,9 +102,16 @@ class Generator:
 
     # -- layers ---------------------------------------------------------------------------------
     def _fc(self, x, name, act=True):
+        """1x1 conv = dense layer over the last axis, bias (+ ReLU) in the GEMM epilogue (stock cuBLASLt)."""
         w, b = self.P[name]
-        y = torch.matmul(x, w) + b
-        return torch.relu(y) if act else y
+        x2 = x.reshape(-1, x.shape[-1])
+        if act and x2.is_cuda:
+            y = torch._addmm_activation(b, x2, w, use_gelu=False)  # relu(x.w + b)
+        else:
+            y = torch.addmm(b, x2, w)
+            if act:
+                y = torch.relu_(y)
+        return y.view(*x.shape[:-1], w.shape[1])
 
     def _dense_conv(self, feature, blk, k=16):
         """ops.py:1897-1915 on (b,n,c) -> (b,n,72+c)."""

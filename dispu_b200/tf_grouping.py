@@ -5,7 +5,19 @@ import numbers
 
 import torch
 
+from . import _lib
 from ._t import call, ptr, req, stream_ptr
+
+_ws_cache = {}
+
+
+def _workspace(nbytes, device):
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
 
 
 def query_ball_point(radius, nsample, xyz, new_xyz):
@@ -26,8 +38,14 @@ def query_ball_point(radius, nsample, xyz, new_xyz):
     radius = req(radius, torch.float32, 1, "radius")
     idx = torch.empty((b, m, nsample), dtype=torch.int32, device=xyz.device)
     cnt = torch.empty((b, m), dtype=torch.int32, device=xyz.device)
-    call("dispu_query_ball_point", b, n, m, ptr(radius), nsample, ptr(xyz), ptr(new_xyz), ptr(idx), ptr(cnt),
-         stream_ptr())
+    if n >= 2048 and b > 0 and m > 0:  # large clouds: uniform-grid kernel (same results), scratch from the torch allocator
+        nbytes = int(_lib.lib().dispu_query_ball_point_workspace_bytes(b, n, m))
+        ws = _workspace(nbytes, xyz.device)
+        call("dispu_query_ball_point_ws", b, n, m, ptr(radius), nsample, ptr(xyz), ptr(new_xyz), ptr(idx), ptr(cnt),
+             ptr(ws), ws.numel(), stream_ptr())
+    else:
+        call("dispu_query_ball_point", b, n, m, ptr(radius), nsample, ptr(xyz), ptr(new_xyz), ptr(idx), ptr(cnt),
+             stream_ptr())
     return idx, cnt
 
 

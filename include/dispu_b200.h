@@ -77,6 +77,15 @@ int dispu_prob_sample(int b, int n, int m, const float *inp_p, const float *inp_
 int dispu_query_ball_point(int b, int n, int m, const float *radius, int nsample, const float *xyz1,
                            const float *xyz2, int *idx, int *pts_cnt, dispu_stream_t stream);
 
+/* Same op through a uniform grid (cell edge >= radius): identical idx / pts_cnt, O(points in the 27
+ * neighbouring cells) work per query instead of O(n).  Needs scratch the reference interface has no
+ * slot for: dispu_query_ball_point_workspace_bytes(b,n,m) bytes, any contents.  Falls back to the
+ * brute-force kernel for n < 2048 or workspace == NULL. */
+size_t dispu_query_ball_point_workspace_bytes(int b, int n, int m);
+int dispu_query_ball_point_ws(int b, int n, int m, const float *radius, int nsample, const float *xyz1,
+                              const float *xyz2, int *idx, int *pts_cnt, void *workspace, size_t workspace_bytes,
+                              dispu_stream_t stream);
+
 /* GroupPoint / GroupPointGrad.  groupPointLauncher tf_grouping.cpp:146 (kernel
  * tf_grouping_g.cu:40) and groupPointGradLauncher :177 (kernel :61; zero fill of
  * tf_grouping.cpp:208 done here). */

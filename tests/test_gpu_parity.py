@@ -133,6 +133,29 @@ def test_query_ball_point(rng, n, m, r, ns):
         assert np.array_equal(idx, ri.cpu().numpy())  # rows with cnt==0 were pre-zeroed above
 
 
+@pytest.mark.parametrize("n,m,r,ns,kind", [(16384, 4096, (32 / 16384) ** (1 / 3), 32, "ball"), (65536, 512, (32 / 65536) ** (1 / 3), 32, "ball"),
+                                           (3000, 300, 0.6, 16, "ball"),      # > 256 hits per query: serial fallback inside the grid kernel
+                                           (5000, 200, 0.25, 64, "lattice"),  # exact-boundary distances, duplicates
+                                           (2048, 64, 0.004, 8, "ball"),      # radius far below the cell floor (grid capped at 32^3)
+                                           (4000, 50, 3.0, 16, "ball")])      # radius larger than the cloud: one cell
+def test_query_ball_point_grid(rng, n, m, r, ns, kind):
+    b = 2
+    xyz = unit_ball(rng, b, n) if kind == "ball" else lattice(rng, b, n, q=12)
+    q = np.ascontiguousarray(xyz[:, rng.permutation(n)[:m]])
+    q[:, : m // 4] += rng.normal(0, 0.05, (b, m // 4, 3)).astype(np.float32)  # some queries off the cloud / outside the bbox
+    idx, cnt = G.query_ball_point(r, ns, T(xyz), T(q))
+    oi, oc = O.query_ball_point(r, ns, xyz, q)
+    assert np.array_equal(cnt.cpu().numpy(), oc)
+    assert np.array_equal(idx.cpu().numpy(), oi)
+    # the brute-force kernel (no workspace) agrees too
+    from dispu_b200._t import call, ptr, stream_ptr
+    i2 = torch.empty_like(idx); c2 = torch.empty_like(cnt)
+    rad = torch.full((b,), r, dtype=torch.float32, device=dev)
+    x1, x2 = T(xyz), T(q)
+    call("dispu_query_ball_point", b, n, m, ptr(rad), ns, ptr(x1), ptr(x2), ptr(i2), ptr(c2), stream_ptr())
+    assert torch.equal(i2, idx) and torch.equal(c2, cnt)
+
+
 def test_query_ball_point_empty_rows_and_radii(rng):
     xyz = unit_ball(rng, 2, 500)
     q = (unit_ball(rng, 2, 20) + np.float32(5.0)).astype(np.float32)  # far away: zero hits
