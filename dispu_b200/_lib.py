@@ -39,6 +39,8 @@ SIGNATURES = {
     "dispu_nn_distance_grad": ([_i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p], _i),
     "dispu_chamfer_workspace_bytes": ([_i, _i, _i], _sz),
     "dispu_chamfer": ([_i, _i, _p, _i, _p, _p, _p, _p, _p, _sz, _p], _i),
+    "dispu_repulsion_workspace_bytes": ([_i, _i], _sz),
+    "dispu_repulsion_loss": ([_i, _i, _i, C.c_float, _p, _p, _p, _p, _sz, _p], _i),
     "dispu_sa_mlp": ([_i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _p], _i),
 }
 

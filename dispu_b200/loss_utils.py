@@ -53,3 +53,20 @@ def hausdorff_loss(pred, gt, radius=1.0, forward_weight=1.0, threshold=None):
     if forward_weight != 1.0 or threshold is not None:
         raise NotImplementedError("the live call sites (DisPU/model.py:75-79) use the defaults")
     return chamfer_hausdorff(pred, gt, None if radius == 1.0 else radius)[1]
+
+
+def get_repulsion_loss(pred, nsample=20, radius=0.07, knn=False, use_l1=False, h=0.001, out=None):
+    """loss_utils.py:271-298 (the live call: DisPU/model.py:83, defaults).  pred (b,n,3) -> scalar tensor.
+    Ball query on the B200 kernel, then one fused pass (no (b,n,nsample,3) tensor, no top_k)."""
+    if knn or use_l1:
+        raise NotImplementedError("the live call site uses the ball-query / squared-distance form")
+    from .tf_grouping import query_ball_point
+    pred = req(pred, torch.float32, 3, "pred")
+    b, n, _ = pred.shape
+    idx, _ = query_ball_point(radius, nsample, pred, pred)
+    if out is None:
+        out = torch.empty((2,), dtype=torch.float32, device=pred.device)
+    nbytes = int(_lib.lib().dispu_repulsion_workspace_bytes(b, n))
+    ws = _workspace(nbytes, pred.device)
+    call("dispu_repulsion_loss", b, n, nsample, float(h), ptr(pred), ptr(idx), ptr(out), ptr(ws), ws.numel(), stream_ptr())
+    return out[0]

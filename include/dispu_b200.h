@@ -146,6 +146,14 @@ size_t dispu_chamfer_workspace_bytes(int b, int n_gt, int n_pred);
 int dispu_chamfer(int b, int n_gt, const float *gt, int n_pred, const float *pred, const float *radius,
                   float *out, float *per_cloud, void *workspace, size_t workspace_bytes, dispu_stream_t stream);
 
+/* Repulsion loss (Common/loss_utils.py:271-298, DisPU/model.py:83), fused after the ball query:
+ * idx (b,n,nsample) = QueryBallPoint(radius, nsample, pred, pred); per point the five smallest squared
+ * distances to its grouped points, drop the smallest, mean over (b,n,4) of max(0, h - d2).
+ * out[0] = mean, out[1] = sum (multi-GPU partial).  workspace: dispu_repulsion_workspace_bytes(b,n). */
+size_t dispu_repulsion_workspace_bytes(int b, int n);
+int dispu_repulsion_loss(int b, int n, int nsample, float h, const float *pred, const int *idx, float *out,
+                         void *workspace, size_t workspace_bytes, dispu_stream_t stream);
+
 /* ---- Common/pointnet_util.py set abstraction --------------------------------------------- */
 
 /* Fused group -> centre-subtract -> concat -> 1x1-conv MLP (bias, ReLU) -> max over nsample:

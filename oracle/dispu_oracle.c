@@ -21,7 +21,7 @@
  * (SURVEY.md §4/§8c).  This restatement is pinned instead against the reference's own code
  * compiled from /root/reference (oracle/build_ref.sh -> oracle/_ref/): the host loops
  * (nnsearch, threenn_cpu, threeinterpolate_cpu, query_ball_point_cpu, group_point_cpu,
- * nanoflann kNN) in tests/test_oracle_vs_ref.py on CPU, and the recompiled CUDA kernels
+ * nanoflann kNN) in tests/test_oracle.py on CPU, and the recompiled CUDA kernels
  * (FPS, ball query, group, NnDistance) in the -m gpu tests; fixtures generated that way are
  * committed under tests/golden/.
  */
@@ -452,6 +452,32 @@ int orc_sa_mlp(int b, int n, int m, int nsample, int c_pts, int layout, const fl
         }
     free(x);
     free(y);
+    return 0;
+}
+
+/* get_repulsion_loss — Common/loss_utils.py:271-298 with the live defaults (ball query, squared L2):
+ * per point the squared distances to its nsample grouped points (idx row, pad repeats included),
+ * top_k(-d2,5)[1:] = the 2nd..5th smallest, loss = mean over (b,n,4) of max(0, h - d2). */
+int orc_repulsion_loss(int b, int n, int nsample, float h, const float *pred, const int *idx, float *loss) {
+    double acc = 0.0;
+    float *d = (float *)malloc(sizeof(float) * (size_t)nsample);
+    if (!d) return -2;
+    for (int i = 0; i < b; ++i)
+        for (int j = 0; j < n; ++j) {
+            const float *c = pred + ((size_t)i * n + j) * 3;
+            for (int s = 0; s < nsample; ++s) {
+                const float *q = pred + ((size_t)i * n + idx[((size_t)i * n + j) * nsample + s]) * 3;
+                d[s] = d2_cpu(q[0] - c[0], q[1] - c[1], q[2] - c[2]);
+            }
+            for (int a = 0; a < 5 && a < nsample; ++a) { /* partial selection sort of the 5 smallest */
+                int mn = a;
+                for (int t = a + 1; t < nsample; ++t) if (d[t] < d[mn]) mn = t;
+                float tf = d[a]; d[a] = d[mn]; d[mn] = tf;
+            }
+            for (int a = 1; a < 5 && a < nsample; ++a) acc += (double)fmaxf(0.0f, h - d[a]);
+        }
+    free(d);
+    *loss = (float)(acc / ((double)b * n * 4));
     return 0;
 }
 

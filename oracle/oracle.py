@@ -221,6 +221,17 @@ def sa_mlp(xyz, points, new_xyz, idx, weights, biases, layout=0):
     return out
 
 
+def repulsion_loss(pred, idx, h=0.001):
+    """loss_utils.py:271-298 given the ball-query idx (b,n,nsample)."""
+    pred, idx = _f(pred), _i(idx)
+    b, n, _ = pred.shape
+    out = C.c_float()
+    lib().orc_repulsion_loss.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = lib().orc_repulsion_loss(b, n, idx.shape[2], float(h), _p(pred), _p(idx), C.byref(out))
+    assert rc == 0, rc
+    return np.float32(out.value)
+
+
 def selection_sort(dist, k):
     dist = _f(dist)
     b, m, n = dist.shape

@@ -288,6 +288,21 @@ def test_chamfer(rng, b, n_gt, n_pred):
     assert np.array_equal(out, out2)
 
 
+def test_repulsion_loss(rng):
+    """fused repulsion loss vs the oracle and vs the unfused op sequence."""
+    b, n = 4, 1024
+    pred = (unit_ball(rng, b, n) * np.float32(0.5)).astype(np.float32)
+    got = float(LU.get_repulsion_loss(T(pred), nsample=20, radius=0.07, h=0.001))
+    idx, _ = O.query_ball_point(0.07, 20, pred, pred)
+    want = float(O.repulsion_loss(pred, idx, 0.001))
+    assert got == pytest.approx(want, rel=1e-5)
+    g = G.group_point(T(pred), T(idx)) - T(pred).unsqueeze(2)
+    val = torch.topk(-(g ** 2).sum(-1), 5)[0][:, :, 1:]
+    unfused = float(torch.clamp(0.001 + val, min=0).mean())
+    assert got == pytest.approx(unfused, rel=1e-5)
+    assert got > 0
+
+
 # ---------------------------------------------------------------- set abstraction
 @pytest.mark.parametrize("c_pts,mlp,ns,layout", [(0, [32, 32, 64], 32, 0), (64, [64, 64, 128], 32, 0), (5, [16], 16, 1),
                                                  (7, [24, 9], 24, 0), (0, [8, 8], 200, 0)])
@@ -429,3 +444,46 @@ def test_sa_mlp_tc_c3_shapes(rng):
     assert np.array_equal(idx2.cpu().numpy(), o_idx2)
     want2 = O.sa_mlp(o_new, f1.cpu().numpy(), o_new2, o_idx2, [w for w, _ in l2], [c for _, c in l2], 0)
     np.testing.assert_allclose(f2.cpu().numpy(), want2, rtol=2e-5, atol=2e-5)
+
+
+# ---------------------------------------------------------------- committed golden fixtures (reference code outputs)
+import os as _os  # noqa: E402
+
+_GOLD = _os.path.join(_os.path.dirname(__file__), "golden")
+
+
+def test_cuda_path_against_reference_gpu_goldens():
+    """tests/golden/ref_gpu.npz: outputs of the reference's own CUDA kernels (run on a B200) on ref_cpu.npz's inputs."""
+    gi = np.load(_os.path.join(_GOLD, "ref_cpu.npz"))
+    gg = np.load(_os.path.join(_GOLD, "ref_gpu.npz"))
+    assert np.array_equal(S.farthest_point_sample(150, T(gi["ball_a"])).cpu().numpy(), gg["ball_fps150"])
+    assert np.array_equal(S.farthest_point_sample(200, T(gi["lat_a"])).cpu().numpy(), gg["lat_fps200"])
+    assert np.array_equal(S.farthest_point_sample(64, T(gi["big"])).cpu().numpy(), gg["big_fps64"])
+    assert np.array_equal(S.farthest_point_sample(200, T(gi["ball_b"])).cpu().numpy(), gg["ballb_fps200"])
+    for tag in ("ball", "lat"):
+        a, q = T(gi[f"{tag}_a"]), T(gi[f"{tag}_b"])
+        for r, ns in ((0.3, 16), (0.12, 8)):
+            idx, cnt = G.query_ball_point(r, ns, a, q)
+            assert np.array_equal(cnt.cpu().numpy(), gg[f"{tag}_qbp_r{r}_ns{ns}_cnt"])
+            assert np.array_equal(idx.cpu().numpy(), gg[f"{tag}_qbp_r{r}_ns{ns}_idx"])
+        d1, i1, d2, i2 = N.nn_distance(a, q)
+        assert np.array_equal(d1.cpu().numpy(), gg[f"{tag}_nn_d1"]) and np.array_equal(i1.cpu().numpy(), gg[f"{tag}_nn_i1"])
+        assert np.array_equal(d2.cpu().numpy(), gg[f"{tag}_nn_d2"]) and np.array_equal(i2.cpu().numpy(), gg[f"{tag}_nn_i2"])
+
+
+def test_cuda_path_against_reference_cpu_goldens():
+    """tests/golden/ref_cpu.npz: outputs of the reference host loops (threenn_cpu, threeinterpolate_cpu,
+    group_point_cpu, nanoflann kNN).  The GPU ops for these follow the host arithmetic bit for bit."""
+    gi = np.load(_os.path.join(_GOLD, "ref_cpu.npz"))
+    for tag in ("ball", "lat"):
+        d, i = I.three_nn(T(gi[f"{tag}_a"]), T(gi[f"{tag}_b"]))
+        assert np.array_equal(d.cpu().numpy(), gi[f"{tag}_3nn_d"]) and np.array_equal(i.cpu().numpy(), gi[f"{tag}_3nn_i"])
+    out = I.three_interpolate(T(gi["feat_b"]), T(gi["ball_3nn_i"]), T(gi["ball_3nn_w"]))
+    assert np.array_equal(out.cpu().numpy(), gi["ball_interp"])
+    assert np.array_equal(G.group_point(T(gi["feat_a"]), T(gi["ball_group_idx"])).cpu().numpy(), gi["ball_group"])
+    _, ki = G.knn(16, T(gi["ball_a"]), T(gi["ball_a"]))
+    assert np.array_equal(ki.cpu().numpy(), gi["ball_knn16"])  # == nanoflann on distinct distances
+    # NnDistance CPU op (nnsearch): same argmin; distances equal up to the FMA contraction (GPU vs host)
+    d1, i1, d2, i2 = N.nn_distance(T(gi["ball_a"]), T(gi["ball_b"]))
+    assert np.array_equal(i1.cpu().numpy(), gi["ball_nn_i1"]) and np.array_equal(i2.cpu().numpy(), gi["ball_nn_i2"])
+    np.testing.assert_allclose(d1.cpu().numpy(), gi["ball_nn_d1"], rtol=1e-5, atol=1e-9)

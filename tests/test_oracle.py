@@ -185,3 +185,12 @@ def test_selection_sort_known_answer():
     outi, out = O.selection_sort(dist, 3)
     assert (outi[..., :3] == np.array([3, 2, 1])).all()
     assert np.array_equal(out[..., :3], np.sort(dist, -1)[..., :3])
+
+
+def test_repulsion_loss_against_numpy(rng):
+    pred = (unit_ball(rng, 2, 300) * np.float32(0.4)).astype(np.float32)
+    idx, _ = O.query_ball_point(0.07, 20, pred, pred)
+    g = O.group_point(pred, idx) - pred[:, :, None, :]
+    d = np.sort((g.astype(np.float64) ** 2).sum(-1), axis=-1)[:, :, 1:5]
+    want = np.maximum(0.0, 0.001 - d).mean()
+    np.testing.assert_allclose(O.repulsion_loss(pred, idx, 0.001), want, rtol=1e-5)
