@@ -29,6 +29,8 @@ SIGNATURES = {
     "dispu_query_ball_point_ws": ([_i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _sz, _p], _i),
     "dispu_group_point": ([_i, _i, _i, _i, _i, _p, _p, _p, _p], _i),
     "dispu_group_point_grad": ([_i, _i, _i, _i, _i, _p, _p, _p, _p], _i),
+    "dispu_group_max": ([_i, _i, _i, _i, _i, _p, _p, _p, _p], _i),
+    "dispu_group_affine_relu": ([_i, _i, _i, _i, _i, _p, _p, C.c_float, _p, _p, _p], _i),
     "dispu_selection_sort": ([_i, _i, _i, _i, _p, _p, _p, _p], _i),
     "dispu_knn": ([_i, _i, _i, _i, _p, _p, _p, _p, _p], _i),
     "dispu_three_nn": ([_i, _i, _i, _p, _p, _p, _p, _p], _i),

@@ -119,6 +119,70 @@ three_nn_weights_kernel(long long rows, const float *__restrict__ dist, float *_
     }
 }
 
+
+// Fused GroupPoint + centre term + ReLU:  out[b,i,s,:] = relu(P[b,idx[b,i,s],:] + sign * Q[b,i,:]).
+// This is the first layer of a grouped MLP after hoisting it to per-point GEMMs: for grouped input
+// [x_j - x_i, x_j, f_j] and weights [Wa; Wb; Wc],  row.W + b = (x_j(Wa+Wb) + f_j Wc + b) - x_i Wa = P[j] - Q[i]
+// (Common/ops.py:1033-1058 PointShuffle2 conv0; :1897-1905 dense_conv l0).  The (b,m,ns,C_in) grouped /
+// concatenated tensors of the reference are never written.
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+group_affine_relu_kernel(long long total_vec, int m_ns, int ns, int n, int c_vec, float sign,
+                         const float *__restrict__ P, const float *__restrict__ Q, const int *__restrict__ idx,
+                         float *__restrict__ out) {
+    for (long long e = (long long)blockIdx.x * kThreads + threadIdx.x; e < total_vec;
+         e += (long long)gridDim.x * kThreads) {
+        const long long row = e / c_vec;  // (b, i, s)
+        const int l = (int)(e - row * c_vec);
+        const long long cloud = row / m_ns;
+        const long long grp = row / ns;   // (b, i)
+        const int ii = __ldg(idx + row);
+        const long long ps = (cloud * n + ii) * (long long)c_vec + l;
+        const long long qs = grp * (long long)c_vec + l;
+        if (VEC == 4) {
+            const float4 p = __ldg(reinterpret_cast<const float4 *>(P) + ps);
+            const float4 q = Q ? __ldg(reinterpret_cast<const float4 *>(Q) + qs) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 o;
+            o.x = fmaxf(__fmaf_rn(sign, q.x, p.x), 0.f);
+            o.y = fmaxf(__fmaf_rn(sign, q.y, p.y), 0.f);
+            o.z = fmaxf(__fmaf_rn(sign, q.z, p.z), 0.f);
+            o.w = fmaxf(__fmaf_rn(sign, q.w, p.w), 0.f);
+            reinterpret_cast<float4 *>(out)[e] = o;
+        } else {
+            const float q = Q ? __ldg(Q + qs) : 0.f;
+            out[e] = fmaxf(__fmaf_rn(sign, q, __ldg(P + ps)), 0.f);
+        }
+    }
+}
+
+// Fused GroupPoint + reduce_max over nsample:  out[b,i,:] = max_s points[b,idx[b,i,s],:]
+// (e.g. the skip connection of PointShuffle2, Common/ops.py:1049: reduce_max(grouped_feat, axis=2)).
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+group_max_kernel(long long total_vec, int m, int ns, int n, int c_vec, const float *__restrict__ points,
+                 const int *__restrict__ idx, float *__restrict__ out) {
+    for (long long e = (long long)blockIdx.x * kThreads + threadIdx.x; e < total_vec;
+         e += (long long)gridDim.x * kThreads) {
+        const long long grp = e / c_vec;  // (b, i)
+        const int l = (int)(e - grp * c_vec);
+        const long long cloud = grp / m;
+        const int *row = idx + grp * ns;
+        if (VEC == 4) {
+            const float4 *p4 = reinterpret_cast<const float4 *>(points);
+            float4 mx = __ldg(p4 + (cloud * n + __ldg(row)) * (long long)c_vec + l);
+            for (int s = 1; s < ns; ++s) {
+                const float4 v = __ldg(p4 + (cloud * n + __ldg(row + s)) * (long long)c_vec + l);
+                mx.x = fmaxf(mx.x, v.x); mx.y = fmaxf(mx.y, v.y); mx.z = fmaxf(mx.z, v.z); mx.w = fmaxf(mx.w, v.w);
+            }
+            reinterpret_cast<float4 *>(out)[e] = mx;
+        } else {
+            float mx = __ldg(points + (cloud * n + __ldg(row)) * (long long)c_vec + l);
+            for (int s = 1; s < ns; ++s) mx = fmaxf(mx, __ldg(points + (cloud * n + __ldg(row + s)) * (long long)c_vec + l));
+            out[e] = mx;
+        }
+    }
+}
+
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 static int gather_rows(int b, int n, int c, long long rows_per_cloud, const float *src, const int *idx, float *out,
@@ -222,5 +286,43 @@ extern "C" int dispu_three_nn_weights(int b, int n, const float *dist, float *we
     DISPU_REQUIRE(dist && weight, DISPU_ENULL);
     count_launch();
     three_nn_weights_kernel<<<grid_for(rows), kThreads, 0, (cudaStream_t)stream>>>(rows, dist, weight);
+    return finish_launch();
+}
+
+extern "C" int dispu_group_affine_relu(int b, int n, int c, int m, int nsample, const float *P, const float *Q,
+                                       float sign, const int *idx, float *out, dispu_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DISPU_REQUIRE(b >= 0 && n > 0 && c >= 0 && m >= 0 && nsample >= 0, DISPU_EINVAL);
+    if (b == 0 || m == 0 || nsample == 0 || c == 0) return DISPU_OK;
+    DISPU_REQUIRE(P && idx && out, DISPU_ENULL);
+    const long long rows = (long long)b * m * nsample;
+    count_launch();
+    if (c % 4 == 0 && aligned16(P) && aligned16(out) && (!Q || aligned16(Q))) {
+        const long long total = rows * (c / 4);
+        group_affine_relu_kernel<4><<<grid_for(total), kThreads, 0, stream>>>(total, m * nsample, nsample, n, c / 4, sign, P, Q,
+                                                                            idx, out);
+    } else {
+        const long long total = rows * c;
+        group_affine_relu_kernel<1><<<grid_for(total), kThreads, 0, stream>>>(total, m * nsample, nsample, n, c, sign, P, Q, idx,
+                                                                            out);
+    }
+    return finish_launch();
+}
+
+extern "C" int dispu_group_max(int b, int n, int c, int m, int nsample, const float *points, const int *idx, float *out,
+                               dispu_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DISPU_REQUIRE(b >= 0 && n > 0 && c >= 0 && m >= 0 && nsample > 0, DISPU_EINVAL);
+    if (b == 0 || m == 0 || c == 0) return DISPU_OK;
+    DISPU_REQUIRE(points && idx && out, DISPU_ENULL);
+    const long long groups = (long long)b * m;
+    count_launch();
+    if (c % 4 == 0 && aligned16(points) && aligned16(out)) {
+        const long long total = groups * (c / 4);
+        group_max_kernel<4><<<grid_for(total), kThreads, 0, stream>>>(total, m, nsample, n, c / 4, points, idx, out);
+    } else {
+        const long long total = groups * c;
+        group_max_kernel<1><<<grid_for(total), kThreads, 0, stream>>>(total, m, nsample, n, c, points, idx, out);
+    }
     return finish_launch();
 }

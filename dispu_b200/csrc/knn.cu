@@ -82,6 +82,283 @@ knn_kernel(int n, int m, int k, const float *__restrict__ data, const float *__r
     }
 }
 
+
+// ---- selection kernel (k <= 32): no insertion in the common case -------------------------------------------
+// A warp owns one query and takes the dataset in chunks of 1024 candidates, 32 per lane, whose squared
+// distances stay in registers.  Threshold by LANE MINIMA: sort the 32 per-lane minima across the warp
+// (bitonic, shuffles); the k-th smallest of them, M, bounds the k-th smallest distance of the chunk from
+// above (k different lanes each hold a value <= M).  Every candidate with d <= tau = min(M, carried k-th
+// best) is compacted into a small shared-memory buffer by ballot (about 32(H32-H16) ~ 22 survivors for
+// k = 16), the carried list joins it, and the survivors are ordered by rank-counting on the (d, idx) key —
+// ties to the lower index, the order of tf.nn.top_k.  A query whose survivors overflow the
+// buffer (masses of exactly equal distances) is redone with the ballot-ranked insertion scan.
+constexpr int kKsWarps = 8;
+constexpr int kKsChunk = 1024;
+constexpr int kKsQueriesPerWarp = 4;
+constexpr int kKsCap = 128;
+
+__device__ __forceinline__ float warp_sort32_asc(float v, int lane) {
+#pragma unroll
+    for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+#pragma unroll
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            const float o = __shfl_xor_sync(kFull, v, j);
+            const bool up = (lane & k2) == 0, lower = (lane & j) == 0;
+            v = (lower == up) ? fminf(v, o) : fmaxf(v, o);
+        }
+    }
+    return v;
+}
+
+// Slow exact path for one query: serial definition with a lane-distributed sorted list (32 entries).
+__device__ __noinline__ void knn_insertion_scan(int n, int k, const float *__restrict__ pts, float qx, float qy, float qz,
+                                                int lane, float &ld, int &li) {
+    const float inf = __int_as_float(0x7f800000);
+    ld = inf; li = 0;
+    float tau = inf;
+    for (int c0 = 0; c0 < n; c0 += 32) {
+        const int c = c0 + lane;
+        float d = inf;
+        if (c < n) d = d2_ref_cpu(__fsub_rn(qx, __ldg(pts + (size_t)c * 3)), __fsub_rn(qy, __ldg(pts + (size_t)c * 3 + 1)),
+                                  __fsub_rn(qz, __ldg(pts + (size_t)c * 3 + 2)));
+        unsigned vote = __ballot_sync(kFull, c < n && d < tau);
+        while (vote) {
+            const int src = __ffs(vote) - 1;
+            vote &= vote - 1;
+            const float dn = __shfl_sync(kFull, d, src);
+            if (!(dn < tau)) continue;
+            const int pos = __popc(__ballot_sync(kFull, ld <= dn));
+            const float pd = __shfl_up_sync(kFull, ld, 1);
+            const int pi = __shfl_up_sync(kFull, li, 1);
+            if (lane > pos) { ld = pd; li = pi; }
+            if (lane == pos) { ld = dn; li = c0 + src; }
+            tau = __shfl_sync(kFull, ld, k - 1);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kKsWarps * 32)
+knn_select_kernel(int n, int m, int k, const float *__restrict__ data, const float *__restrict__ query,
+                  float *__restrict__ dist, int *__restrict__ idx) {
+    __shared__ float4 s_tile[kKsChunk];
+    __shared__ float s_bd[kKsWarps][kKsCap];
+    __shared__ int s_bi[kKsWarps][kKsCap];
+    __shared__ float s_od[kKsWarps][32];
+    __shared__ int s_oi[kKsWarps][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cloud = blockIdx.y;
+    const float *pts = data + (size_t)cloud * n * 3;
+    const int q0 = (blockIdx.x * kKsWarps + warp) * kKsQueriesPerWarp;
+    const float inf = __int_as_float(0x7f800000);
+    const unsigned lt_mask = (1u << lane) - 1u;
+    float *bd = s_bd[warp];
+    int *bi = s_bi[warp];
+
+    float ld[kKsQueriesPerWarp];  // carried list: lane j holds the j-th best so far
+    int li[kKsQueriesPerWarp];
+    bool overflow[kKsQueriesPerWarp];
+    float qx[kKsQueriesPerWarp], qy[kKsQueriesPerWarp], qz[kKsQueriesPerWarp];
+#pragma unroll
+    for (int u = 0; u < kKsQueriesPerWarp; ++u) {
+        ld[u] = inf; li[u] = 0; overflow[u] = false;
+        const int j = min(q0 + u, m - 1);
+        const float *q = query + ((size_t)cloud * m + j) * 3;
+        qx[u] = __ldg(q); qy[u] = __ldg(q + 1); qz[u] = __ldg(q + 2);
+    }
+    for (int t0 = 0; t0 < n; t0 += kKsChunk) {
+        const int tn = min(kKsChunk, n - t0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < tn; e += kKsWarps * 32) {
+            const float *p = pts + (size_t)(t0 + e) * 3;
+            s_tile[e] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
+        }
+        __syncthreads();
+        if (q0 >= m) continue;
+#pragma unroll 1
+        for (int u = 0; u < kKsQueriesPerWarp; ++u) {
+            if (overflow[u]) continue;
+            if (t0 > 0) {
+                // later chunks: the carried list is already tight (expected k*ln(n/1024) improvements in total),
+                // so a threshold-gated step per 32 candidates with ballot-ranked insertion is cheaper than
+                // another selection round
+                float tau_u = __shfl_sync(kFull, ld[u], k - 1);
+                for (int c0 = 0; c0 < tn; c0 += 32) {
+                    const int c = c0 + lane;
+                    float dv = inf;
+                    if (c < tn) {
+                        const float4 p = s_tile[c];
+                        dv = d2_ref_cpu(__fsub_rn(qx[u], p.x), __fsub_rn(qy[u], p.y), __fsub_rn(qz[u], p.z));
+                    }
+                    unsigned vote = __ballot_sync(kFull, dv < tau_u);
+                    while (vote) {
+                        const int src = __ffs(vote) - 1;
+                        vote &= vote - 1;
+                        const float dn = __shfl_sync(kFull, dv, src);
+                        if (!(dn < tau_u)) continue;
+                        const int pos = __popc(__ballot_sync(kFull, ld[u] <= dn));
+                        const float pd = __shfl_up_sync(kFull, ld[u], 1);
+                        const int pi = __shfl_up_sync(kFull, li[u], 1);
+                        if (lane > pos) { ld[u] = pd; li[u] = pi; }
+                        if (lane == pos) { ld[u] = dn; li[u] = t0 + c0 + src; }
+                        tau_u = __shfl_sync(kFull, ld[u], k - 1);
+                    }
+                }
+                continue;
+            }
+            // 32 candidates per lane: c = s*32 + lane (conflict-free LDS.128), distances in registers
+            float d[32];
+            float lmin = inf;
+#pragma unroll
+            for (int sI = 0; sI < 32; ++sI) {
+                const int c = sI * 32 + lane;
+                float v = inf;
+                if (c < tn) {
+                    const float4 p = s_tile[c];
+                    // diff = query - data, accumulated dimension by dimension (nanoflann.hpp:323-348)
+                    v = d2_ref_cpu(__fsub_rn(qx[u], p.x), __fsub_rn(qy[u], p.y), __fsub_rn(qz[u], p.z));
+                }
+                d[sI] = v;
+                lmin = fminf(lmin, v);
+            }
+            const float sorted_min = warp_sort32_asc(lmin, lane);
+            const float M = __shfl_sync(kFull, sorted_min, k - 1);
+            const float tau_carry = __shfl_sync(kFull, ld[u], k - 1);
+            const float tau = fminf(M, tau_carry);
+            // survivors: carried entries first, then this chunk's candidates, all with d <= tau
+            int S = 0;
+            {
+                const bool keep = ld[u] <= tau && ld[u] < inf;
+                const unsigned mask = __ballot_sync(kFull, keep);
+                if (keep) { const int pos = __popc(mask & lt_mask); bd[pos] = ld[u]; bi[pos] = li[u]; }
+                S = __popc(mask);
+            }
+#pragma unroll
+            for (int sI = 0; sI < 32; ++sI) {
+                const bool keep = d[sI] <= tau && d[sI] < inf;
+                const unsigned mask = __ballot_sync(kFull, keep);
+                if (mask) {
+                    const int pos = S + __popc(mask & lt_mask);
+                    if (keep && pos < kKsCap) { bd[pos] = d[sI]; bi[pos] = t0 + sI * 32 + lane; }
+                    S += __popc(mask);
+                }
+            }
+            __syncwarp();
+            if (S > kKsCap) { overflow[u] = true; continue; }
+            // rank by counting on the (d, idx) key; ranks < 32 become the new carried list
+            for (int e0 = 0; e0 < S; e0 += 32) {
+                const int e = e0 + lane;
+                const float de = e < S ? bd[e] : inf;
+                const int ie = e < S ? bi[e] : 0x7fffffff;
+                int rank = 0;
+                for (int f = 0; f < S; ++f) {
+                    const float df = bd[f];
+                    const int jf = bi[f];
+                    rank += (df < de) || (df == de && jf < ie);
+                }
+                if (e < S && rank < 32) {  // ranks are a permutation of 0..S-1: hand element e to lane `rank`
+                    s_od[warp][rank] = de;
+                    s_oi[warp][rank] = ie;
+                }
+            }
+            __syncwarp();
+            const int have = min(S, 32);
+            ld[u] = lane < have ? s_od[warp][lane] : inf;
+            li[u] = lane < have ? s_oi[warp][lane] : 0;
+            __syncwarp();
+        }
+    }
+#pragma unroll 1
+    for (int u = 0; u < kKsQueriesPerWarp; ++u) {
+        const int j = q0 + u;
+        if (j >= m) continue;
+        if (overflow[u]) knn_insertion_scan(n, k, pts, qx[u], qy[u], qz[u], lane, ld[u], li[u]);
+        if (lane < k) {
+            const size_t o = ((size_t)cloud * m + j) * k + lane;
+            if (dist) dist[o] = ld[u];
+            idx[o] = li[u];
+        }
+    }
+}
+
+// ---- warp-per-query kernel (k <= 32) -----------------------------------------------------------------
+// The thread-per-query kernel above pays its 75-instruction sorted insertion on every candidate for which
+// ANY of a warp's 32 queries improves — i.e. almost always.  Here a warp owns ONE query: each lane
+// tests one candidate per step against the warp-uniform threshold tau (= current k-th best), so the
+// common step is 13 instructions and an insertion happens only for a genuine improvement
+// (~k(1+ln(n/k)) times per query).  The running list is distributed over the lanes (lane j holds the
+// j-th best (d, idx), ascending, 32 entries), an insertion is a ballot-ranked shift by one lane.
+// Candidates are taken in ascending index inside a step (lowest lane first) and only on strict
+// improvement, so equal distances keep the lower index first — the order of tf.nn.top_k.
+constexpr int kKwWarps = 8;
+constexpr int kKwTile = 2048;        // float4 candidates per shared-memory tile
+constexpr int kKwQueriesPerWarp = 4; // queries a warp processes against each tile load
+
+__global__ void __launch_bounds__(kKwWarps * 32)
+knn_warp_kernel(int n, int m, int k, const float *__restrict__ data, const float *__restrict__ query,
+                float *__restrict__ dist, int *__restrict__ idx) {
+    __shared__ float4 s_tile[kKwTile];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cloud = blockIdx.y;
+    const float *pts = data + (size_t)cloud * n * 3;
+    const int q0 = (blockIdx.x * kKwWarps + warp) * kKwQueriesPerWarp;
+    const float inf = __int_as_float(0x7f800000);
+
+    float ld[kKwQueriesPerWarp];
+    int li[kKwQueriesPerWarp];
+    float tau[kKwQueriesPerWarp], qx[kKwQueriesPerWarp], qy[kKwQueriesPerWarp], qz[kKwQueriesPerWarp];
+#pragma unroll
+    for (int u = 0; u < kKwQueriesPerWarp; ++u) {
+        ld[u] = inf; li[u] = 0; tau[u] = inf;
+        const int j = min(q0 + u, m - 1);
+        const float *q = query + ((size_t)cloud * m + j) * 3;
+        qx[u] = __ldg(q); qy[u] = __ldg(q + 1); qz[u] = __ldg(q + 2);
+    }
+    for (int t0 = 0; t0 < n; t0 += kKwTile) {
+        const int tn = min(kKwTile, n - t0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < tn; e += kKwWarps * 32) {
+            const float *p = pts + (size_t)(t0 + e) * 3;
+            s_tile[e] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
+        }
+        __syncthreads();
+        if (q0 < m) {
+            for (int c0 = 0; c0 < tn; c0 += 32) {
+                const int c = c0 + lane;
+                const bool cvalid = c < tn;
+                const float4 p = s_tile[cvalid ? c : 0];
+#pragma unroll
+                for (int u = 0; u < kKwQueriesPerWarp; ++u) {
+                    // diff = query - data, accumulated dimension by dimension (nanoflann.hpp:323-348)
+                    const float d = d2_ref_cpu(__fsub_rn(qx[u], p.x), __fsub_rn(qy[u], p.y), __fsub_rn(qz[u], p.z));
+                    unsigned vote = __ballot_sync(kFull, cvalid && d < tau[u]);
+                    while (vote) {
+                        const int src = __ffs(vote) - 1;
+                        vote &= vote - 1;
+                        const float dn = __shfl_sync(kFull, d, src);
+                        if (!(dn < tau[u])) continue;  // tau shrank since the vote
+                        const int in = t0 + c0 + src;
+                        const int pos = __popc(__ballot_sync(kFull, ld[u] <= dn));  // equal distances: earlier index stays first
+                        const float pd = __shfl_up_sync(kFull, ld[u], 1);
+                        const int pi = __shfl_up_sync(kFull, li[u], 1);
+                        if (lane > pos) { ld[u] = pd; li[u] = pi; }
+                        if (lane == pos) { ld[u] = dn; li[u] = in; }
+                        tau[u] = __shfl_sync(kFull, ld[u], k - 1);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < kKwQueriesPerWarp; ++u) {
+        const int j = q0 + u;
+        if (j < m && lane < k) {
+            const size_t o = ((size_t)cloud * m + j) * k + lane;
+            if (dist) dist[o] = ld[u];
+            idx[o] = li[u];
+        }
+    }
+}
+
 // The KT-slot list holds the KT smallest; the first k of them are the k smallest, so running
 // with KT >= k is exact.
 template <int KT>
@@ -155,6 +432,12 @@ extern "C" int dispu_knn(int b, int n, int m, int k, const float *xyz1, const fl
     if (b == 0 || m == 0) return DISPU_OK;
     DISPU_REQUIRE(xyz1 && xyz2 && idx, DISPU_ENULL);
     DISPU_REQUIRE(b <= 65535, DISPU_EUNSUPPORTED);
+    if (k <= 32) {
+        count_launch();
+        knn_select_kernel<<<dim3(ceil_div(m, kKsWarps * kKsQueriesPerWarp), b), kKsWarps * 32, 0, stream>>>(n, m, k, xyz1, xyz2,
+                                                                                                  dist, idx);
+        return finish_launch();
+    }
     if (k <= 4) return launch_knn<4>(b, n, m, k, xyz1, xyz2, dist, idx, stream);
     if (k <= 8) return launch_knn<8>(b, n, m, k, xyz1, xyz2, dist, idx, stream);
     if (k <= 16) return launch_knn<16>(b, n, m, k, xyz1, xyz2, dist, idx, stream);

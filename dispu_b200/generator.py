@@ -44,6 +44,14 @@ class DispuOps:
         d = r - 2.0 * torch.bmm(feat, feat.transpose(1, 2)) + r.transpose(1, 2)
         return torch.topk(-d, k, dim=2, sorted=True)[1].to(torch.int32)
 
+    # fused forms of GroupPoint (no (b,m,k,c) intermediates); their presence switches the generator to the
+    # hoisted formulation of the first grouped layer (see Generator._dense_conv / point_shuffle)
+    def group_max(self, feature, idx):
+        return tf_grouping.group_max(feature, idx)
+
+    def group_affine_relu(self, P, Q, idx, sign):
+        return tf_grouping.group_affine_relu(P, Q, idx, sign)
+
 
 def _xavier(gen, cin, cout, device, fan_in=None, fan_out=None):
     fi = cin if fan_in is None else fan_in
@@ -56,8 +64,9 @@ def _xavier(gen, cin, cout, device, fan_in=None, fan_out=None):
 class Generator:
     """coarse, fine = G(inputs (b,n,3)); up_ratio 4: (b,4n,3) each."""
 
-    def __init__(self, up_ratio=4, device="cuda", seed=7, ops=None):
+    def __init__(self, up_ratio=4, device="cuda", seed=7, ops=None, hoist=True):
         self.up_ratio = up_ratio
+        self.hoist = hoist  # use the fused / hoisted grouped-layer formulation when the backend offers it
         self.device = torch.device(device)
         self.ops = ops if ops is not None else DispuOps()
         g = torch.Generator().manual_seed(seed)
@@ -113,8 +122,33 @@ class Generator:
                 y = torch.relu_(y)
         return y.view(*x.shape[:-1], w.shape[1])
 
+    def _dense_conv_hoisted(self, feature, blk, k=16):
+        """Same function as _dense_conv with every term that does not depend on the neighbour hoisted to ONE
+        per-point GEMM (exact reassociation of the 1x1 convs over concat[central, neigh-central | y | central]):
+            y0 = relu(neigh.W0e + central.(W0c-W0e) + b0)         -> fused gather + centre term + ReLU kernel
+            y1 = relu(y0.W1a + (central.W1c + b1))
+            y2 =      y1.W2a + y0.W2b + (central.W2c + b2)
+        so neither the tiled `central` nor any concatenated (b,n,k,*) tensor is materialised."""
+        c = feature.shape[-1]
+        (w0, b0), (w1, b1), (w2, b2) = (self.P[f"layer{blk}_l{i}"] for i in range(3))
+        key = f"_hoist{blk}"
+        if key not in self.P:
+            wcat = torch.cat([w0[c:], w0[:c] - w0[c:], w1[24:], w2[48:]], dim=1).contiguous()  # (c, 96)
+            bcat = torch.cat([torch.zeros_like(b0), b0, b1, b2]).contiguous()
+            self.P[key] = (wcat, bcat, w1[:24].contiguous(), w2[:24].contiguous(), w2[24:48].contiguous())
+        wcat, bcat, w1a, w2a, w2b = self.P[key]
+        idx = self.ops.feature_knn(k + 1, feature)[:, :, 1:].contiguous()
+        proj = torch.addmm(bcat, feature.reshape(-1, c), wcat).view(*feature.shape[:2], 96)
+        pn, pc, t1, t2 = (proj[..., i * 24:(i + 1) * 24].contiguous() for i in range(4))
+        y0 = self.ops.group_affine_relu(pn, pc, idx, 1.0)  # (b,n,k,24)
+        y1 = torch.relu_(torch.matmul(y0, w1a) + t1.unsqueeze(2))
+        y2 = torch.matmul(y1, w2a) + torch.matmul(y0, w2b) + t2.unsqueeze(2)
+        return torch.cat([y2.max(dim=2)[0], y1.max(dim=2)[0], y0.max(dim=2)[0], feature], dim=-1)
+
     def _dense_conv(self, feature, blk, k=16):
         """ops.py:1897-1915 on (b,n,c) -> (b,n,72+c)."""
+        if hasattr(self.ops, "group_affine_relu") and self.hoist:
+            return self._dense_conv_hoisted(feature, blk, k)
         idx = self.ops.feature_knn(k + 1, feature)[:, :, 1:].contiguous()  # drop self, ops.py:1867-1868
         neigh = self.ops.group(feature, idx)  # (b,n,k,c)
         central = feature.unsqueeze(2).expand(-1, -1, k, -1)
@@ -152,20 +186,36 @@ class Generator:
         """PointShuffle2 ops.py:1012-1087 with mlp=[128,128,256], kNN grouping, NL + Local."""
         b, m, c = feature.shape
         idx = self.ops.knn3d(nsample, xyz, xyz)  # ops.py:165 (nanoflann in the reference)
+        hoist = hasattr(self.ops, "group_affine_relu") and self.hoist
         grouped_xyz_raw = self.ops.group(xyz, idx)
-        grouped_feature = torch.cat([grouped_xyz_raw, self.ops.group(feature, idx)], dim=-1)  # 131
         grouped_xyz = grouped_xyz_raw - xyz.unsqueeze(2)
-        grouped_feat = torch.cat([grouped_xyz, grouped_feature], dim=-1)  # 134
+        if not hoist:
+            grouped_feature = torch.cat([grouped_xyz_raw, self.ops.group(feature, idx)], dim=-1)  # 131
+            grouped_feat = torch.cat([grouped_xyz, grouped_feature], dim=-1)  # 134
         # non-local cell
         kv = self._fc(feature, "nl_kv", act=False)
         key, val = kv[..., :64], kv[..., 64:]
         q = self._fc(feature, "nl_query", act=False)
         att = torch.softmax(torch.bmm(q, key.transpose(1, 2)) / math.sqrt(64.0), dim=-1)
         nonlocal_pt = self._fc(torch.bmm(att, val), "nl_back")
-        # skip
-        skip = self._fc(grouped_feat.max(dim=2)[0], "skip")
-        # local cell
-        gf = self._fc(self._fc(grouped_feat, "conv0"), "conv1")  # (b,m,s,128)
+        if hoist:
+            # grouped row = [x_j - x_i, x_j, f_j]; conv0 row.W + b = (x_j(Wa+Wb) + f_j Wc + b) - x_i Wa = P[j] - Q[i]:
+            # one per-point GEMM, then the fused gather + centre term + ReLU kernel; the 131/134-channel grouped
+            # tensors of ops.py:1033-1036 are never built.  max_s commutes with "- x_i" exactly.
+            w0, b0 = self.P["conv0"]
+            if "_hoist_ps" not in self.P:
+                self.P["_hoist_ps"] = (torch.cat([w0[0:3] + w0[3:6], w0[6:]], dim=0).contiguous(), w0[0:3].contiguous())
+            wp, wa = self.P["_hoist_ps"]
+            xf = torch.cat([xyz, feature], dim=-1)  # (b,m,131) per point
+            pm = torch.addmm(b0, xf.reshape(-1, 131), wp).view(b, m, 128)
+            qm = torch.matmul(xyz, wa)
+            y0 = self.ops.group_affine_relu(pm, qm, idx, -1.0)  # relu(conv0): (b,m,s,128)
+            gf = self._fc(y0, "conv1")
+            mx = self.ops.group_max(xf, idx)  # [max_s x_j, max_s f_j]
+            skip = self._fc(torch.cat([mx[..., :3] - xyz, mx], dim=-1), "skip")
+        else:
+            skip = self._fc(grouped_feat.max(dim=2)[0], "skip")
+            gf = self._fc(self._fc(grouped_feat, "conv0"), "conv1")  # (b,m,s,128)
         w, bias = self.P["wconv0"]
         wn = torch.relu((torch.matmul(grouped_xyz, w) + bias) / math.sqrt(1.0 + BN_EPS))  # (b,m,s,16)
         gf = torch.matmul(gf.transpose(2, 3), wn)  # (b,m,128,16)

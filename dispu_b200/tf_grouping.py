@@ -125,3 +125,28 @@ def knn_point(k, xyz1, xyz2):
     """tf_grouping.py:116.  Returns (val, idx) with val = NEGATED squared distances, like top_k(-dist)."""
     dist, idx = knn(k, xyz1, xyz2)
     return -dist, idx
+
+
+def group_max(points, idx):
+    """Fused group_point + reduce_max over nsample: points (b,n,c), idx (b,m,ns) -> (b,m,c).  Forward only."""
+    points = req(points, torch.float32, 3, "points")
+    idx = req(idx, torch.int32, 3, "idx")
+    b, n, c = points.shape
+    _, m, ns = idx.shape
+    out = torch.empty((b, m, c), dtype=torch.float32, device=points.device)
+    call("dispu_group_max", b, n, c, m, ns, ptr(points), ptr(idx), ptr(out), stream_ptr())
+    return out
+
+
+def group_affine_relu(P, Q, idx, sign=-1.0):
+    """out[b,i,s,:] = relu(P[b,idx[b,i,s],:] + sign*Q[b,i,:]): the first layer of a grouped MLP after hoisting it to
+    per-point GEMMs (see dispu_group_affine_relu).  P (b,n,c), Q (b,m,c) or None, idx (b,m,ns) -> (b,m,ns,c)."""
+    P = req(P, torch.float32, 3, "P")
+    idx = req(idx, torch.int32, 3, "idx")
+    if Q is not None:
+        Q = req(Q, torch.float32, 3, "Q")
+    b, n, c = P.shape
+    _, m, ns = idx.shape
+    out = torch.empty((b, m, ns, c), dtype=torch.float32, device=P.device)
+    call("dispu_group_affine_relu", b, n, c, m, ns, ptr(P), ptr(Q), float(sign), ptr(idx), ptr(out), stream_ptr())
+    return out

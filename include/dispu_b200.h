@@ -94,6 +94,17 @@ int dispu_group_point(int b, int n, int c, int m, int nsample, const float *poin
 int dispu_group_point_grad(int b, int n, int c, int m, int nsample, const float *grad_out, const int *idx,
                            float *grad_points, dispu_stream_t stream);
 
+/* GroupPoint fused with what the reference does to its output (no (b,m,nsample,c) intermediate):
+ *   dispu_group_max:          out[b,i,:]   = max_s points[b,idx[b,i,s],:]        (group_point + reduce_max,
+ *                             e.g. Common/ops.py:1049)
+ *   dispu_group_affine_relu:  out[b,i,s,:] = relu(P[b,idx[b,i,s],:] + sign*Q[b,i,:])   — the first layer of a
+ *                             grouped MLP hoisted to per-point GEMMs (Common/ops.py:1033-1058, :1897-1905);
+ *                             Q (b,m,c) may be NULL. */
+int dispu_group_max(int b, int n, int c, int m, int nsample, const float *points, const int *idx, float *out,
+                    dispu_stream_t stream);
+int dispu_group_affine_relu(int b, int n, int c, int m, int nsample, const float *P, const float *Q, float sign,
+                            const int *idx, float *out, dispu_stream_t stream);
+
 /* SelectionSort.  selectionSortLauncher tf_grouping.cpp:112 (kernel tf_grouping_g.cu:83). */
 int dispu_selection_sort(int b, int n, int m, int k, const float *dist, int *outi, float *out,
                          dispu_stream_t stream);
