@@ -43,6 +43,9 @@ SIGNATURES = {
     "dispu_chamfer": ([_i, _i, _p, _i, _p, _p, _p, _p, _p, _sz, _p], _i),
     "dispu_repulsion_workspace_bytes": ([_i, _i], _sz),
     "dispu_repulsion_loss": ([_i, _i, _i, C.c_float, _p, _p, _p, _p, _sz, _p], _i),
+    "dispu_dense_packed_bytes": ([_i, _i], _sz),
+    "dispu_dense_pack": ([_i, _i, _p, _p, _p], _i),
+    "dispu_dense_tf32x3": ([C.c_longlong, _i, _i, _p, _p, _p, _i, _p, _p], _i),
     "dispu_sa_mlp": ([_i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _p], _i),
 }
 

@@ -47,7 +47,9 @@ struct TcPlan {
     int n_wg;     // warpgroups per CTA (each runs its own tile stream)
 };
 
-__device__ __forceinline__ void wg_barrier(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
+__device__ __forceinline__ void wg_barrier(int wg, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(wg + 1), "r"(threads) : "memory");
+}
 
 // Hidden-layer epilogue for COLS accumulator columns starting at c0 of my row: bias + ReLU, TF32 hi/lo
 // split, and the result becomes columns [c0, c0+COLS) of the next layer's A operand in TMEM.
@@ -118,7 +120,11 @@ __device__ __forceinline__ void epilogue_pool(uint32_t tmem_d_row, int N, int c0
 // registers and the next layer's A operand is written back with tcgen05.st; shared memory holds
 // only the weights.  Column plan inside a warpgroup's region for layer l (P = planes):
 //   A_hi [0,K_l)  A_lo [K_l,2K_l)  D [dcol_l, dcol_l+N_l)  with dcol_l >= P*K_l and >= P*N_l (next A).
-template <bool kX3, int NS>
+// kSplit: warps per TMEM lane quarter inside a warpgroup (1 or 2).  With 2, a warpgroup is 256 threads and the
+// two warps that share a quarter take alternate 8-column gather chunks / 16-column epilogue chunks of the same
+// rows, halving the serial length of every gather / epilogue phase (used when the column budget only allows
+// two tile streams per SM).
+template <bool kX3, int NS, int kSplit>
 __global__ void __launch_bounds__(512, 1)
 sa_mlp_tc_kernel(int n, int m, const float *__restrict__ xyz, const float *__restrict__ points,
                  const float *__restrict__ new_xyz, const int *__restrict__ idx, TcPlan plan,
@@ -129,7 +135,9 @@ sa_mlp_tc_kernel(int n, int m, const float *__restrict__ xyz, const float *__res
     constexpr int P = kX3 ? 2 : 1;
 
     const int tid = threadIdx.x;
-    const int wg = tid >> 7, t = tid & 127, lane = tid & 31, q = (tid >> 5) & 3;
+    constexpr int kWgThreads = 128 * kSplit;
+    const int wg = tid / kWgThreads, t = tid & 127, lane = tid & 31, q = (tid >> 5) & 3;
+    const int half = (tid / 128) % kSplit;  // which of the kSplit warps of my lane quarter I am
     const uint32_t smem_base = smem_u32(smem);
 
     // ---- one-time setup: barriers, TMEM, weights (hi/lo planes, K-major UMMA layout) ------------
@@ -203,7 +211,7 @@ sa_mlp_tc_kernel(int n, int m, const float *__restrict__ xyz, const float *__res
                 gz = __fsub_rn(__ldg(pxyz + 2), __ldg(ctr + 2));
                 if (c_pts) pf = points + (cloud * n + ii) * (long long)c_pts;
             }
-            for (int k0 = 0; k0 < K0; k0 += 8) {
+            for (int k0 = half * 8; k0 < K0; k0 += 8 * kSplit) {
                 float x[8];
 #pragma unroll
                 for (int hlf = 0; hlf < 2; ++hlf) {
@@ -242,9 +250,9 @@ sa_mlp_tc_kernel(int n, int m, const float *__restrict__ xyz, const float *__res
             const int K = plan.K[l], N = plan.N[l], dcol = plan.dcol[l];
             tmem_st_wait();  // my A-operand stores have landed
             tc_fence_before_sync();
-            wg_barrier(wg);
+            wg_barrier(wg, kWgThreads);
             // ---- (2) one thread of the warpgroup issues the layer's MMAs ------------------------
-            if (t == 0) {
+            if (t == 0 && half == 0) {
                 tc_fence_after_sync();
                 const uint32_t idesc = make_idesc_tf32(kTcRows, N);
                 const uint32_t lboB = (uint32_t)(N / 8) * 128u;
@@ -264,21 +272,35 @@ sa_mlp_tc_kernel(int n, int m, const float *__restrict__ xyz, const float *__res
                 }
                 mma_commit(&s_bar[wg]);
             }
-            mbar_wait(&s_bar[wg], phase);
+            // only the issuing warp polls the mbarrier; the rest of the warpgroup sleeps on a hardware barrier
+            // (128-512 threads spinning on try_wait would eat the issue slots the other warpgroups' epilogues need)
+            if ((tid % kWgThreads) < 32) mbar_wait(&s_bar[wg], phase);
             phase ^= 1;
+            wg_barrier(wg, kWgThreads);
             tc_fence_after_sync();
 
             // ---- (3) epilogue on my accumulator row -------------------------------------------------
             const float *sb = reinterpret_cast<const float *>(smem + plan.offBias[l]);
-            if (l != plan.n_layers - 1) {
-                for (int c0 = 0; c0 + 32 <= N; c0 += 32) epilogue_hidden<kX3, 32>(tmem_row, dcol, N, c0, sb);
-                if (N & 16) epilogue_hidden<kX3, 16>(tmem_row, dcol, N, N - 16, sb);
-            } else {
-                const long long g = R / NS;
-                const bool gvalid = (long long)tile * kTcRows + (t / NS) * NS < total_rows;
-                for (int c0 = 0; c0 + 32 <= N; c0 += 32)
-                    epilogue_pool<NS, 32>(tmem_row + dcol, N, c0, sb, gmask, lane, gvalid, out + g * N);
-                if (N & 16) epilogue_pool<NS, 16>(tmem_row + dcol, N, N - 16, sb, gmask, lane, gvalid, out + g * N);
+            if (kSplit == 1) {
+                if (l != plan.n_layers - 1) {
+                    for (int c0 = 0; c0 + 32 <= N; c0 += 32) epilogue_hidden<kX3, 32>(tmem_row, dcol, N, c0, sb);
+                    if (N & 16) epilogue_hidden<kX3, 16>(tmem_row, dcol, N, N - 16, sb);
+                } else {
+                    const long long g = R / NS;
+                    const bool gvalid = (long long)tile * kTcRows + (t / NS) * NS < total_rows;
+                    for (int c0 = 0; c0 + 32 <= N; c0 += 32)
+                        epilogue_pool<NS, 32>(tmem_row + dcol, N, c0, sb, gmask, lane, gvalid, out + g * N);
+                    if (N & 16) epilogue_pool<NS, 16>(tmem_row + dcol, N, N - 16, sb, gmask, lane, gvalid, out + g * N);
+                }
+            } else {  // alternate 16-column chunks between the warps sharing my lane quarter
+                if (l != plan.n_layers - 1) {
+                    for (int c0 = half * 16; c0 < N; c0 += 16 * kSplit) epilogue_hidden<kX3, 16>(tmem_row, dcol, N, c0, sb);
+                } else {
+                    const long long g = R / NS;
+                    const bool gvalid = (long long)tile * kTcRows + (t / NS) * NS < total_rows;
+                    for (int c0 = half * 16; c0 < N; c0 += 16 * kSplit)
+                        epilogue_pool<NS, 16>(tmem_row + dcol, N, c0, sb, gmask, lane, gvalid, out + g * N);
+                }
             }
         }
         // the next gather overwrites [0, P*K0): only my own lanes, after my own tcgen05.wait::ld
@@ -467,15 +489,15 @@ int sa_mlp_tc_launch(int b, int n, int m, int ns, int c_pts, int layout, const f
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     long long grid_ll = ceil_div64(n_tiles, plan.n_wg);
     const int grid = grid_ll < sms ? (int)grid_ll : sms;
-    const int threads = plan.n_wg * 128;
+    const int split = plan.n_wg <= 2 ? 2 : 1;
+    const int threads = plan.n_wg * 128 * split;
     count_launch();
 #define DISPU_TC_LAUNCH(X3, NSV)                                                                                   \
     do {                                                                                                           \
-        cudaError_t e_ = cudaFuncSetAttribute(sa_mlp_tc_kernel<X3, NSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                              (int)off);                                                           \
+        auto kern_ = split == 2 ? sa_mlp_tc_kernel<X3, NSV, 2> : sa_mlp_tc_kernel<X3, NSV, 1>;                        \
+        cudaError_t e_ = cudaFuncSetAttribute(kern_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)off);       \
         if (e_ != cudaSuccess) return (int)e_;                                                                     \
-        sa_mlp_tc_kernel<X3, NSV><<<grid, threads, off, stream>>>(n, m, xyz, points, new_xyz, idx, plan, out,       \
-                                                                  total_rows, n_tiles);                            \
+        kern_<<<grid, threads, off, stream>>>(n, m, xyz, points, new_xyz, idx, plan, out, total_rows, n_tiles);     \
     } while (0)
     if (x3) {
         if (ns == 8) DISPU_TC_LAUNCH(true, 8); else if (ns == 16) DISPU_TC_LAUNCH(true, 16); else DISPU_TC_LAUNCH(true, 32);

@@ -64,8 +64,10 @@ def _xavier(gen, cin, cout, device, fan_in=None, fan_out=None):
 class Generator:
     """coarse, fine = G(inputs (b,n,3)); up_ratio 4: (b,4n,3) each."""
 
-    def __init__(self, up_ratio=4, device="cuda", seed=7, ops=None, hoist=True):
+    def __init__(self, up_ratio=4, device="cuda", seed=7, ops=None, hoist=True, tc=True):
         self.up_ratio = up_ratio
+        self.tc = tc  # dense layers on the tcgen05 3xTF32 kernel (GPU only)
+        self._packed = {}
         self.hoist = hoist  # use the fused / hoisted grouped-layer formulation when the backend offers it
         self.device = torch.device(device)
         self.ops = ops if ops is not None else DispuOps()
@@ -111,16 +113,33 @@ class Generator:
 
     # -- layers ---------------------------------------------------------------------------------
     def _fc(self, x, name, act=True):
-        """1x1 conv = dense layer over the last axis, bias (+ ReLU) in the GEMM epilogue (stock cuBLASLt)."""
+        """1x1 conv = dense layer over the last axis with bias (+ ReLU) fused.  On the GPU every such layer runs on
+        the tcgen05 3xTF32 kernel (dense.PackedLinear, fp32-level accuracy); the CPU arm uses torch addmm."""
         w, b = self.P[name]
+        if self.tc and x.is_cuda and w.shape[1] <= 256:
+            lin = self._packed.get(name)
+            if lin is None:
+                from .dense import PackedLinear
+                lin = self._packed[name] = PackedLinear(w, b)
+            return lin(x, relu=act)
         x2 = x.reshape(-1, x.shape[-1])
-        if act and x2.is_cuda:
-            y = torch._addmm_activation(b, x2, w, use_gelu=False)  # relu(x.w + b)
-        else:
-            y = torch.addmm(b, x2, w)
-            if act:
-                y = torch.relu_(y)
+        y = torch.addmm(b, x2, w)
+        if act:
+            y = torch.relu_(y)
         return y.view(*x.shape[:-1], w.shape[1])
+
+    def _lin(self, key, x, w, b=None, act=False):
+        """Same as _fc for derived (hoisted) weights, cached under `key`."""
+        if self.tc and x.is_cuda and w.shape[1] <= 256:
+            lin = self._packed.get(key)
+            if lin is None:
+                from .dense import PackedLinear
+                lin = self._packed[key] = PackedLinear(w, b)
+            return lin(x, relu=act)
+        y = torch.matmul(x, w)
+        if b is not None:
+            y = y + b
+        return torch.relu_(y) if act else y
 
     def _dense_conv_hoisted(self, feature, blk, k=16):
         """Same function as _dense_conv with every term that does not depend on the neighbour hoisted to ONE
@@ -138,7 +157,7 @@ class Generator:
             self.P[key] = (wcat, bcat, w1[:24].contiguous(), w2[:24].contiguous(), w2[24:48].contiguous())
         wcat, bcat, w1a, w2a, w2b = self.P[key]
         idx = self.ops.feature_knn(k + 1, feature)[:, :, 1:].contiguous()
-        proj = torch.addmm(bcat, feature.reshape(-1, c), wcat).view(*feature.shape[:2], 96)
+        proj = self._lin(key, feature, wcat, bcat)
         pn, pc, t1, t2 = (proj[..., i * 24:(i + 1) * 24].contiguous() for i in range(4))
         y0 = self.ops.group_affine_relu(pn, pc, idx, 1.0)  # (b,n,k,24)
         y1 = torch.relu_(torch.matmul(y0, w1a) + t1.unsqueeze(2))
@@ -207,8 +226,8 @@ class Generator:
                 self.P["_hoist_ps"] = (torch.cat([w0[0:3] + w0[3:6], w0[6:]], dim=0).contiguous(), w0[0:3].contiguous())
             wp, wa = self.P["_hoist_ps"]
             xf = torch.cat([xyz, feature], dim=-1)  # (b,m,131) per point
-            pm = torch.addmm(b0, xf.reshape(-1, 131), wp).view(b, m, 128)
-            qm = torch.matmul(xyz, wa)
+            pm = self._lin("_hoist_ps_p", xf, wp, b0)
+            qm = self._lin("_hoist_ps_q", xyz, wa)
             y0 = self.ops.group_affine_relu(pm, qm, idx, -1.0)  # relu(conv0): (b,m,s,128)
             gf = self._fc(y0, "conv1")
             mx = self.ops.group_max(xf, idx)  # [max_s x_j, max_s f_j]

@@ -188,6 +188,16 @@ int dispu_sa_mlp(int b, int n, int m, int nsample, int c_pts, int layout, const 
                  const float *const *weights_host_array, const float *const *biases_host_array, float *out,
                  int precision, dispu_stream_t stream);
 
+/* Dense layer on tcgen05 with FP32-level accuracy (3xTF32, FP32 accumulate in TMEM), bias + ReLU fused:
+ *     Y[M,N] = act(X[M,K] . W[K,N] + bias),  N <= 256, any K.
+ * The unit the live generator's grouped MLPs reduce to after hoisting their first layer (Common/ops.py:1055-1072:
+ * conv1 over (b,4N,16,128) rows, the [1,128]-conv = 2048->256 per point; tf_util.conv2d, Common/tf_util.py:120-185).
+ * W is packed once (TF32 hi/lo planes in UMMA layout) into dispu_dense_packed_bytes(K,N) bytes by dispu_dense_pack. */
+size_t dispu_dense_packed_bytes(int K, int N);
+int dispu_dense_pack(int K, int N, const float *W, void *packed, dispu_stream_t stream);
+int dispu_dense_tf32x3(long long M, int K, int N, const float *X, const void *packed, const float *bias, int relu,
+                       float *Y, dispu_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -514,10 +514,37 @@ def test_generator_hoisted_equals_reference_op_sequence():
     inp, _ = bench.synth_batch(0, b=4)
     x = T(inp)
     with torch.no_grad():
-        c1, f1 = Generator(device=dev, hoist=True)(x)
-        c0, f0 = Generator(device=dev, hoist=False)(x)
+        c1, f1 = Generator(device=dev, hoist=True, tc=True)(x)
+        c0, f0 = Generator(device=dev, hoist=False, tc=False)(x)  # reference op sequence on stock fp32 GEMMs
     # feature-space kNN can flip between two (nearly) equidistant neighbours under reassociation: compare robustly
     for a, bb in ((c1, c0), (f1, f0)):
         err = (a - bb).abs()
         assert float(err.median()) < 1e-5
         assert float((err > 1e-3).float().mean()) < 0.02
+
+
+@pytest.mark.parametrize("M,K,N", [(1000, 131, 128), (300, 3, 24), (128, 482, 256), (4100, 2048, 256), (77, 64, 3), (5000, 120, 48),
+                                   (16384, 128, 128), (129, 256, 64)])
+@pytest.mark.parametrize("relu", [False, True])
+def test_dense_tf32x3(rng, M, K, N, relu):
+    """tcgen05 3xTF32 dense layer vs a float64 reference: fp32-level accuracy (tolerance 1e-5 relative to the row scale)."""
+    from dispu_b200.dense import PackedLinear
+    x = rng.standard_normal((M, K)).astype(np.float32)
+    w = (rng.standard_normal((K, N)) / np.sqrt(K)).astype(np.float32)
+    b = rng.standard_normal((N,)).astype(np.float32)
+    want = x.astype(np.float64) @ w.astype(np.float64) + b
+    if relu:
+        want = np.maximum(want, 0)
+    lin = PackedLinear(T(w), T(b))
+    got = lin(T(x), relu=relu).cpu().numpy()
+    scale = max(1.0, float(np.abs(want).max()))
+    tol = 6e-6 * np.sqrt(K) * scale  # 3xTF32: each product good to ~2^-21, fp32 accumulation over K terms
+    assert np.abs(got - want).max() <= tol
+    # an fp32 cuBLAS SGEMM of the same product is no more accurate than this by more than a small factor
+    ref32 = (T(x) @ T(w) + T(b)).cpu().numpy()
+    if relu:
+        ref32 = np.maximum(ref32, 0)
+    assert np.abs(got - want).max() <= 10 * np.abs(ref32 - want).max() + 1e-6 * scale
+    # 3-D input view, no bias
+    got2 = PackedLinear(T(w))(T(x).view(1, M, K)).cpu().numpy()[0]
+    assert np.abs(got2 - (x.astype(np.float64) @ w.astype(np.float64))).max() <= tol
