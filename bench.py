@@ -368,109 +368,104 @@ def measured_peaks():
     return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
-def dominant_kernel_roofline(gen, d_inp, d_gt, stream, flush):
-    """Times each of this library's kernels at the shapes the step launches them with (CUDA events on
-    the launching stream, L2 flushed) and reports the roofline of the one with the largest share of the step.
-    achieved = ALGORITHMIC bytes per launch (DESIGN.md §4 / SURVEY.md §8d per-unit figures x units) / duration."""
+def dominant_kernel_roofline(gen, d_inp, d_gt, stream, flush, reps=10):
+    """Per-kernel device time INSIDE the step: the step runs eagerly `reps` times with a CUDA-event pair around
+    every C-ABI call of this library (dispu_b200._t._profile; a spin kernel at the head of each step keeps the
+    launch queue full so the pairs bracket execution, not host launch latency; L2 flushed before each step).
+    Reports the roofline of the kernel family with the largest share of the step:
+    achieved = ALGORITHMIC flops (2*M*K*N of each dense launch) or bytes / measured duration."""
     import torch
-    from dispu_b200 import loss_utils, tf_grouping
-    hbm, _, which = measured_peaks()
+    from dispu_b200 import _t, loss_utils
+    hbm, bf16_peak, which = measured_peaks()
+    out_c = torch.zeros((4,), dtype=torch.float32, device=d_inp.device)
+    recs = []
     with torch.no_grad():
-        coarse, fine = gen(d_inp)
-        b, m, _ = coarse.shape
-        n_in = d_inp.shape[1]
-        k = 16
-        feat = torch.randn((b, m, 128), device=coarse.device)
-        q128 = torch.randn((b, m, 128), device=coarse.device)
-        xf = torch.randn((b, m, 131), device=coarse.device)
-        f24 = torch.randn((b, n_in, 24), device=coarse.device)
-        idx = tf_grouping.knn(k, coarse, coarse)[1]
-        idx_in = tf_grouping.knn(k, d_inp, d_inp)[1]
+        for rep in range(reps + 2):
+            flush.zero_()
+            torch.cuda._sleep(4_000_000)  # ~2 ms of device spin: the whole step is enqueued behind it
+            _t._profile = [] if rep >= 2 else None
+            try:
+                coarse, fine = gen(d_inp)
+                loss_utils.chamfer_hausdorff(coarse, d_gt, out=out_c)
+                loss_utils.chamfer_hausdorff(fine, d_gt, out=out_c)
+                prof = _t._profile
+            finally:
+                _t._profile = None
+            stream.synchronize()
+            if prof:
+                recs.append([(k, a.elapsed_time(b)) for k, a, b in prof])
+    per_key = {}
+    for step in recs:
+        for k, ms in step:
+            e = per_key.setdefault(k, [0.0, 0])
+            e[0] += ms
+            e[1] += 1
+    n = len(recs)
+    b, m = d_inp.shape[0], d_inp.shape[1] * UP
+    n_in, kk = d_inp.shape[1], 16
 
-        def t(fn, iters=20):
-            for _ in range(3):
-                fn()
-            tot = 0.0
-            for _ in range(iters):
-                flush.zero_()
-                e0 = torch.cuda.Event(enable_timing=True)
-                e1 = torch.cuda.Event(enable_timing=True)
-                e0.record(stream)
-                fn()
-                e1.record(stream)
-                e1.synchronize()
-                tot += e0.elapsed_time(e1)
-            return tot / iters
+    def alg_bytes(key):
+        """SURVEY.md §8d / DESIGN.md §4 algorithmic bytes of one launch of the non-GEMM kernels at the step's shapes."""
+        nm = key.split(" ")[0]
+        if nm == "dispu_knn":
+            return b * (12 * m + 12 * m + 4 * m * kk)
+        if nm == "dispu_chamfer":
+            return b * (12 * m + 12 * m) + 16
+        if nm == "dispu_group_max_ld":
+            return b * (4 * m * kk + 4 * m * 132 + 4 * m * 132)
+        if nm == "dispu_weightnet_aggregate":
+            return b * m * (4 * kk * 128 + 4 * 2048 + 4 * kk + 12)
+        if nm == "dispu_feature_knn":
+            c = int(key.split(" ")[1].split(",")[3])
+            return b * n_in * (4 * c + 4 * kk)
+        if nm == "dispu_dense_conv":
+            c = int(key.split(" ")[1].split(",")[2])
+            return b * n_in * (4 * c + 4 * kk + 4 * (72 + c))
+        return None
 
-        cands = {
-            # name: (ms per launch, launches per step, algorithmic bytes per launch)
-            "knn_select_kernel (kNN grouping b=%d n=m=%d k=16)" % (b, m):
-                (t(lambda: tf_grouping.knn(k, coarse, coarse)), 1, b * (12 * m + 12 * m + 4 * m * k + 4 * m * k)),
-            "nn_distance_kernel<reduce> (fused Chamfer b=%d n=m=%d)" % (b, m):
-                (t(lambda: loss_utils.chamfer_hausdorff(fine, d_gt)), 2, b * (12 * m + 12 * m) + 16),
-            "group_affine_relu_kernel<4> (GroupPoint+centre+ReLU c=128 b=%d m=%d ns=16)" % (b, m):
-                (t(lambda: tf_grouping.group_affine_relu(feat, q128, idx, -1.0)), 1,
-                 b * (4 * m * k + 4 * m * 128 + 4 * m * 128 + 4 * m * k * 128)),
-            "group_affine_relu_kernel<4> (c=24 b=%d n=%d ns=16)" % (b, n_in):
-                (t(lambda: tf_grouping.group_affine_relu(f24, f24, idx_in, 1.0)), 4,
-                 b * (4 * n_in * k + 8 * n_in * 24 + 4 * n_in * k * 24)),
-            "group_max_kernel<1> (GroupPoint+max c=131 b=%d m=%d ns=16)" % (b, m):
-                (t(lambda: tf_grouping.group_max(xf, idx)), 1, b * (4 * m * k + 4 * m * 131 + 4 * m * 131)),
-            "gather_rows_kernel<1> (GroupPoint c=3 b=%d m=%d ns=16)" % (b, m):
-                (t(lambda: tf_grouping.group_point(coarse, idx)), 1, b * (4 * m * k + 12 * m + 12 * m * k)),
-        }
-        # ---- the tcgen05 dense layer: every (M,K,N) the step launches it with, timed alone
-        from dispu_b200 import dense as _dense
-        shapes = []
-        orig_call = _dense.PackedLinear.__call__
-
-        def logging_call(self, x, relu=False):
-            shapes.append((x.numel() // self.K, self.K, self.N, bool(relu)))
-            return orig_call(self, x, relu)
-        _dense.PackedLinear.__call__ = logging_call
-        try:
-            gen(d_inp)
-        finally:
-            _dense.PackedLinear.__call__ = orig_call
-        dense_ms, dense_flops, dense_detail = 0.0, 0.0, {}
-        for shp in sorted(set(shapes)):
-            M_, K_, N_, relu_ = shp
-            cnt = shapes.count(shp)
-            xs = torch.randn((M_, K_), device=coarse.device)
-            lin = _dense.PackedLinear(torch.randn((K_, N_), device=coarse.device) / K_ ** 0.5, torch.zeros((N_,), device=coarse.device))
-            ms_ = t(lambda: lin(xs, relu=relu_), iters=10)
+    fam = {}
+    detail = {}
+    for k, (ms_tot, cnt) in per_key.items():
+        ms_step, per_step = ms_tot / n, cnt / n
+        ent = {"ms_per_launch": ms_tot / cnt, "launches_per_step": per_step, "ms_per_step": ms_step}
+        if k.startswith("dispu_dense_tf32x3_ex"):
+            f = k.split(" ")
+            M_, K_, N_ = int(f[1][1:]), int(f[2][1:]), int(f[3][1:])
             fl = 2.0 * M_ * K_ * N_
-            dense_ms += ms_ * cnt
-            dense_flops += fl * cnt
-            dense_detail["M%d K%d N%d" % (M_, K_, N_)] = {"ms": ms_, "launches_per_step": cnt, "TFLOPs": fl / ms_ / 1e9}
-    _, bf16_peak, which_t = measured_peaks()
-    by_kernel = {nm: v[0] * v[1] for nm, v in cands.items()}
-    all_entries = {nm: {"ms": v[0], "launches_per_step": v[1], "alg_bytes": v[2], "GBps": v[2] / (v[0] * 1e-3) / 1e9,
-                        "frac_of_hbm": v[2] / (v[0] * 1e-3) / 1e9 / hbm} for nm, v in cands.items()}
-    n_dense = len(shapes)
-    all_entries["dense_tf32x3_kernel (tcgen05 3xTF32 dense layer)"] = {
-        "ms_total_per_step": dense_ms, "launches_per_step": n_dense, "TFLOPs_algorithmic": dense_flops / dense_ms / 1e9 if dense_ms else None,
-        "shapes": dense_detail}
-    if shapes and dense_ms >= max(by_kernel.values()):
-        achieved = dense_flops / dense_ms / 1e9  # algorithmic (fp32-equivalent) FLOPs per launch / average launch duration
+            ent["TFLOPs_algorithmic"] = fl / (ms_tot / cnt) / 1e9
+            fm = fam.setdefault("dense_tf32x3_kernel", {"ms": 0.0, "launches": 0.0, "flops": 0.0})
+            fm["flops"] += fl * per_step
+        else:
+            ab = alg_bytes(k)
+            if ab is not None:
+                ent["alg_bytes"] = ab
+                ent["GBps"] = ab / (ms_tot / cnt * 1e-3) / 1e9
+                ent["frac_of_hbm"] = ent["GBps"] / hbm
+            fm = fam.setdefault(k.split(" ")[0], {"ms": 0.0, "launches": 0.0, "bytes": 0.0})
+            fm["bytes"] = fm.get("bytes", 0.0) + (ab or 0) * per_step
+        fm["ms"] += ms_step
+        fm["launches"] += per_step
+        detail[k] = ent
+    lib_ms = sum(f["ms"] for f in fam.values())
+    name = max(fam, key=lambda q: fam[q]["ms"])
+    top = fam[name]
+    shares = {q: round(f["ms"] / lib_ms, 4) for q, f in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
+    common = {"ms_per_launch": top["ms"] / top["launches"], "launches_per_step": top["launches"],
+              "ms_per_step": top["ms"], "library_ms_per_step": lib_ms, "share_of_library_time": shares,
+              "how": f"CUDA-event pair around every launch of the step, eager, {n} steps, L2 flushed per step",
+              "all": detail}
+    if name == "dense_tf32x3_kernel":
+        achieved = top["flops"] / top["ms"] / 1e9
         return {"bound": "tensor", "kernel": "dense_tf32x3_kernel (tcgen05.mma kind::tf32, 3xTF32, FP32 accumulate in TMEM)",
                 "achieved": achieved, "peak": bf16_peak, "unit": "TFLOP/s", "frac": achieved / bf16_peak, "traffic": None,
-                "peak_source": which_t + " dense bf16 burst",
-                "algorithmic_flops_per_launch": dense_flops / n_dense, "ms_per_launch": dense_ms / n_dense,
-                "launches_per_step": n_dense,
-                "note": "algorithmic FLOPs = 2*M*K*N of the fp32 contraction; the kernel issues 3x that on the tensor pipe at the TF32 rate "
-                        "(half the bf16 rate), so the ceiling for this figure is peak/6; X is read from HBM as fp32 and split on the fly",
-                "all": all_entries}
-    name = max(by_kernel, key=by_kernel.get)
-    ms, per_step, alg = cands[name]
-    achieved = alg / (ms * 1e-3) / 1e9
-    note = None
-    if name.startswith("knn") or name.startswith("nn_distance"):
-        note = ("exact brute-force search: FP32-ALU bound (O(n*m) distance tests on compulsory bytes), so the HBM fraction is "
-                "small by construction; see profiles/ for its issue-slot utilisation")
+                "peak_source": which + " dense bf16 burst",
+                "algorithmic_flops_per_launch": top["flops"] / top["launches"],
+                "note": "algorithmic FLOPs = 2*M*K*N of the fp32 contraction; the kernel issues 3x that on the tensor pipe at the TF32 "
+                        "rate (half the bf16 rate), so the ceiling for this figure is peak/6; X is read from HBM as fp32 and split on the fly",
+                **common}
+    achieved = top["bytes"] / (top["ms"] * 1e-3) / 1e9
     return {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-            "traffic": None, "peak_source": which, "algorithmic_bytes_per_launch": alg, "ms_per_launch": ms,
-            "launches_per_step": per_step, "note": note, "all": all_entries}
+            "traffic": None, "peak_source": which, "algorithmic_bytes_per_launch": top["bytes"] / top["launches"], **common}
 
 
 def main():

@@ -12,7 +12,18 @@ SO = os.path.join(HERE, "libdispu_b200.so")
 
 EINVAL, ENULL, EUNSUPPORTED, EWORKSPACE = -1, -2, -3, -4
 
-_i, _p, _sz = C.c_int, C.c_void_p, C.c_size_t
+_i, _p, _sz, _ll = C.c_int, C.c_void_p, C.c_size_t, C.c_longlong
+
+
+class DenseArgs(C.Structure):
+    """dispu_dense_args of include/dispu_b200.h (host struct)."""
+    _fields_ = [
+        ("M", _ll), ("K", _i), ("N", _i), ("X", _p), ("ldx", _ll), ("packed", _p), ("bias", _p), ("relu", _i),
+        ("Y", _p), ("ldy", _ll), ("gather_idx", _p), ("gather_n", _i), ("gather_ns", _i), ("gather_rows_per_cloud", _ll),
+        ("Q", _p), ("ldq", _ll), ("sign", C.c_float), ("R1", _p), ("ldr1", _ll), ("R2", _p), ("ldr2", _ll),
+        ("rows_per_batch", _ll), ("packed_batch_stride", _ll),
+    ]
+
 
 # name -> argtypes, exactly the prototypes of include/dispu_b200.h
 SIGNATURES = {
@@ -30,6 +41,7 @@ SIGNATURES = {
     "dispu_group_point": ([_i, _i, _i, _i, _i, _p, _p, _p, _p], _i),
     "dispu_group_point_grad": ([_i, _i, _i, _i, _i, _p, _p, _p, _p], _i),
     "dispu_group_max": ([_i, _i, _i, _i, _i, _p, _p, _p, _p], _i),
+    "dispu_group_max_ld": ([_i, _i, _i, _i, _i, _p, _i, _p, _p, _i, _p], _i),
     "dispu_group_affine_relu": ([_i, _i, _i, _i, _i, _p, _p, C.c_float, _p, _p, _p], _i),
     "dispu_selection_sort": ([_i, _i, _i, _i, _p, _p, _p, _p], _i),
     "dispu_knn": ([_i, _i, _i, _i, _p, _p, _p, _p, _p], _i),
@@ -46,6 +58,12 @@ SIGNATURES = {
     "dispu_dense_packed_bytes": ([_i, _i], _sz),
     "dispu_dense_pack": ([_i, _i, _p, _p, _p], _i),
     "dispu_dense_tf32x3": ([C.c_longlong, _i, _i, _p, _p, _p, _i, _p, _p], _i),
+    "dispu_dense_tf32x3_ex": ([C.POINTER(DenseArgs), _p], _i),
+    "dispu_dense_pack_strided": ([_i, _i, _p, _ll, _ll, _i, _ll, _p, _ll, _p], _i),
+    "dispu_feature_knn": ([_i, _i, _i, _i, _i, _i, _p, _i, _p, _i, _p, _p, _p], _i),
+    "dispu_dense_conv_workspace_bytes": ([_i, _i], _sz),
+    "dispu_dense_conv": ([_i, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _sz, _p], _i),
+    "dispu_weightnet_aggregate": ([_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, C.c_float, _p, _p], _i),
     "dispu_sa_mlp": ([_i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _p], _i),
 }
 

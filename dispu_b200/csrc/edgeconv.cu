@@ -1,0 +1,487 @@
+// Feature-space kNN + EdgeConv dense block + weight-net aggregation for sm_100a.
+//
+//  * dispu_feature_knn — knn_point_2 (tf_ops/grouping/tf_grouping.py:95-114): k nearest neighbours in a
+//    C-dimensional FEATURE space on the matmul-form distance matrix (batch_distance_matrix_general, :61-66)
+//    D = (r_q - 2 q.p) + r_p, ascending, ties to the lower index (tf.nn.top_k).  The reference materialises the
+//    (b,n,n) matrix, runs a full top_k and builds (b,n,k,2) gather_nd pairs; here a warp owns two queries, the
+//    cloud's features sit transposed in shared memory (conflict-free column reads), distances stay in
+//    registers and the k winners are extracted by k rounds of warp arg-min (redux.sync on an order-preserving
+//    key, then on the index).  Arithmetic is pinned (sequential fmaf over the channels), so results are reproducible bit for bit.
+//  * dispu_dense_conv — dense_conv (Common/ops.py:1897-1915) over get_edge_feature (:1856-1877): the three 1x1
+//    convs on concat[central, neighbour-central | y | central] and the max over the k neighbours in ONE pass.
+//    Everything that depends only on the centre point is hoisted to a per-point product (exact reassociation):
+//        y0 = relu(pn[j] + pc[i])            pn = f.W0[c:2c]        pc = f.(W0[:c]-W0[c:]) + b0
+//        y1 = relu(y0.W1[:g] + t1[i])        t1 = f.W1[g:] + b1
+//        y2 =      y1.W2[:g] + y0.W2[g:2g] + t2[i]                  t2 = f.W2[2g:] + b2
+//    so no (b,n,k,*) tensor exists anywhere; the per-edge 24x24 / 48x24 products run as FP32 FMA chains with the
+//    weights broadcast from shared memory (two edges per thread share every weight load).
+//  * dispu_weightnet_aggregate — PointShuffle2's weight net + transposed product (Common/ops.py:1062-1067,
+//    weight_net_hidden :181-191): H[i] = transpose(G[i]) . relu(bn(gx.Ww + bw)) without the (b,m,ns,3),
+//    (b,m,ns,ns) and transposed (b,m,C,ns) intermediates.
+#include "common.cuh"
+
+namespace dispu {
+
+// ------------------------------------------------------------------------------------------------------------------
+// feature kNN
+constexpr int kFkWarps = 8;
+constexpr int kFkQueriesPerWarp = 4;  // processed two at a time
+
+__device__ __forceinline__ unsigned ord_key(float f) {
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// P = candidates per lane per chunk (chunk = 32*P points staged transposed in shared memory).
+template <int P>
+__global__ void __launch_bounds__(kFkWarps * 32)
+feature_knn_kernel(int n, int m, int c, int k, int skip, const float *__restrict__ points, int ldp,
+                   const float *__restrict__ queries, int ldq, float *__restrict__ dist, int *__restrict__ idx) {
+    extern __shared__ float fk_smem[];
+    constexpr int kChunk = 32 * P;
+    constexpr int kStride = kChunk + 1;  // odd stride: the transposing stores are conflict-free too
+    float *s_ft = fk_smem;                           // [c][kStride]
+    float *s_r = s_ft + (size_t)c * kStride;         // [kChunk]
+    float *s_q = s_r + kChunk;                       // [warps][2][c]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cloud = blockIdx.y;
+    const float *pts = points + (size_t)cloud * n * ldp;
+    const float *qry = queries + (size_t)cloud * m * ldq;
+    const int q0 = (blockIdx.x * kFkWarps + warp) * kFkQueriesPerWarp;
+    const float inf = __int_as_float(0x7f800000);
+
+    // carried lists: lane j holds the j-th best (d, idx) of query u so far
+    float bd[kFkQueriesPerWarp];
+    int bi[kFkQueriesPerWarp];
+#pragma unroll
+    for (int u = 0; u < kFkQueriesPerWarp; ++u) { bd[u] = inf; bi[u] = 0x7fffffff; }
+
+    for (int t0 = 0; t0 < n; t0 += kChunk) {
+        const int tn = min(kChunk, n - t0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < tn * c; e += kFkWarps * 32) {
+            const int p = e / c, l = e - p * c;
+            s_ft[(size_t)l * kStride + p] = __ldg(pts + (size_t)(t0 + p) * ldp + l);
+        }
+        __syncthreads();
+        for (int p = threadIdx.x; p < kChunk; p += kFkWarps * 32) {
+            float r = 0.f;
+            if (p < tn)
+                for (int l = 0; l < c; ++l) { const float v = s_ft[(size_t)l * kStride + p]; r = __fmaf_rn(v, v, r); }
+            s_r[p] = r;
+        }
+        __syncthreads();
+        if (q0 >= m) continue;
+#pragma unroll
+        for (int u0 = 0; u0 < kFkQueriesPerWarp; u0 += 2) {
+            if (q0 + u0 >= m) break;
+            // stage the two query vectors (second one clamps to a valid row; its result is discarded)
+            float *sq = s_q + (size_t)warp * 2 * c;
+            __syncwarp();
+            for (int e = lane; e < 2 * c; e += 32) {
+                const int w = e / c, l = e - w * c;
+                sq[e] = __ldg(qry + (size_t)min(q0 + u0 + w, m - 1) * ldq + l);
+            }
+            __syncwarp();
+            float rq0 = 0.f, rq1 = 0.f;
+            for (int l = 0; l < c; ++l) {
+                rq0 = __fmaf_rn(sq[l], sq[l], rq0);
+                rq1 = __fmaf_rn(sq[c + l], sq[c + l], rq1);
+            }
+            float d0[P], d1[P];
+#pragma unroll
+            for (int t = 0; t < P; ++t) { d0[t] = 0.f; d1[t] = 0.f; }
+            for (int l = 0; l < c; ++l) {
+                const float a0 = sq[l], a1 = sq[c + l];
+                const float *col = s_ft + (size_t)l * kStride + lane;
+#pragma unroll
+                for (int t = 0; t < P; ++t) {
+                    const float v = col[t * 32];
+                    d0[t] = __fmaf_rn(a0, v, d0[t]);
+                    d1[t] = __fmaf_rn(a1, v, d1[t]);
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < P; ++t) {
+                const int p = t * 32 + lane;
+                const float rp = s_r[p];
+                d0[t] = p < tn ? __fadd_rn(__fmaf_rn(-2.f, d0[t], rq0), rp) : inf;
+                d1[t] = p < tn ? __fadd_rn(__fmaf_rn(-2.f, d1[t], rq1), rp) : inf;
+            }
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+                const int u = u0 + w;
+                float cd = bd[u];  // carried entry of this lane (inf when none)
+                int ci = bi[u];
+                float nd = inf;
+                int ni = 0x7fffffff;
+                for (int r = 0; r < k; ++r) {
+                    // lane-local minimum; strict '<' keeps the carried entry (lower index) and the lower slot on ties
+                    float lm = cd;
+                    int lt = -1;
+#pragma unroll
+                    for (int t = 0; t < P; ++t) {
+                        const float v = w == 0 ? d0[t] : d1[t];
+                        if (v < lm) { lm = v; lt = t; }
+                    }
+                    const int gi = lt < 0 ? ci : t0 + lt * 32 + lane;
+                    const unsigned key = ord_key(lm);
+                    const unsigned kmin = __reduce_min_sync(kFull, key);
+                    const unsigned imin = __reduce_min_sync(kFull, key == kmin ? (unsigned)gi : 0xffffffffu);
+                    const bool win = key == kmin && (unsigned)gi == imin;
+                    const int wl = __ffs(__ballot_sync(kFull, win)) - 1;
+                    const float dmin = __shfl_sync(kFull, lm, wl);
+                    if (lane == r) { nd = dmin; ni = (int)imin; }
+                    if (win && lane == wl) {
+                        if (lt < 0) {
+                            cd = inf;
+                        } else {
+#pragma unroll
+                            for (int t = 0; t < P; ++t)
+                                if (t == lt) { if (w == 0) d0[t] = inf; else d1[t] = inf; }
+                        }
+                    }
+                }
+                bd[u] = nd;
+                bi[u] = ni;
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < kFkQueriesPerWarp; ++u) {
+        const int j = q0 + u;
+        if (j < m && lane >= skip && lane < k) {
+            const size_t o = ((size_t)cloud * m + j) * (k - skip) + (lane - skip);
+            if (dist) dist[o] = bd[u];
+            idx[o] = bi[u];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// EdgeConv dense block
+constexpr int kEcG = 24;          // growth rate of the live generator (DisPU/generator.py:36)
+constexpr int kEcProjW = 4 * kEcG;  // pn | pc | t1 | t2
+constexpr int kEcThreads = 256;
+constexpr int kEcProjRows = 64;
+
+// proj[row] = [f.W0e | f.(W0c-W0e)+b0 | f.W1c+b1 | f.W2c+b2]
+__global__ void __launch_bounds__(kEcThreads)
+edge_proj_kernel(long long rows, int c, const float *__restrict__ feat, int ldf, const float *__restrict__ w0,
+                 const float *__restrict__ b0, const float *__restrict__ w1, const float *__restrict__ b1,
+                 const float *__restrict__ w2, const float *__restrict__ b2, float *__restrict__ proj) {
+    extern __shared__ __align__(16) float ep_smem[];
+    float *s_w = ep_smem;                          // [c][96]
+    float *s_b = s_w + (size_t)c * kEcProjW;       // [96]
+    float *s_f = s_b + kEcProjW;                   // [64][c+1]
+    const int tid = threadIdx.x;
+    const int fs = c + 1;
+    for (int e = tid; e < c * kEcProjW; e += kEcThreads) {
+        const int l = e / kEcProjW, o = e - l * kEcProjW;
+        const int part = o / kEcG, oc = o - part * kEcG;
+        float v;
+        if (part == 0) v = __ldg(w0 + (size_t)(c + l) * kEcG + oc);
+        else if (part == 1) v = __fsub_rn(__ldg(w0 + (size_t)l * kEcG + oc), __ldg(w0 + (size_t)(c + l) * kEcG + oc));
+        else if (part == 2) v = __ldg(w1 + (size_t)(kEcG + l) * kEcG + oc);
+        else v = __ldg(w2 + (size_t)(2 * kEcG + l) * kEcG + oc);
+        s_w[e] = v;
+    }
+    for (int o = tid; o < kEcProjW; o += kEcThreads) {
+        const int part = o / kEcG, oc = o - part * kEcG;
+        float v = 0.f;
+        if (part == 1 && b0) v = __ldg(b0 + oc);
+        if (part == 2 && b1) v = __ldg(b1 + oc);
+        if (part == 3 && b2) v = __ldg(b2 + oc);
+        s_b[o] = v;
+    }
+    const long long row0 = (long long)blockIdx.x * kEcProjRows;
+    for (int e = tid; e < kEcProjRows * c; e += kEcThreads) {
+        const int r = e / c, l = e - r * c;
+        const long long row = row0 + r;
+        s_f[r * fs + l] = row < rows ? __ldg(feat + row * (long long)ldf + l) : 0.f;
+    }
+    __syncthreads();
+    const int r = tid >> 2, part = tid & 3;
+    float acc[kEcG];
+#pragma unroll
+    for (int o = 0; o < kEcG; ++o) acc[o] = s_b[part * kEcG + o];
+    const float4 *w4 = reinterpret_cast<const float4 *>(s_w) + part * (kEcG / 4);
+    for (int l = 0; l < c; ++l) {
+        const float f = s_f[r * fs + l];
+#pragma unroll
+        for (int q = 0; q < kEcG / 4; ++q) {
+            const float4 w = w4[(size_t)l * (kEcProjW / 4) + q];
+            acc[4 * q + 0] = __fmaf_rn(f, w.x, acc[4 * q + 0]);
+            acc[4 * q + 1] = __fmaf_rn(f, w.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = __fmaf_rn(f, w.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = __fmaf_rn(f, w.w, acc[4 * q + 3]);
+        }
+    }
+    const long long row = row0 + r;
+    if (row < rows) {
+        float4 *o4 = reinterpret_cast<float4 *>(proj + row * kEcProjW + part * kEcG);
+#pragma unroll
+        for (int q = 0; q < kEcG / 4; ++q) o4[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+    }
+}
+
+// y += x . W   (x: 24 values, W: 24x24 row-major as float4 rows in shared memory), two edges share the weight loads
+__device__ __forceinline__ void ec_matvec2(const float4 *__restrict__ w4, const float (&xa)[kEcG], const float (&xb)[kEcG],
+                                           float (&ya)[kEcG], float (&yb)[kEcG]) {
+#pragma unroll
+    for (int i = 0; i < kEcG; ++i) {
+#pragma unroll
+        for (int q = 0; q < kEcG / 4; ++q) {
+            const float4 w = w4[i * (kEcG / 4) + q];
+            ya[4 * q + 0] = __fmaf_rn(xa[i], w.x, ya[4 * q + 0]);
+            ya[4 * q + 1] = __fmaf_rn(xa[i], w.y, ya[4 * q + 1]);
+            ya[4 * q + 2] = __fmaf_rn(xa[i], w.z, ya[4 * q + 2]);
+            ya[4 * q + 3] = __fmaf_rn(xa[i], w.w, ya[4 * q + 3]);
+            yb[4 * q + 0] = __fmaf_rn(xb[i], w.x, yb[4 * q + 0]);
+            yb[4 * q + 1] = __fmaf_rn(xb[i], w.y, yb[4 * q + 1]);
+            yb[4 * q + 2] = __fmaf_rn(xb[i], w.z, yb[4 * q + 2]);
+            yb[4 * q + 3] = __fmaf_rn(xb[i], w.w, yb[4 * q + 3]);
+        }
+    }
+}
+
+__device__ __forceinline__ void ec_load24(const float *__restrict__ p, float (&v)[kEcG]) {
+    const float4 *p4 = reinterpret_cast<const float4 *>(p);
+#pragma unroll
+    for (int q = 0; q < kEcG / 4; ++q) {
+        const float4 t = __ldg(p4 + q);
+        v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+    }
+}
+
+// 8 lanes per point, two edges per lane per pass (k = 16: one pass).  out row = [max y2 | max y1 | max y0 | f_i].
+__global__ void __launch_bounds__(kEcThreads, 1)
+edge_mlp_max_kernel(long long rows, int n, int c, int k, const float *__restrict__ proj, const int *__restrict__ idx,
+                    const float *__restrict__ w1, const float *__restrict__ w2, const float *__restrict__ feat, int ldf,
+                    float *__restrict__ out, int ldo) {
+    __shared__ __align__(16) float s_w1a[kEcG * kEcG], s_w2a[kEcG * kEcG], s_w2b[kEcG * kEcG];
+    const int tid = threadIdx.x;
+    for (int e = tid; e < kEcG * kEcG; e += kEcThreads) {
+        s_w1a[e] = __ldg(w1 + e);                  // W1[:g]
+        s_w2a[e] = __ldg(w2 + e);                  // W2[:g]     (multiplies y1)
+        s_w2b[e] = __ldg(w2 + kEcG * kEcG + e);    // W2[g:2g]   (multiplies y0)
+    }
+    __syncthreads();
+    const int t = tid & 7;
+    const long long row = (long long)blockIdx.x * (kEcThreads / 8) + (tid >> 3);
+    const bool valid = row < rows;
+    const long long rowc = valid ? row : rows - 1;  // keep every lane in the shuffles
+    const long long cloud = rowc / n;
+    const float *prow = proj + rowc * kEcProjW;
+    const int *irow = idx + rowc * (long long)k;
+    const float neg_inf = __int_as_float(0xff800000);
+    float m0[kEcG], m1[kEcG], m2[kEcG];
+#pragma unroll
+    for (int o = 0; o < kEcG; ++o) { m0[o] = neg_inf; m1[o] = neg_inf; m2[o] = neg_inf; }
+
+    for (int s0 = t; s0 < k; s0 += 16) {
+        const int s1 = (s0 + 8 < k) ? s0 + 8 : s0;  // odd tail: the duplicate edge does not change the max
+        const int ja = __ldg(irow + s0), jb = __ldg(irow + s1);
+        float ya0[kEcG], yb0[kEcG];
+        {
+            float pc[kEcG];
+            ec_load24(prow + kEcG, pc);
+            ec_load24(proj + (cloud * n + ja) * kEcProjW, ya0);
+            ec_load24(proj + (cloud * n + jb) * kEcProjW, yb0);
+#pragma unroll
+            for (int o = 0; o < kEcG; ++o) {
+                ya0[o] = fmaxf(__fadd_rn(ya0[o], pc[o]), 0.f);
+                yb0[o] = fmaxf(__fadd_rn(yb0[o], pc[o]), 0.f);
+            }
+        }
+        float ya2[kEcG], yb2[kEcG];
+        ec_load24(prow + 3 * kEcG, ya2);
+#pragma unroll
+        for (int o = 0; o < kEcG; ++o) yb2[o] = ya2[o];
+        ec_matvec2(reinterpret_cast<const float4 *>(s_w2b), ya0, yb0, ya2, yb2);
+        float ya1[kEcG], yb1[kEcG];
+        ec_load24(prow + 2 * kEcG, ya1);
+#pragma unroll
+        for (int o = 0; o < kEcG; ++o) yb1[o] = ya1[o];
+        ec_matvec2(reinterpret_cast<const float4 *>(s_w1a), ya0, yb0, ya1, yb1);
+#pragma unroll
+        for (int o = 0; o < kEcG; ++o) {
+            m0[o] = fmaxf(m0[o], fmaxf(ya0[o], yb0[o]));
+            ya1[o] = fmaxf(ya1[o], 0.f);
+            yb1[o] = fmaxf(yb1[o], 0.f);
+            m1[o] = fmaxf(m1[o], fmaxf(ya1[o], yb1[o]));
+        }
+        ec_matvec2(reinterpret_cast<const float4 *>(s_w2a), ya1, yb1, ya2, yb2);
+#pragma unroll
+        for (int o = 0; o < kEcG; ++o) m2[o] = fmaxf(m2[o], fmaxf(ya2[o], yb2[o]));
+    }
+    // max over the 8 lanes of the point
+#pragma unroll
+    for (int off = 1; off < 8; off <<= 1) {
+#pragma unroll
+        for (int o = 0; o < kEcG; ++o) {
+            m0[o] = fmaxf(m0[o], __shfl_xor_sync(kFull, m0[o], off));
+            m1[o] = fmaxf(m1[o], __shfl_xor_sync(kFull, m1[o], off));
+            m2[o] = fmaxf(m2[o], __shfl_xor_sync(kFull, m2[o], off));
+        }
+    }
+    if (!valid) return;
+    float4 *o4 = reinterpret_cast<float4 *>(out + row * (long long)ldo);
+    // 18 float4 of maxima: chunk q goes to lane q % 8 (static register indices, predicated stores)
+#pragma unroll
+    for (int q = 0; q < kEcG / 4; ++q) {
+        if ((q & 7) == t) o4[q] = make_float4(m2[4 * q], m2[4 * q + 1], m2[4 * q + 2], m2[4 * q + 3]);
+        if (((q + 6) & 7) == t) o4[q + 6] = make_float4(m1[4 * q], m1[4 * q + 1], m1[4 * q + 2], m1[4 * q + 3]);
+        if (((q + 12) & 7) == t) o4[q + 12] = make_float4(m0[4 * q], m0[4 * q + 1], m0[4 * q + 2], m0[4 * q + 3]);
+    }
+    const float4 *f4 = reinterpret_cast<const float4 *>(feat + row * (long long)ldf);
+    for (int q = t; q < c / 4; q += 8) o4[3 * kEcG / 4 + q] = __ldg(f4 + q);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// weight net + transposed product:  H[i][ch][t] = sum_s G[i][s][ch] * relu(((xyz[idx[i][s]]-xyz[i]).Ww[:,t] + bw[t]) * scale)
+constexpr int kWaThreads = 256;
+constexpr int kWaPts = 4;   // points per CTA
+constexpr int kWaNs = 16;   // nsample
+constexpr int kWaT = 16;    // hidden units of the weight net
+constexpr int kWaC = 128;   // channels of G
+
+__global__ void __launch_bounds__(kWaThreads)
+weightnet_aggregate_kernel(long long pts_total, int m, const float *__restrict__ xyz, const int *__restrict__ idx,
+                           const float *__restrict__ G, const float *__restrict__ Ww, const float *__restrict__ bw,
+                           float bn_scale, float *__restrict__ out) {
+    __shared__ __align__(16) float s_g[kWaPts][kWaNs][kWaC];   // 32 KB
+    __shared__ __align__(16) float s_wn[kWaPts][kWaNs][kWaT];  // 4 KB
+    const int tid = threadIdx.x;
+    const long long p0 = (long long)blockIdx.x * kWaPts;
+    const int np = (int)min((long long)kWaPts, pts_total - p0);
+    {
+        const float4 *g4 = reinterpret_cast<const float4 *>(G + p0 * (long long)(kWaNs * kWaC));
+        float4 *s4 = reinterpret_cast<float4 *>(&s_g[0][0][0]);
+        const int n4 = np * kWaNs * kWaC / 4;
+        for (int e = tid; e < n4; e += kWaThreads) s4[e] = __ldg(g4 + e);
+    }
+    for (int e = tid; e < np * kWaNs * kWaT; e += kWaThreads) {
+        const int p = e / (kWaNs * kWaT), rem = e - p * (kWaNs * kWaT);
+        const int s = rem / kWaT, t = rem - s * kWaT;
+        const long long pt = p0 + p;
+        const long long cloud = pt / m;
+        const float *ctr = xyz + pt * 3;
+        const float *q = xyz + (cloud * m + __ldg(idx + pt * kWaNs + s)) * 3;
+        const float gx = __fsub_rn(__ldg(q), __ldg(ctr)), gy = __fsub_rn(__ldg(q + 1), __ldg(ctr + 1)),
+                    gz = __fsub_rn(__ldg(q + 2), __ldg(ctr + 2));
+        float a = __fmaf_rn(gz, __ldg(Ww + 2 * kWaT + t), __fmaf_rn(gy, __ldg(Ww + kWaT + t), __fmul_rn(gx, __ldg(Ww + t))));
+        a = __fmul_rn(__fadd_rn(a, bw ? __ldg(bw + t) : 0.f), bn_scale);
+        s_wn[p][s][t] = fmaxf(a, 0.f);
+    }
+    __syncthreads();
+    // thread -> (point pair slot, 4 channels, 4 hidden units): 16 accumulators, 16 FMA per two LDS.128
+    const int half = tid >> 7;         // which of two points per pass
+    const int chq = (tid & 127) >> 2;  // channels 4*chq .. 4*chq+3
+    const int tq = tid & 3;            // hidden units 4*tq .. 4*tq+3
+    for (int pp = half; pp < np; pp += 2) {
+        float acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b2 = 0; b2 < 4; ++b2) acc[a][b2] = 0.f;
+#pragma unroll
+        for (int s = 0; s < kWaNs; ++s) {
+            const float4 g = *reinterpret_cast<const float4 *>(&s_g[pp][s][4 * chq]);
+            const float4 w = *reinterpret_cast<const float4 *>(&s_wn[pp][s][4 * tq]);
+            const float gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                acc[a][0] = __fmaf_rn(gv[a], w.x, acc[a][0]);
+                acc[a][1] = __fmaf_rn(gv[a], w.y, acc[a][1]);
+                acc[a][2] = __fmaf_rn(gv[a], w.z, acc[a][2]);
+                acc[a][3] = __fmaf_rn(gv[a], w.w, acc[a][3]);
+            }
+        }
+        float *o = out + (p0 + pp) * (long long)(kWaC * kWaT);
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+            *reinterpret_cast<float4 *>(o + (4 * chq + a) * kWaT + 4 * tq) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+    }
+}
+
+static inline bool ec_aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace dispu
+
+using namespace dispu;
+
+template <int P>
+static int launch_feature_knn(int b, int n, int m, int c, int k, int skip, const float *points, int ldp, const float *queries,
+                              int ldq, float *dist, int *idx, cudaStream_t stream) {
+    const size_t smem = ((size_t)c * (32 * P + 1) + 32 * P + (size_t)kFkWarps * 2 * c) * sizeof(float);
+    if (smem > 220 * 1024) return DISPU_EUNSUPPORTED;
+    cudaError_t e = cudaFuncSetAttribute(feature_knn_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    count_launch();
+    dim3 grid(ceil_div(m, kFkWarps * kFkQueriesPerWarp), b);
+    feature_knn_kernel<P><<<grid, kFkWarps * 32, smem, stream>>>(n, m, c, k, skip, points, ldp, queries, ldq, dist, idx);
+    return finish_launch();
+}
+
+extern "C" int dispu_feature_knn(int b, int n, int m, int c, int k, int skip, const float *points, int ldp,
+                                 const float *queries, int ldq, float *dist, int *idx, dispu_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DISPU_REQUIRE(b >= 0 && n > 0 && m >= 0 && c > 0 && k > 0 && skip >= 0 && skip < k, DISPU_EINVAL);
+    DISPU_REQUIRE(k <= n && ldp >= c && ldq >= c, DISPU_EINVAL);
+    DISPU_REQUIRE(k <= 32 && c <= 128, DISPU_EUNSUPPORTED);
+    if (b == 0 || m == 0) return DISPU_OK;
+    DISPU_REQUIRE(points && queries && idx, DISPU_ENULL);
+    // largest chunk (32*P candidates) that covers the cloud and whose transposed features fit in shared memory
+    auto fits = [&](int P) { return ((size_t)c * (32 * P + 1) + 32 * P + (size_t)kFkWarps * 2 * c) * sizeof(float) <= 220 * 1024; };
+    if (n > 512 && fits(32)) return launch_feature_knn<32>(b, n, m, c, k, skip, points, ldp, queries, ldq, dist, idx, stream);
+    if (n > 256 && fits(16)) return launch_feature_knn<16>(b, n, m, c, k, skip, points, ldp, queries, ldq, dist, idx, stream);
+    return launch_feature_knn<8>(b, n, m, c, k, skip, points, ldp, queries, ldq, dist, idx, stream);
+}
+
+extern "C" size_t dispu_dense_conv_workspace_bytes(int b, int n) {
+    if (b <= 0 || n <= 0) return 0;
+    return (size_t)b * n * kEcProjW * sizeof(float);
+}
+
+extern "C" int dispu_dense_conv(int b, int n, int c, int k, int growth, const float *feat, int ldf, const int *idx,
+                                const float *w0, const float *b0, const float *w1, const float *b1, const float *w2,
+                                const float *b2, float *out, int ldo, void *workspace, size_t workspace_bytes,
+                                dispu_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DISPU_REQUIRE(b >= 0 && n > 0 && c > 0 && k > 0 && growth > 0, DISPU_EINVAL);
+    DISPU_REQUIRE(ldf >= c && ldo >= 3 * growth + c, DISPU_EINVAL);
+    DISPU_REQUIRE(growth == kEcG && c % 4 == 0 && c <= 128 && ldf % 4 == 0 && ldo % 4 == 0, DISPU_EUNSUPPORTED);
+    if (b == 0) return DISPU_OK;
+    DISPU_REQUIRE(feat && idx && w0 && w1 && w2 && out, DISPU_ENULL);
+    DISPU_REQUIRE(ec_aligned16(feat) && ec_aligned16(out), DISPU_EUNSUPPORTED);
+    DISPU_REQUIRE(workspace && workspace_bytes >= dispu_dense_conv_workspace_bytes(b, n) && ec_aligned16(workspace),
+                  DISPU_EWORKSPACE);
+    float *proj = reinterpret_cast<float *>(workspace);
+    const long long rows = (long long)b * n;
+    const size_t smem = ((size_t)c * kEcProjW + kEcProjW + (size_t)kEcProjRows * (c + 1)) * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(edge_proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    count_launch(2);
+    edge_proj_kernel<<<(unsigned)ceil_div64(rows, kEcProjRows), kEcThreads, smem, stream>>>(rows, c, feat, ldf, w0, b0, w1, b1,
+                                                                                          w2, b2, proj);
+    edge_mlp_max_kernel<<<(unsigned)ceil_div64(rows, kEcThreads / 8), kEcThreads, 0, stream>>>(rows, n, c, k, proj, idx, w1, w2,
+                                                                                             feat, ldf, out, ldo);
+    return finish_launch();
+}
+
+extern "C" int dispu_weightnet_aggregate(int b, int m, int nsample, int C, int T, const float *xyz, const int *idx,
+                                         const float *G, const float *Ww, const float *bw, float bn_scale, float *out,
+                                         dispu_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DISPU_REQUIRE(b >= 0 && m > 0 && nsample > 0 && C > 0 && T > 0, DISPU_EINVAL);
+    DISPU_REQUIRE(nsample == kWaNs && C == kWaC && T == kWaT, DISPU_EUNSUPPORTED);
+    if (b == 0) return DISPU_OK;
+    DISPU_REQUIRE(xyz && idx && G && Ww && out, DISPU_ENULL);
+    DISPU_REQUIRE(ec_aligned16(G) && ec_aligned16(out), DISPU_EUNSUPPORTED);
+    const long long pts = (long long)b * m;
+    count_launch();
+    weightnet_aggregate_kernel<<<(unsigned)ceil_div64(pts, kWaPts), kWaThreads, 0, stream>>>(pts, m, xyz, idx, G, Ww, bw,
+                                                                                           bn_scale, out);
+    return finish_launch();
+}

@@ -159,8 +159,8 @@ group_affine_relu_kernel(long long total_vec, int m_ns, int ns, int n, int c_vec
 // (e.g. the skip connection of PointShuffle2, Common/ops.py:1049: reduce_max(grouped_feat, axis=2)).
 template <int VEC>
 __global__ void __launch_bounds__(kThreads)
-group_max_kernel(long long total_vec, int m, int ns, int n, int c_vec, const float *__restrict__ points,
-                 const int *__restrict__ idx, float *__restrict__ out) {
+group_max_kernel(long long total_vec, int m, int ns, int n, int c_vec, const float *__restrict__ points, long long ldp_vec,
+                 const int *__restrict__ idx, float *__restrict__ out, long long ldo_vec) {
     for (long long e = (long long)blockIdx.x * kThreads + threadIdx.x; e < total_vec;
          e += (long long)gridDim.x * kThreads) {
         const long long grp = e / c_vec;  // (b, i)
@@ -169,16 +169,16 @@ group_max_kernel(long long total_vec, int m, int ns, int n, int c_vec, const flo
         const int *row = idx + grp * ns;
         if (VEC == 4) {
             const float4 *p4 = reinterpret_cast<const float4 *>(points);
-            float4 mx = __ldg(p4 + (cloud * n + __ldg(row)) * (long long)c_vec + l);
+            float4 mx = __ldg(p4 + (cloud * n + __ldg(row)) * ldp_vec + l);
             for (int s = 1; s < ns; ++s) {
-                const float4 v = __ldg(p4 + (cloud * n + __ldg(row + s)) * (long long)c_vec + l);
+                const float4 v = __ldg(p4 + (cloud * n + __ldg(row + s)) * ldp_vec + l);
                 mx.x = fmaxf(mx.x, v.x); mx.y = fmaxf(mx.y, v.y); mx.z = fmaxf(mx.z, v.z); mx.w = fmaxf(mx.w, v.w);
             }
-            reinterpret_cast<float4 *>(out)[e] = mx;
+            reinterpret_cast<float4 *>(out)[grp * ldo_vec + l] = mx;
         } else {
-            float mx = __ldg(points + (cloud * n + __ldg(row)) * (long long)c_vec + l);
-            for (int s = 1; s < ns; ++s) mx = fmaxf(mx, __ldg(points + (cloud * n + __ldg(row + s)) * (long long)c_vec + l));
-            out[e] = mx;
+            float mx = __ldg(points + (cloud * n + __ldg(row)) * ldp_vec + l);
+            for (int s = 1; s < ns; ++s) mx = fmaxf(mx, __ldg(points + (cloud * n + __ldg(row + s)) * ldp_vec + l));
+            out[grp * ldo_vec + l] = mx;
         }
     }
 }
@@ -309,20 +309,27 @@ extern "C" int dispu_group_affine_relu(int b, int n, int c, int m, int nsample, 
     return finish_launch();
 }
 
-extern "C" int dispu_group_max(int b, int n, int c, int m, int nsample, const float *points, const int *idx, float *out,
-                               dispu_stream_t stream_) {
+extern "C" int dispu_group_max_ld(int b, int n, int c, int m, int nsample, const float *points, int ldp, const int *idx,
+                                  float *out, int ldo, dispu_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     DISPU_REQUIRE(b >= 0 && n > 0 && c >= 0 && m >= 0 && nsample > 0, DISPU_EINVAL);
+    DISPU_REQUIRE(ldp >= c && ldo >= c, DISPU_EINVAL);
     if (b == 0 || m == 0 || c == 0) return DISPU_OK;
     DISPU_REQUIRE(points && idx && out, DISPU_ENULL);
     const long long groups = (long long)b * m;
     count_launch();
-    if (c % 4 == 0 && aligned16(points) && aligned16(out)) {
+    if (c % 4 == 0 && ldp % 4 == 0 && ldo % 4 == 0 && aligned16(points) && aligned16(out)) {
         const long long total = groups * (c / 4);
-        group_max_kernel<4><<<grid_for(total), kThreads, 0, stream>>>(total, m, nsample, n, c / 4, points, idx, out);
+        group_max_kernel<4><<<grid_for(total), kThreads, 0, stream>>>(total, m, nsample, n, c / 4, points, ldp / 4, idx, out,
+                                                                      ldo / 4);
     } else {
         const long long total = groups * c;
-        group_max_kernel<1><<<grid_for(total), kThreads, 0, stream>>>(total, m, nsample, n, c, points, idx, out);
+        group_max_kernel<1><<<grid_for(total), kThreads, 0, stream>>>(total, m, nsample, n, c, points, ldp, idx, out, ldo);
     }
     return finish_launch();
+}
+
+extern "C" int dispu_group_max(int b, int n, int c, int m, int nsample, const float *points, const int *idx, float *out,
+                               dispu_stream_t stream_) {
+    return dispu_group_max_ld(b, n, c, m, nsample, points, c, idx, out, c, stream_);
 }

@@ -1,15 +1,23 @@
-"""Dense layer on the tcgen05 tensor cores with FP32-level accuracy (3xTF32): y = act(x.W + b).
-The weight is packed once (TF32 hi/lo planes, UMMA layout); see dispu_dense_tf32x3 in include/dispu_b200.h."""
+"""Dense layer on the tcgen05 tensor cores with FP32-level accuracy (3xTF32): y = act(x.W + b) [+ residuals].
+The weight is packed once (TF32 hi/lo planes, UMMA layout); see dispu_dense_tf32x3(_ex) in include/dispu_b200.h."""
 from __future__ import annotations
+
+import ctypes as C
 
 import torch
 
 from . import _lib
-from ._t import call, ptr, req, stream_ptr
+from ._t import call, ptr, req, rows, stream_ptr
 
 
 class PackedLinear:
-    """W (K,N) float32 with N <= 256, optional bias (N,).  __call__(x (..., K), relu) -> (..., N)."""
+    """W (K,N) float32 with N <= 256, optional bias (N,).  __call__(x (..., K), relu) -> (..., N).
+
+    x may be a column slice of a wider buffer (x[..., a:a+K]); `out` may be one too — the layer then writes
+    straight into its slot of a concatenated tensor.  `gather=(idx, Q, sign)`: the operand rows are
+    relu(x[b, idx[b,i,s], :] + sign*Q[b,i,:]) (x is the per-point table (b,n,K), idx (b,m,ns), Q (b,m,K) or None),
+    i.e. GroupPoint + centre term + ReLU fused into the load.  `residuals`: up to two (..., N) tensors added after
+    the activation."""
 
     def __init__(self, weight, bias=None):
         weight = req(weight, torch.float32, 2, "weight")
@@ -21,12 +29,82 @@ class PackedLinear:
         self.packed = torch.empty((nbytes,), dtype=torch.uint8, device=weight.device)
         call("dispu_dense_pack", self.K, self.N, ptr(weight), ptr(self.packed), stream_ptr())
 
-    def __call__(self, x, relu=False):
-        x = x.contiguous()
-        if x.dtype != torch.float32 or not x.is_cuda or x.shape[-1] != self.K:
-            raise ValueError(f"PackedLinear expects a float32 CUDA tensor with last dim {self.K}")
-        M = x.numel() // self.K
-        y = torch.empty((*x.shape[:-1], self.N), dtype=torch.float32, device=x.device)
-        call("dispu_dense_tf32x3", M, self.K, self.N, ptr(x), ptr(self.packed), ptr(self.bias), 1 if relu else 0, ptr(y),
-             stream_ptr())
-        return y
+    def __call__(self, x, relu=False, out=None, gather=None, residuals=()):
+        if x.shape[-1] != self.K:
+            raise ValueError(f"PackedLinear expects last dim {self.K}, got {tuple(x.shape)}")
+        a = _lib.DenseArgs()
+        xp, xm, ldx = rows(x, "x")
+        a.K, a.N, a.X, a.ldx = self.K, self.N, xp, ldx
+        a.packed, a.bias, a.relu = ptr(self.packed), ptr(self.bias), 1 if relu else 0
+        if gather is not None:
+            idx, Q, sign = gather
+            idx = req(idx, torch.int32, 3, "idx")
+            b, m, ns = idx.shape
+            if x.dim() != 3 or x.shape[0] != b:
+                raise ValueError("gather: x must be (b,n,K)")
+            a.gather_idx, a.gather_n, a.gather_ns, a.gather_rows_per_cloud = ptr(idx), x.shape[1], ns, m * ns
+            if Q is not None:
+                qp, qm, ldq = rows(Q, "Q")
+                if qm != b * m or Q.shape[-1] != self.K:
+                    raise ValueError("gather: Q must be (b,m,K)")
+                a.Q, a.ldq = qp, ldq
+            a.sign = float(sign)
+            M = b * m * ns
+            oshape = (b, m, ns, self.N)
+        else:
+            M = xm
+            oshape = (*x.shape[:-1], self.N)
+        a.M = M
+        if out is None:
+            out = torch.empty(oshape, dtype=torch.float32, device=x.device)
+        yp, ym, ldy = rows(out, "out")
+        if ym != M or out.shape[-1] != self.N:
+            raise ValueError(f"out: expected {M} rows of {self.N}, got {tuple(out.shape)}")
+        a.Y, a.ldy = yp, ldy
+        for i, r in enumerate(residuals):
+            rp, rm, ldr = rows(r, "residual")
+            if rm != M or r.shape[-1] != self.N:
+                raise ValueError("residual shape mismatch")
+            if i == 0:
+                a.R1, a.ldr1 = rp, ldr
+            elif i == 1:
+                a.R2, a.ldr2 = rp, ldr
+            else:
+                raise ValueError("at most two residuals")
+        call("dispu_dense_tf32x3_ex", C.byref(a), stream_ptr())
+        return out
+
+
+class BatchedOperand:
+    """Per-batch right-hand operands W_i (K,N), N <= 256, packed every call from a strided source:
+    W_i[k][n] = src[i*batch_stride + k*stride_k + n*stride_n] — e.g. k^T and v of PointNonLocalCell
+    (Common/ops.py:326-339), which are activations, not weights."""
+
+    def __init__(self, batch, K, N, device):
+        self.batch, self.K, self.N = batch, K, N
+        nb = int(_lib.lib().dispu_dense_packed_bytes(K, N))
+        self.stride = (nb + 15) // 16 * 16
+        self.packed = torch.empty((batch * self.stride,), dtype=torch.uint8, device=device)
+
+    def pack(self, src, offset, stride_k, stride_n, batch_stride):
+        """src: float32 CUDA tensor (storage base); offset in floats."""
+        if src.dtype != torch.float32 or not src.is_cuda:
+            raise ValueError("BatchedOperand.pack expects a float32 CUDA tensor")
+        call("dispu_dense_pack_strided", self.K, self.N, src.data_ptr() + 4 * offset, stride_k, stride_n, self.batch,
+             batch_stride, ptr(self.packed), self.stride, stream_ptr())
+        return self
+
+    def matmul(self, x, out=None, relu=False):
+        """x (batch, rows, K) [row-strided ok] -> out (batch, rows, N); rows % 128 == 0."""
+        a = _lib.DenseArgs()
+        xp, xm, ldx = rows(x, "x")
+        if x.dim() != 3 or x.shape[0] != self.batch or x.shape[2] != self.K:
+            raise ValueError("BatchedOperand.matmul: x must be (batch, rows, K)")
+        if out is None:
+            out = torch.empty((self.batch, x.shape[1], self.N), dtype=torch.float32, device=x.device)
+        yp, ym, ldy = rows(out, "out")
+        a.M, a.K, a.N, a.X, a.ldx = xm, self.K, self.N, xp, ldx
+        a.packed, a.relu, a.Y, a.ldy = ptr(self.packed), 1 if relu else 0, yp, ldy
+        a.rows_per_batch, a.packed_batch_stride = x.shape[1], self.stride
+        call("dispu_dense_tf32x3_ex", C.byref(a), stream_ptr())
+        return out

@@ -46,11 +46,29 @@ class DispuOps:
 
     # fused forms of GroupPoint (no (b,m,k,c) intermediates); their presence switches the generator to the
     # hoisted formulation of the first grouped layer (see Generator._dense_conv / point_shuffle)
-    def group_max(self, feature, idx):
-        return tf_grouping.group_max(feature, idx)
+    def group_max(self, feature, idx, out=None):
+        return tf_grouping.group_max(feature, idx, out=out)
 
     def group_affine_relu(self, P, Q, idx, sign):
         return tf_grouping.group_affine_relu(P, Q, idx, sign)
+
+
+def _lib_dense_args():
+    from . import _lib
+    return _lib.DenseArgs()
+
+
+def _batched_matmul(a, x, op, j, nb, out):
+    """out (b,rows,N) = x (b,rows,K) . W_{b*nb + j}: one column block of a per-cloud product (see BatchedOperand)."""
+    import ctypes as C
+    from ._t import call, ptr, rows, stream_ptr
+    xp, xm, ldx = rows(x, "x")
+    yp, ym, ldy = rows(out, "out")
+    a.M, a.K, a.N, a.X, a.ldx = xm, op.K, op.N, xp, ldx
+    a.packed, a.relu, a.Y, a.ldy = ptr(op.packed) + j * op.stride, 0, yp, ldy
+    a.rows_per_batch, a.packed_batch_stride = x.shape[1], nb * op.stride
+    call("dispu_dense_tf32x3_ex", C.byref(a), stream_ptr())
+    return out
 
 
 def _xavier(gen, cin, cout, device, fan_in=None, fan_out=None):
@@ -64,9 +82,13 @@ def _xavier(gen, cin, cout, device, fan_in=None, fan_out=None):
 class Generator:
     """coarse, fine = G(inputs (b,n,3)); up_ratio 4: (b,4n,3) each."""
 
-    def __init__(self, up_ratio=4, device="cuda", seed=7, ops=None, hoist=True, tc=True):
+    def __init__(self, up_ratio=4, device="cuda", seed=7, ops=None, hoist=True, tc=True, fused=None):
         self.up_ratio = up_ratio
         self.tc = tc  # dense layers on the tcgen05 3xTF32 kernel (GPU only)
+        # fused: the whole forward on this library's kernels with no concat / slice / gather intermediates
+        # (forward_fused); default = whenever the CUDA backend, hoisting and the tensor-core layers are all on
+        self.fused = fused
+        self._bufs = {}
         self._packed = {}
         self.hoist = hoist  # use the fused / hoisted grouped-layer formulation when the backend offers it
         self.device = torch.device(device)
@@ -242,7 +264,113 @@ class Generator:
         gf = gf + skip + nonlocal_pt
         return self._fc(gf, "aggregation")
 
+    # -- fused forward ------------------------------------------------------------------------------
+    def _prepare_fused(self):
+        """Derived weights of the fused formulation (exact reassociations of the reference's 1x1 convs)."""
+        if "_f_ready" in self.P:
+            return
+        P = self.P
+        wq, bq = P["nl_query"]
+        P["_f_query"] = ((wq * 0.125).contiguous(), (bq * 0.125).contiguous())  # softmax(q.k/sqrt(64)): 1/8 is exact
+        w, b = P["up_conv1"]
+        P["_f_up1"] = (w[:480].contiguous(), b)
+        P["_f_grid"] = torch.matmul(self.grid, w[480:482]).contiguous()  # (r, 256): the grid columns of the tiled input
+        w0, b0 = P["conv0"]  # rows: [x_j - x_i (3) | x_j (3) | f_j (128)]
+        z1 = torch.zeros((1, w0.shape[1]), device=w0.device)
+        P["_f_psp"] = (torch.cat([z1, w0[0:3] + w0[3:6], w0[6:]], dim=0).contiguous(), b0)  # on [0 | x | f] (132)
+        P["_f_psq"] = (w0[0:3].contiguous(), None)
+        ws, bs = P["skip"]  # rows as conv0; input = [max_s x_j - x_i | max_s x_j | max_s f_j]
+        z = torch.zeros((1, ws.shape[1]), device=ws.device)
+        P["_f_skip"] = (torch.cat([z, ws[0:3] + ws[3:6], ws[6:], -ws[0:3], z], dim=0).contiguous(), bs)  # on [0|mx|mf|x_i|0] (136)
+        P["_f_ready"] = True
+
+    def _buffers(self, b, n, dev):
+        key = (b, n, str(dev))
+        if key not in self._bufs:
+            m = n * self.up_ratio
+            self._bufs[key] = {
+                "feat": torch.zeros((b, n, 480), dtype=torch.float32, device=dev),
+                "xf": torch.zeros((b, m, 132), dtype=torch.float32, device=dev),   # [0 | coarse xyz | coarse_feat]
+                "mxz": torch.zeros((b, m, 136), dtype=torch.float32, device=dev),  # [group_max(xf) | coarse xyz | 0]
+            }
+        return self._bufs[key]
+
+    def _fx(self, x, name, act=True, **kw):
+        """Dense layer `name` on the tcgen05 kernel with the extended options of dense.PackedLinear.__call__."""
+        lin = self._packed.get(name)
+        if lin is None:
+            from .dense import PackedLinear
+            w, b = self.P[name]
+            lin = self._packed[name] = PackedLinear(w, b)
+        return lin(x, relu=act, **kw)
+
+    def forward_fused(self, inputs):
+        """Same function as forward() with every layer on this library's kernels: layers write into their slot of the
+        tensors the reference builds with tf.concat, grouped layers gather inside the operand load, the EdgeConv
+        dense blocks and the feature-space kNN are single kernels, the non-local attention is two batched tcgen05
+        products around a softmax."""
+        from . import ops as O
+        from .dense import BatchedOperand
+        self._prepare_fused()
+        P = self.P
+        b, n, _ = inputs.shape
+        m = n * self.up_ratio
+        dev = inputs.device
+        buf = self._buffers(b, n, dev)
+        feat, xf, mxz = buf["feat"], buf["xf"], buf["mxz"]
+        # ---- feature_extraction_GCN (ops.py:1437-1486): feat = [blk4 | blk3 | blk2 | blk1 (96) | l0 (24)]
+        l0 = feat[..., 456:480]
+        self._fx(inputs, "layer0", act=False, out=l0)
+        O.dense_conv(l0, [P[f"layer1_l{i}"] for i in range(3)], out=feat[..., 360:456])
+        for blk, lo in ((2, 240), (3, 120), (4, 0)):
+            prep = self._fx(feat[..., lo + 120:480], f"layer{blk}_prep")
+            O.dense_conv(prep, [P[f"layer{blk}_l{i}"] for i in range(3)], out=feat[..., lo:lo + 120])
+        # ---- duplicate_up (ops.py:1152-1199): the tiled features share one product; copy r adds its grid term
+        h = self._fx(feat, "_f_up1", act=False)  # (b,n,256)
+        net = torch.relu_(h.unsqueeze(1) + P["_f_grid"].view(1, self.up_ratio, 1, -1)).view(b, m, -1)
+        coarse_feat = xf[..., 4:132]
+        self._fx(net, "up_conv2", out=coarse_feat)
+        # ---- coarse coordinate_regressor
+        coarse = self._fx(self._fx(self._fx(coarse_feat, "coarse_fc0"), "coarse_fc1"), "coarse_fc2", act=False)
+        xf[..., 1:4].copy_(coarse)
+        # ---- PointShuffle2 (ops.py:1012-1087)
+        idx = self.ops.knn3d(16, coarse, coarse)
+        # non-local cell (PointNonLocalCell ops.py:302-346): q.k^T and att.v as batched tcgen05 products
+        kv = self._fx(coarse_feat, "nl_kv", act=False)       # (b,m,128): key | value
+        q = self._fx(coarse_feat, "_f_query", act=False)     # (b,m,64), pre-scaled by 1/sqrt(64)
+        nb = m // 256
+        if m % 256:
+            raise ValueError("forward_fused: 4*n must be a multiple of 256")
+        kop = BatchedOperand(b * nb, 64, 256, dev).pack(kv, 0, 1, 128, 256 * 128)
+        att = torch.empty((b, m, m), dtype=torch.float32, device=dev)
+        a = _lib_dense_args()
+        for j in range(nb):
+            _batched_matmul(a, q, kop, j, nb, att[..., j * 256:(j + 1) * 256])
+        att = torch.softmax(att, dim=-1)
+        vop = BatchedOperand(b, m, 64, dev).pack(kv, 64, 128, 1, m * 128)
+        nonlocal_pt = self._fx(vop.matmul(att), "nl_back")
+        # local cell: conv0 hoisted to per-point products, gathered + ReLU'd inside conv1's operand load
+        pm = self._fx(xf, "_f_psp", act=False)       # (b,m,128) = x_j(Wa+Wb) + f_j Wc + b
+        qm = self._fx(coarse, "_f_psq", act=False)   # (b,m,128) = x_i Wa
+        gf = self._fx(pm, "conv1", gather=(idx, qm, -1.0))  # (b,m,16,128)
+        ww, bw = P["wconv0"]
+        H = O.weightnet_aggregate(coarse, idx, gf, ww, bw, 1.0 / math.sqrt(1.0 + BN_EPS))  # (b,m,2048)
+        # skip connection: max over the group commutes with the centre shift
+        self.ops.group_max(xf, idx, out=mxz[..., 0:132])
+        mxz[..., 132:135].copy_(coarse)
+        skip = self._fx(mxz, "_f_skip")
+        g = self._fx(H, "after_conv", residuals=(skip, nonlocal_pt))
+        fine_feat = self._fx(g, "aggregation")
+        off = self._fx(self._fx(self._fx(fine_feat, "fine_fc0"), "fine_fc1"), "fine_fc2", act=False)
+        fine = coarse + (torch.sigmoid(off) - 0.5)
+        return coarse, fine
+
     def forward(self, inputs):
+        fused = self.fused
+        if fused is None:
+            fused = self.tc and self.hoist and inputs.is_cuda and isinstance(self.ops, DispuOps)
+        if fused:
+            return self.forward_fused(inputs)
         feat = self.feature_extraction(inputs)
         coarse_feat = self.duplicate_up(feat)
         coarse = self.regressor(coarse_feat, "coarse")

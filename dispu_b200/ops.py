@@ -48,3 +48,48 @@ def dilat_group(xyz, points, k, dilation=1, use_xyz=False):
     else:
         grouped_points = grouped_xyz
     return grouped_xyz, grouped_points, idx
+
+
+def get_edge_feature_idx(point_cloud, k=16):
+    """Neighbour indices of get_edge_feature (ops.py:1866-1868): knn_point_2(k+1) in feature space, self dropped."""
+    return tf_grouping.feature_knn(k + 1, point_cloud, point_cloud, skip=1, need_dist=False)[1]
+
+
+def dense_conv(feature, weights, k=16, idx=None, out=None):
+    """dense_conv (ops.py:1897-1915) fused with get_edge_feature (:1856-1877) and the max over the k neighbours.
+    feature (b,n,c) [a column slice is fine]; weights = ((w0,b0),(w1,b1),(w2,b2)) with w0 (2c,g), w1 (g+c,g),
+    w2 (2g+c,g), g = 24 -> (y (b,n,3g+c), idx (b,n,k)).  `out` may be a column slice of a wider buffer."""
+    from ._lib import lib
+    from ._t import call, ptr, rows, stream_ptr
+    (w0, b0), (w1, b1), (w2, b2) = weights
+    b, n, c = feature.shape
+    g = w0.shape[1]
+    if idx is None:
+        idx = get_edge_feature_idx(feature, k)
+    fp, _, ldf = rows(feature, "feature")
+    if out is None:
+        out = torch.empty((b, n, 3 * g + c), dtype=torch.float32, device=feature.device)
+    op, om, ldo = rows(out, "out")
+    if om != b * n or out.shape[-1] != 3 * g + c:
+        raise ValueError("dense_conv: out must be (b,n,3g+c)")
+    nbytes = int(lib().dispu_dense_conv_workspace_bytes(b, n))
+    ws = tf_grouping._workspace(nbytes, feature.device)
+    call("dispu_dense_conv", b, n, c, idx.shape[2], g, fp, ldf, ptr(idx), ptr(w0), ptr(b0), ptr(w1), ptr(b1), ptr(w2),
+         ptr(b2), op, ldo, ptr(ws), ws.numel(), stream_ptr())
+    return out, idx
+
+
+def weightnet_aggregate(xyz, idx, G, Ww, bw, bn_scale, out=None):
+    """PointShuffle2's weight net + transposed product (ops.py:1062-1067): xyz (b,m,3), idx (b,m,ns), G (b,m,ns,C),
+    Ww (3,T), bw (T) -> (b,m,C*T) = flatten(transpose(G) . relu(bn(gx.Ww+bw)))."""
+    from ._t import call, ptr, req, stream_ptr
+    xyz = req(xyz, torch.float32, 3, "xyz")
+    idx = req(idx, torch.int32, 3, "idx")
+    G = req(G, torch.float32, 4, "G")
+    b, m, ns, C = G.shape
+    T = Ww.shape[1]
+    if out is None:
+        out = torch.empty((b, m, C * T), dtype=torch.float32, device=G.device)
+    call("dispu_weightnet_aggregate", b, m, ns, C, T, ptr(xyz), ptr(idx), ptr(G), ptr(Ww), ptr(bw), float(bn_scale),
+         ptr(out), stream_ptr())
+    return out

@@ -127,14 +127,22 @@ def knn_point(k, xyz1, xyz2):
     return -dist, idx
 
 
-def group_max(points, idx):
-    """Fused group_point + reduce_max over nsample: points (b,n,c), idx (b,m,ns) -> (b,m,c).  Forward only."""
-    points = req(points, torch.float32, 3, "points")
+def group_max(points, idx, out=None):
+    """Fused group_point + reduce_max over nsample: points (b,n,c), idx (b,m,ns) -> (b,m,c).  Forward only.
+    points / out may be column slices of wider buffers."""
+    from ._t import rows
     idx = req(idx, torch.int32, 3, "idx")
+    if points.dim() != 3:
+        raise ValueError("group_max expects points (b,n,c)")
     b, n, c = points.shape
     _, m, ns = idx.shape
-    out = torch.empty((b, m, c), dtype=torch.float32, device=points.device)
-    call("dispu_group_max", b, n, c, m, ns, ptr(points), ptr(idx), ptr(out), stream_ptr())
+    pp, _, ldp = rows(points, "points")
+    if out is None:
+        out = torch.empty((b, m, c), dtype=torch.float32, device=points.device)
+    op, om, ldo = rows(out, "out")
+    if om != b * m or out.shape[-1] != c:
+        raise ValueError("group_max: out must be (b,m,c)")
+    call("dispu_group_max_ld", b, n, c, m, ns, pp, ldp, ptr(idx), op, ldo, stream_ptr())
     return out
 
 
@@ -150,3 +158,30 @@ def group_affine_relu(P, Q, idx, sign=-1.0):
     out = torch.empty((b, m, ns, c), dtype=torch.float32, device=P.device)
     call("dispu_group_affine_relu", b, n, c, m, ns, ptr(P), ptr(Q), float(sign), ptr(idx), ptr(out), stream_ptr())
     return out
+
+
+def feature_knn(k, points, queries, skip=0, need_dist=True):
+    """Feature-space kNN on the matmul-form distance matrix (knn_point_2's arithmetic, tf_grouping.py:61-66,95-114):
+    points (b,n,c), queries (b,m,c) [column slices of wider buffers are fine] -> (dist, idx) (b,m,k-skip), ascending,
+    ties to the lower index; the first `skip` neighbours are dropped (get_edge_feature drops the self match,
+    Common/ops.py:1868)."""
+    from ._t import rows
+    if points.dim() != 3 or queries.dim() != 3 or points.shape[0] != queries.shape[0] or points.shape[2] != queries.shape[2]:
+        raise ValueError("feature_knn expects points (b,n,c) and queries (b,m,c)")
+    b, n, c = points.shape
+    m = queries.shape[1]
+    if not (0 < k <= n) or not (0 <= skip < k):
+        raise ValueError("feature_knn expects 0 < k <= n and 0 <= skip < k")
+    pp, _, ldp = rows(points, "points")
+    qp, _, ldq = rows(queries, "queries")
+    idx = torch.empty((b, m, k - skip), dtype=torch.int32, device=points.device)
+    dist = torch.empty((b, m, k - skip), dtype=torch.float32, device=points.device) if need_dist else None
+    call("dispu_feature_knn", b, n, m, c, k, skip, pp, ldp, qp, ldq, ptr(dist), ptr(idx), stream_ptr())
+    return dist, idx
+
+
+def knn_point_2(k, points, queries, sort=True, unique=True):
+    """tf_grouping.py:95-114.  Returns (distances (b,m,k), indices (b,m,k)); the reference returns the indices as
+    (b,m,k,2) gather_nd pairs whose batch column is implicit here.  `unique` is a no-op in the reference too
+    (prepare_for_unique_top_k :89-91 rebinds a local)."""
+    return feature_knn(k, points, queries)

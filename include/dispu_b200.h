@@ -104,6 +104,9 @@ int dispu_group_max(int b, int n, int c, int m, int nsample, const float *points
                     dispu_stream_t stream);
 int dispu_group_affine_relu(int b, int n, int c, int m, int nsample, const float *P, const float *Q, float sign,
                             const int *idx, float *out, dispu_stream_t stream);
+/* dispu_group_max with row strides (floats) on points and out: the result lands in its column slot of a wider buffer. */
+int dispu_group_max_ld(int b, int n, int c, int m, int nsample, const float *points, int ldp, const int *idx, float *out,
+                       int ldo, dispu_stream_t stream);
 
 /* SelectionSort.  selectionSortLauncher tf_grouping.cpp:112 (kernel tf_grouping_g.cu:83). */
 int dispu_selection_sort(int b, int n, int m, int k, const float *dist, int *outi, float *out,
@@ -197,6 +200,77 @@ size_t dispu_dense_packed_bytes(int K, int N);
 int dispu_dense_pack(int K, int N, const float *W, void *packed, dispu_stream_t stream);
 int dispu_dense_tf32x3(long long M, int K, int N, const float *X, const void *packed, const float *bias, int relu,
                        float *Y, dispu_stream_t stream);
+
+/* The same kernel with everything the generator's layers need to run without concat / slice / add passes
+ * (HOST struct; zero-initialise, unset fields keep the plain behaviour):
+ *   - ldx / ldy: row strides in floats (0 = dense), so a layer reads a column slice of a wider buffer and writes
+ *     straight into its slot of the tensor the reference builds with tf.concat (Common/ops.py:1455-1486);
+ *   - gather front-end (GroupPoint + centre term + ReLU fused into the operand load, Common/ops.py:1033-1058):
+ *       A[r,:] = relu(X[cloud(r), gather_idx[r], :] + sign * Q[r / gather_ns, :]),  cloud(r) = r / gather_rows_per_cloud,
+ *     X is then (clouds, gather_n, K) with row stride ldx and Q (M / gather_ns, K) with row stride ldq (NULL: no Q);
+ *   - R1 / R2: residuals added AFTER the activation, Y = act(X.W + b) + R1 + R2 (tf.add at Common/ops.py:1074-1077);
+ *   - batched weights: rows [i*rows_per_batch, (i+1)*rows_per_batch) multiply the packed weight at
+ *     packed + i*packed_batch_stride bytes (per-cloud operands such as q.k^T and att.v of PointNonLocalCell,
+ *     Common/ops.py:326-339); rows_per_batch must be a multiple of 128. */
+typedef struct dispu_dense_args {
+    long long M;
+    int K, N;
+    const float *X;
+    long long ldx;
+    const void *packed;
+    const float *bias;
+    int relu;
+    float *Y;
+    long long ldy;
+    const int *gather_idx;
+    int gather_n, gather_ns;
+    long long gather_rows_per_cloud;
+    const float *Q;
+    long long ldq;
+    float sign;
+    const float *R1;
+    long long ldr1;
+    const float *R2;
+    long long ldr2;
+    long long rows_per_batch;
+    long long packed_batch_stride;
+} dispu_dense_args;
+int dispu_dense_tf32x3_ex(const dispu_dense_args *args, dispu_stream_t stream);
+/* Pack W[k][n] = src[k*stride_k + n*stride_n] for `batch` operands (source advances by w_batch_stride floats,
+ * destination by packed_batch_stride bytes, a multiple of 16 and >= dispu_dense_packed_bytes(K,N)). */
+int dispu_dense_pack_strided(int K, int N, const float *W, long long stride_k, long long stride_n, int batch,
+                             long long w_batch_stride, void *packed, long long packed_batch_stride,
+                             dispu_stream_t stream);
+
+/* ---- feature-space kNN + EdgeConv dense block --------------------------------------------- */
+
+/* knn_point_2 (tf_ops/grouping/tf_grouping.py:95-114) as get_edge_feature calls it (Common/ops.py:1866-1868):
+ * k nearest neighbours in a c-dimensional feature space on D = (r_q - 2 q.p) + r_p (batch_distance_matrix_general,
+ * tf_grouping.py:61-66), ascending, ties to the lower index (tf.nn.top_k); the first `skip` neighbours are dropped
+ * (the reference drops the self match with idx[:, :, 1:]).  points (b,n,c) row stride ldp, queries (b,m,c) row
+ * stride ldq -> dist / idx (b,m,k-skip); dist may be NULL.  Accumulation order is pinned (sequential fmaf over the
+ * channels) and bit-identical to oracle/dispu_oracle.c:orc_feature_knn.  k <= 32, c <= 128. */
+int dispu_feature_knn(int b, int n, int m, int c, int k, int skip, const float *points, int ldp, const float *queries,
+                      int ldq, float *dist, int *idx, dispu_stream_t stream);
+
+/* dense_conv (Common/ops.py:1897-1915) on the edge feature of get_edge_feature (:1856-1877), 3 layers of `growth`
+ * channels, fused with the max over the k neighbours; no (b,n,k,*) tensor is built.
+ *   feat (b,n,c) row stride ldf; idx (b,n,k) neighbour indices inside the cloud;
+ *   w0 (2c,g) b0 (g) | w1 (g+c,g) b1 | w2 (2g+c,g) b2  row-major 1x1-conv kernels, biases may be NULL;
+ *   out (b,n,3g+c) row stride ldo = [max y2 | max y1 | max y0 | feat]  (the concat order of :1901-1913).
+ * workspace: dispu_dense_conv_workspace_bytes(b,n) bytes.  growth == 24, c % 4 == 0, c <= 128, ldf/ldo % 4 == 0. */
+size_t dispu_dense_conv_workspace_bytes(int b, int n);
+int dispu_dense_conv(int b, int n, int c, int k, int growth, const float *feat, int ldf, const int *idx, const float *w0,
+                     const float *b0, const float *w1, const float *b1, const float *w2, const float *b2, float *out,
+                     int ldo, void *workspace, size_t workspace_bytes, dispu_stream_t stream);
+
+/* Weight net + transposed product of PointShuffle2 (Common/ops.py:1062-1067, weight_net_hidden :181-191):
+ *   wn[s][t]   = relu(((xyz[idx[i][s]] - xyz[i]) . Ww[:,t] + bw[t]) * bn_scale)
+ *   out[i][ch*T + t] = sum_s G[i][s][ch] * wn[s][t]
+ * xyz (b,m,3), idx (b,m,nsample), G (b,m,nsample,C), Ww (3,T), bw (T) or NULL -> out (b,m,C*T), the operand of the
+ * [1,C] after_conv (:1068).  Instantiated for nsample = 16, C = 128, T = 16 (the live generator). */
+int dispu_weightnet_aggregate(int b, int m, int nsample, int C, int T, const float *xyz, const int *idx, const float *G,
+                              const float *Ww, const float *bw, float bn_scale, float *out, dispu_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -499,3 +499,158 @@ int orc_selection_sort(int b, int n, int m, int k, const float *dist, int *outi,
     }
     return 0;
 }
+
+/* ---------------------------------------------------------------------------------------
+ * Feature-space kNN — knn_point_2 (tf_ops/grouping/tf_grouping.py:95-114) on the matmul-form
+ * distance matrix batch_distance_matrix_general (:61-66):
+ *     D[q][p] = (r_q - 2*dot(q,p)) + r_p,   r_x = sum_c x_c^2
+ * then tf.nn.top_k(-D, k): ascending D, ties to the lower index.  The `unique` flag is a no-op
+ * (prepare_for_unique_top_k :89-91 rebinds a local).  Call site: get_edge_feature
+ * (Common/ops.py:1866-1868: k+1 neighbours of the cloud in itself, column 0 dropped).
+ * TensorFlow leaves the accumulation order of reduce_sum / matmul unspecified; this restatement
+ * (and the CUDA kernel, bit for bit) uses sequential fmaf over the channels for both.
+ * ld* = row strides in floats.  dist may be NULL.
+ * ------------------------------------------------------------------------------------- */
+int orc_feature_knn(int b, int n, int m, int c, int k, const float *points, int ldp, const float *queries,
+                    int ldq, float *dist, int *idx) {
+    if (k <= 0 || k > n || c <= 0) return -1;
+    float *bd = (float *)malloc(sizeof(float) * (size_t)k);
+    int *bi = (int *)malloc(sizeof(int) * (size_t)k);
+    float *rp = (float *)malloc(sizeof(float) * (size_t)n);
+    if (!bd || !bi || !rp) return -2;
+    for (int i = 0; i < b; ++i) {
+        for (int p = 0; p < n; ++p) {
+            const float *x = points + ((size_t)i * n + p) * ldp;
+            float r = 0.0f;
+            for (int l = 0; l < c; ++l) r = fmaf(x[l], x[l], r);
+            rp[p] = r;
+        }
+        for (int j = 0; j < m; ++j) {
+            const float *q = queries + ((size_t)i * m + j) * ldq;
+            float rq = 0.0f;
+            for (int l = 0; l < c; ++l) rq = fmaf(q[l], q[l], rq);
+            int cnt = 0;
+            for (int p = 0; p < n; ++p) {
+                const float *x = points + ((size_t)i * n + p) * ldp;
+                float dot = 0.0f;
+                for (int l = 0; l < c; ++l) dot = fmaf(q[l], x[l], dot);
+                float d = fmaf(-2.0f, dot, rq) + rp[p];
+                if (cnt < k || d < bd[cnt - 1]) {
+                    int pos = cnt < k ? cnt : k - 1;
+                    while (pos > 0 && bd[pos - 1] > d) {
+                        bd[pos] = bd[pos - 1];
+                        bi[pos] = bi[pos - 1];
+                        --pos;
+                    }
+                    bd[pos] = d;
+                    bi[pos] = p;
+                    if (cnt < k) ++cnt;
+                }
+            }
+            for (int s = 0; s < k; ++s) {
+                if (dist) dist[((size_t)i * m + j) * k + s] = bd[s];
+                idx[((size_t)i * m + j) * k + s] = bi[s];
+            }
+        }
+    }
+    free(bd); free(bi); free(rp);
+    return 0;
+}
+
+/* ---------------------------------------------------------------------------------------
+ * EdgeConv dense block — dense_conv (Common/ops.py:1897-1915) on the edge feature of
+ * get_edge_feature (:1856-1877), n=3 layers, growth g, conv2d = 1x1 conv + bias (+ReLU)
+ * (Common/tf_util.py:120-185), literal op order (nothing hoisted):
+ *     e   = [f_i, f_j - f_i]                       (2c)     j = idx[i][s]
+ *     y0  = relu(e.W0 + b0)          z1 = [y0, f_i]         (g + c)
+ *     y1  = relu(z1.W1 + b1)         z2 = [y1, y0, f_i]     (2g + c)
+ *     y2  =      z2.W2 + b2          z3 = [y2, y1, y0, f_i] (3g + c)
+ *     out[i] = max_s z3
+ * Accumulation in double, rounded to float per activation: the comparator for a 1e-5 bound, not a
+ * bit-exact twin (the CUDA kernel hoists the f_i terms to per-point products).
+ * feat (b,n,ldf) ; idx (b,n,k) ; out (b,n,ldo) receives 3g+c columns.
+ * ------------------------------------------------------------------------------------- */
+int orc_dense_conv(int b, int n, int c, int k, int g, const float *feat, int ldf, const int *idx,
+                   const float *w0, const float *b0, const float *w1, const float *b1, const float *w2,
+                   const float *b2, float *out, int ldo) {
+    if (c <= 0 || g <= 0 || k <= 0) return -1;
+    const int wz = 3 * g + c;
+    float *z = (float *)malloc(sizeof(float) * (size_t)wz);
+    float *e = (float *)malloc(sizeof(float) * (size_t)(2 * c));
+    if (!z || !e) return -2;
+    for (int i = 0; i < b; ++i)
+        for (int p = 0; p < n; ++p) {
+            const float *fi = feat + ((size_t)i * n + p) * ldf;
+            float *o = out + ((size_t)i * n + p) * ldo;
+            for (int s = 0; s < k; ++s) {
+                const int j = idx[((size_t)i * n + p) * k + s];
+                const float *fj = feat + ((size_t)i * n + j) * ldf;
+                for (int l = 0; l < c; ++l) { e[l] = fi[l]; e[c + l] = fj[l] - fi[l]; }
+                float *y2 = z, *y1 = z + g, *y0 = z + 2 * g, *zf = z + 3 * g;
+                for (int l = 0; l < c; ++l) zf[l] = fi[l];
+                for (int oc = 0; oc < g; ++oc) {
+                    double acc = 0.0;
+                    for (int ic = 0; ic < 2 * c; ++ic) acc += (double)e[ic] * w0[(size_t)ic * g + oc];
+                    acc += b0 ? b0[oc] : 0.0;
+                    y0[oc] = acc > 0.0 ? (float)acc : 0.0f;
+                }
+                for (int oc = 0; oc < g; ++oc) { /* z1 = [y0, f_i] */
+                    double acc = 0.0;
+                    for (int ic = 0; ic < g; ++ic) acc += (double)y0[ic] * w1[(size_t)ic * g + oc];
+                    for (int ic = 0; ic < c; ++ic) acc += (double)fi[ic] * w1[(size_t)(g + ic) * g + oc];
+                    acc += b1 ? b1[oc] : 0.0;
+                    y1[oc] = acc > 0.0 ? (float)acc : 0.0f;
+                }
+                for (int oc = 0; oc < g; ++oc) { /* z2 = [y1, y0, f_i], no activation */
+                    double acc = 0.0;
+                    for (int ic = 0; ic < g; ++ic) acc += (double)y1[ic] * w2[(size_t)ic * g + oc];
+                    for (int ic = 0; ic < g; ++ic) acc += (double)y0[ic] * w2[(size_t)(g + ic) * g + oc];
+                    for (int ic = 0; ic < c; ++ic) acc += (double)fi[ic] * w2[(size_t)(2 * g + ic) * g + oc];
+                    acc += b2 ? b2[oc] : 0.0;
+                    y2[oc] = (float)acc;
+                }
+                for (int l = 0; l < wz; ++l) o[l] = (s == 0 || z[l] > o[l]) ? z[l] : o[l];
+            }
+        }
+    free(z); free(e);
+    return 0;
+}
+
+/* ---------------------------------------------------------------------------------------
+ * Weighted local aggregation of PointShuffle2 (Common/ops.py:1062-1068) with weight_net_hidden
+ * (:181-191, one hidden layer of 16 units, bn=True evaluated with its initial moving statistics:
+ * mean 0, variance 1, eps 1e-3 => a scale of 1/sqrt(1+eps)):
+ *     gx[s]   = xyz[idx[i][s]] - xyz[i]
+ *     wn[s][t] = relu((gx[s].Ww[:,t] + bw[t]) * bn_scale)
+ *     H[i][ch][t] = sum_s G[i][s][ch] * wn[s][t]           (= transpose(G) . wn, :1066-1067)
+ * out (b,m,C*T) row = (ch, t) flattened, the operand of the [1,C] "after_conv" (:1068-1072).
+ * ------------------------------------------------------------------------------------- */
+int orc_weightnet_aggregate(int b, int m, int ns, int C, int T, const float *xyz, const int *idx, const float *G,
+                            const float *Ww, const float *bw, float bn_scale, float *out) {
+    float *wn = (float *)malloc(sizeof(float) * (size_t)ns * T);
+    if (!wn) return -2;
+    for (int i = 0; i < b; ++i)
+        for (int p = 0; p < m; ++p) {
+            const float *ctr = xyz + ((size_t)i * m + p) * 3;
+            const int *row = idx + ((size_t)i * m + p) * ns;
+            for (int s = 0; s < ns; ++s) {
+                const float *q = xyz + ((size_t)i * m + row[s]) * 3;
+                float gx[3] = {q[0] - ctr[0], q[1] - ctr[1], q[2] - ctr[2]};
+                for (int t = 0; t < T; ++t) {
+                    double a = (double)gx[0] * Ww[t] + (double)gx[1] * Ww[T + t] + (double)gx[2] * Ww[2 * T + t];
+                    a = (a + (bw ? bw[t] : 0.0)) * bn_scale;
+                    wn[s * T + t] = a > 0.0 ? (float)a : 0.0f;
+                }
+            }
+            const float *g = G + ((size_t)i * m + p) * ns * C;
+            float *o = out + ((size_t)i * m + p) * C * T;
+            for (int ch = 0; ch < C; ++ch)
+                for (int t = 0; t < T; ++t) {
+                    double a = 0.0;
+                    for (int s = 0; s < ns; ++s) a += (double)g[(size_t)s * C + ch] * wn[s * T + t];
+                    o[ch * T + t] = (float)a;
+                }
+        }
+    free(wn);
+    return 0;
+}

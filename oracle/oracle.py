@@ -266,3 +266,45 @@ def three_nn_weights(dist):
     inv = (np.float32(1.0) / d).astype(np.float32)
     norm = inv.sum(axis=2, keepdims=True, dtype=np.float32)
     return (inv / norm).astype(np.float32)
+
+
+# ---- feature-space kNN / EdgeConv dense block / weight-net aggregation ------------
+
+def feature_knn(k, points, queries, skip=0):
+    """knn_point_2 (tf_grouping.py:95-114): (k, points (b,n,c), queries (b,m,c)) -> (dist, idx) (b,m,k-skip)."""
+    points, queries = _f(points), _f(queries)
+    b, n, c = points.shape
+    m = queries.shape[1]
+    dist = np.empty((b, m, k), np.float32)
+    idx = np.empty((b, m, k), np.int32)
+    rc = lib().orc_feature_knn(b, n, m, c, k, _p(points), c, _p(queries), c, _p(dist), _p(idx))
+    assert rc == 0, rc
+    return np.ascontiguousarray(dist[:, :, skip:]), np.ascontiguousarray(idx[:, :, skip:])
+
+
+def dense_conv(feat, idx, w0, b0, w1, b1, w2, b2):
+    """dense_conv (Common/ops.py:1897-1915), literal op order -> (b,n,3g+c)."""
+    feat, idx = _f(feat), _i(idx)
+    b, n, c = feat.shape
+    k = idx.shape[2]
+    g = w0.shape[1]
+    ws = [_f(w0), _f(w1), _f(w2)]
+    bs = [None if x is None else _f(x) for x in (b0, b1, b2)]
+    out = np.empty((b, n, 3 * g + c), np.float32)
+    rc = lib().orc_dense_conv(b, n, c, k, g, _p(feat), c, _p(idx), _p(ws[0]), _p(bs[0]), _p(ws[1]), _p(bs[1]),
+                              _p(ws[2]), _p(bs[2]), _p(out), 3 * g + c)
+    assert rc == 0, rc
+    return out
+
+
+def weightnet_aggregate(xyz, idx, G, Ww, bw, bn_scale):
+    """Common/ops.py:1062-1067 -> (b,m,C*T)."""
+    xyz, idx, G, Ww = _f(xyz), _i(idx), _f(G), _f(Ww)
+    bw = None if bw is None else _f(bw)
+    b, m, ns, Cc = G.shape
+    T = Ww.shape[1]
+    out = np.empty((b, m, Cc * T), np.float32)
+    lib().orc_weightnet_aggregate.argtypes = [C.c_int] * 5 + [C.c_void_p] * 5 + [C.c_float, C.c_void_p]
+    rc = lib().orc_weightnet_aggregate(b, m, ns, Cc, T, _p(xyz), _p(idx), _p(G), _p(Ww), _p(bw), float(bn_scale), _p(out))
+    assert rc == 0, rc
+    return out

@@ -194,3 +194,54 @@ def test_repulsion_loss_against_numpy(rng):
     d = np.sort((g.astype(np.float64) ** 2).sum(-1), axis=-1)[:, :, 1:5]
     want = np.maximum(0.0, 0.001 - d).mean()
     np.testing.assert_allclose(O.repulsion_loss(pred, idx, 0.001), want, rtol=1e-5)
+
+
+# ---- feature-space kNN / EdgeConv dense block / weight net: oracle vs independent numpy restatements
+def test_feature_knn_oracle_vs_numpy():
+    """orc_feature_knn vs tf_grouping.py:61-66 + top_k restated in float64 (indices where the gaps are clear)."""
+    rng = np.random.default_rng(5)
+    f = rng.standard_normal((2, 96, 24)).astype(np.float32)
+    q = rng.standard_normal((2, 40, 24)).astype(np.float32)
+    d, i = O.feature_knn(9, f, q)
+    r_q = (q.astype(np.float64) ** 2).sum(-1)
+    r_p = (f.astype(np.float64) ** 2).sum(-1)
+    D = r_q[:, :, None] - 2 * np.einsum("bic,bjc->bij", q.astype(np.float64), f.astype(np.float64)) + r_p[:, None, :]
+    assert np.array_equal(i, np.argsort(D, axis=-1, kind="stable")[:, :, :9])
+    np.testing.assert_allclose(d, np.sort(D, axis=-1)[:, :, :9], atol=2e-5)
+    # exact ties go to the lower index; skip drops the leading neighbours (get_edge_feature, ops.py:1868)
+    t = np.zeros((1, 8, 4), np.float32)
+    assert np.array_equal(O.feature_knn(4, t, t)[1][0, 3], [0, 1, 2, 3])
+    assert np.array_equal(O.feature_knn(4, t, t, skip=1)[1][0, 3], [1, 2, 3])
+
+
+def test_dense_conv_oracle_vs_numpy():
+    """orc_dense_conv vs the literal concat/conv2d sequence of Common/ops.py:1897-1915 in numpy float64."""
+    rng = np.random.default_rng(6)
+    b, n, c, k, g = 2, 50, 12, 7, 24
+    f = rng.standard_normal((b, n, c)).astype(np.float32)
+    _, idx = O.feature_knn(k + 1, f, f, skip=1)
+    ws = [(rng.standard_normal((ci, g)) / 4).astype(np.float32) for ci in (2 * c, g + c, 2 * g + c)]
+    bs = [(rng.standard_normal(g) / 4).astype(np.float32) for _ in range(3)]
+    got = O.dense_conv(f, idx, ws[0], bs[0], ws[1], bs[1], ws[2], bs[2])
+    fi = np.broadcast_to(f[:, :, None, :], (b, n, k, c)).astype(np.float64)
+    fj = f[np.arange(b)[:, None, None], idx].astype(np.float64)
+    y = np.concatenate([fi, fj - fi], -1)
+    y = np.concatenate([np.maximum(y @ ws[0] + bs[0], 0), fi], -1)
+    y = np.concatenate([np.maximum(y @ ws[1] + bs[1], 0), y], -1)
+    y = np.concatenate([y @ ws[2] + bs[2], y], -1)
+    np.testing.assert_allclose(got, y.max(2), rtol=1e-5, atol=1e-5)
+
+
+def test_weightnet_aggregate_oracle_vs_numpy():
+    rng = np.random.default_rng(7)
+    b, m, ns, C, T = 2, 30, 16, 128, 16
+    xyz = rng.uniform(-1, 1, (b, m, 3)).astype(np.float32)
+    idx = rng.integers(0, m, (b, m, ns)).astype(np.int32)
+    G = rng.standard_normal((b, m, ns, C)).astype(np.float32)
+    Ww = rng.standard_normal((3, T)).astype(np.float32)
+    bw = rng.standard_normal(T).astype(np.float32)
+    H = O.weightnet_aggregate(xyz, idx, G, Ww, bw, 0.9995)
+    gx = xyz[np.arange(b)[:, None, None], idx] - xyz[:, :, None, :]
+    wn = np.maximum((gx.astype(np.float64) @ Ww + bw) * 0.9995, 0)
+    want = np.einsum("bmsc,bmst->bmct", G.astype(np.float64), wn).reshape(b, m, -1)
+    np.testing.assert_allclose(H, want, rtol=1e-5, atol=1e-5)
