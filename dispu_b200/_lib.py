@@ -21,7 +21,8 @@ class DenseArgs(C.Structure):
         ("M", _ll), ("K", _i), ("N", _i), ("X", _p), ("ldx", _ll), ("packed", _p), ("bias", _p), ("relu", _i),
         ("Y", _p), ("ldy", _ll), ("gather_idx", _p), ("gather_n", _i), ("gather_ns", _i), ("gather_rows_per_cloud", _ll),
         ("Q", _p), ("ldq", _ll), ("sign", C.c_float), ("R1", _p), ("ldr1", _ll), ("R2", _p), ("ldr2", _ll),
-        ("rows_per_batch", _ll), ("packed_batch_stride", _ll),
+        ("rows_per_batch", _ll), ("packed_batch_stride", _ll), ("n_blocks", _i), ("packed_block_stride", _ll),
+        ("wn_xyz", _p), ("wn_w", _p), ("wn_b", _p), ("wn_scale", C.c_float),
     ]
 
 

@@ -36,7 +36,8 @@ _profile = None
 def _profile_key(name, args):
     if name == "dispu_dense_tf32x3_ex":
         a = args[0]._obj
-        tag = (" gather" if a.gather_idx else "") + (" batched" if a.rows_per_batch else "") + (" +res" if a.R1 else "")
+        tag = ((" gather" if a.gather_idx else "") + (" batched" if a.rows_per_batch else "") + (" +res" if a.R1 else "") +
+               (f" x{a.n_blocks}blocks" if a.n_blocks > 1 else "") + (" +weightnet" if a.wn_xyz else ""))
         return f"{name} M{a.M} K{a.K} N{a.N}{tag}"
     ints = [str(x) for x in args if isinstance(x, int) and not isinstance(x, bool) and 0 <= x < (1 << 24)]
     return name + (" " + ",".join(ints[:6]) if ints else "")

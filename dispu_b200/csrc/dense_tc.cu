@@ -16,6 +16,8 @@
 //               N=N_pad) and releases the stage with tcgen05.commit.
 // Up to four smem stages (full/empty mbarriers) and two TMEM accumulators (full/empty mbarriers) keep loads,
 // MMAs and the epilogue of consecutive tiles overlapped.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -26,8 +28,9 @@ using namespace tc;
 constexpr int kDnKC = 32;        // K columns per pipeline chunk
 constexpr int kDnMaxStages = 4;
 constexpr int kDnProducerWarps = 8;
-constexpr int kDnThreads = (kDnProducerWarps + 4 + 1) * 32;  // producers | epilogue | MMA issuer
-constexpr int kDnSmemBudget = 216 * 1024;
+constexpr int kDnEpiWarps = 8;      // two per TMEM lane quarter, alternating 16-column blocks
+constexpr int kDnThreads = (kDnProducerWarps + kDnEpiWarps + 1) * 32;  // producers | epilogue | MMA issuer
+constexpr int kDnSmemBudget = 196 * 1024;  // + <= 29 KB static (epilogue staging, weight-net rows, bias, barriers) <= 227 KB
 
 __host__ __device__ __forceinline__ int dn_npad(int N) { return (N + 15) & ~15; }
 __host__ __device__ __forceinline__ int dn_chunks(int K) { return (K + kDnKC - 1) / kDnKC; }
@@ -87,7 +90,17 @@ struct DenseParams {
     long long ldr2;
     // batched weights: rows [i*rows_per_batch, (i+1)*rows_per_batch) use packed + i*packed_batch_stride
     long long rows_per_batch, packed_batch_stride;
+    // column blocks: tile t -> row tile t / n_blocks, block j = t % n_blocks; block j multiplies the operand at
+    // (+ j*packed_block_stride bytes) and writes its N columns at column offset j*N of Y
+    int n_blocks;
+    long long packed_block_stride;
+    // weight-net epilogue (kEpi == 1): Y[row/16][ch*16 + t] = sum_s act(acc)[16*(row/16)+s][ch] * wn[s][t],
+    // wn[s][t] = relu(((xyz[cloud, gidx[row]] - xyz[row/16]) . wn_w[:,t] + wn_b[t]) * wn_scale)
+    const float *wn_xyz, *wn_w, *wn_b;
+    float wn_scale;
     int n_tiles, n_stages;
+    long long *dbg_buf;  // development only: clock64 samples of CTA 0 (3 roles x 64 iterations x 8 slots)
+    int dbg;  // development only (DISPU_DENSE_DBG): 1 = no A loads, 2 = no weight TMA, 4 = no MMA issue; results are garbage
 };
 
 // four consecutive floats k..k+3 of a row (zero beyond K)
@@ -104,9 +117,23 @@ __device__ __forceinline__ float4 dn_load4(const float *__restrict__ row, int k,
     return v;
 }
 
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA bulk copy global -> shared (UBLKCP), completion reported to an mbarrier as transaction bytes
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+constexpr int kDnEpiStride = 20;  // floats per staged epilogue row (16 + 4: 16-byte aligned, conflict-free stores)
+
 // kResident: the whole packed weight stays in shared memory for the CTA's lifetime (small K*N) and the pipeline
-// stages hold only X chunks; otherwise every stage carries its X chunk and the matching weight chunk.
-template <bool kResident>
+// stages hold only X chunks; otherwise every stage carries its X chunk and the matching weight chunk.  Weights
+// always arrive by TMA bulk copies (one elected thread, mbarrier transaction bytes): the pre-packed planes are
+// contiguous, so a chunk is ONE copy and no thread touches the bytes.
+template <bool kResident, bool kGather, int kEpi>
 __global__ void __launch_bounds__(kDnThreads, 1)
 dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
     const long long M = prm.M;
@@ -115,12 +142,14 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
     const uint8_t *__restrict__ packed = prm.packed;
     const float *__restrict__ bias = prm.bias;
     const int relu = prm.relu;
-    float *__restrict__ Y = prm.Y;
     const int n_tiles = prm.n_tiles, n_stages = prm.n_stages;
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t s_full[kDnMaxStages], s_empty[kDnMaxStages], s_tfull[2], s_tempty[2];
+    __shared__ __align__(8) uint64_t s_full[kDnMaxStages], s_empty[kDnMaxStages], s_tfull[2], s_tempty[2], s_wfull;
     __shared__ uint32_t s_tmem;
-    __shared__ float s_bias[256];
+    __shared__ __align__(16) float s_bias[256];
+    __shared__ __align__(16) float s_epi[kDnEpiWarps][32 * kDnEpiStride];
+    __shared__ __align__(16) float s_wn[kEpi == 1 ? 4 : 1][kEpi == 1 ? 32 * 16 : 4];  // weight-net rows of each epilogue warp
+    __shared__ float s_wnw[64];                                                          // wn_w (3x16) | wn_b (16)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int npad = dn_npad(N);
@@ -130,105 +159,156 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
     const uint32_t stage_bytes = kResident ? 2 * a_plane : 2 * a_plane + 2 * b_plane;  // A_hi | A_lo [| B_hi | B_lo]
     const uint32_t w_base = (uint32_t)n_stages * stage_bytes;                           // resident weights live here
     const uint32_t smem_base = smem_u32(smem);
-    constexpr int kMmaWarp = kDnProducerWarps + 4;
+    constexpr int kMmaWarp = kDnProducerWarps + kDnEpiWarps;
 
     if (tid == 0) {
         for (int s = 0; s < kDnMaxStages; ++s) {
-            mbar_init(&s_full[s], kDnProducerWarps);  // one arrival per producer warp
-            mbar_init(&s_empty[s], 1);                // tcgen05.commit
+            mbar_init(&s_full[s], kDnProducerWarps + (kResident ? 0 : 1));  // producer warps (+ the TMA issuer's expect_tx)
+            mbar_init(&s_empty[s], 1);                                      // tcgen05.commit
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&s_tfull[a], 1);   // tcgen05.commit
-            mbar_init(&s_tempty[a], 4);  // one arrival per epilogue warp
+            mbar_init(&s_tempty[a], kDnEpiWarps);  // one arrival per epilogue warp
         }
+        mbar_init(&s_wfull, 1);
         fence_mbar_init();
+        if (kResident) {  // whole weight, one bulk copy per K-chunk, all on one barrier
+            mbar_arrive_expect_tx(&s_wfull, (uint32_t)nchunks * 2u * b_plane);
+            for (int c = 0; c < nchunks; ++c)
+                bulk_g2s(smem_base + w_base + (uint32_t)c * 2u * b_plane, packed + (size_t)c * 2u * b_plane, 2u * b_plane, &s_wfull);
+        }
     }
     if (warp == kMmaWarp) tmem_alloc(&s_tmem, 512);
     for (int e = tid; e < 256; e += kDnThreads) s_bias[e] = (bias && e < N) ? __ldg(bias + e) : 0.f;
-    if (kResident) {
-        const float4 *src = reinterpret_cast<const float4 *>(packed);
-        float4 *dst = reinterpret_cast<float4 *>(smem + w_base);
-        const int n16 = (int)((size_t)nchunks * 2 * b_plane / 16);
-        for (int e = tid; e < n16; e += kDnThreads) dst[e] = __ldg(src + e);
-        fence_proxy_async_smem();
-    }
+    if (kEpi == 1 && tid < 64) s_wnw[tid] = tid < 48 ? __ldg(prm.wn_w + tid) : (prm.wn_b ? __ldg(prm.wn_b + tid - 48) : 0.f);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = s_tmem;
 
     if (warp < kDnProducerWarps) {
-        // ================= producers: thread (r, h) owns float4 columns h*4..h*4+3 of row r's chunk =================
-        const int r = tid & 127, h = tid >> 7;
-        uint32_t it = 0;  // global chunk counter -> stage / phase
-        const uint32_t row_off = (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
+        // ================= producers =================
+        // Mapping: warp w owns rows 16w..16w+15 of the tile; lane l covers row 16w + (l&7) [+8] and the 16-byte K-groups
+        // (l>>3) [+4] of the chunk, i.e. one load instruction reads 8 rows x 64 contiguous bytes (8 L1 lines instead of
+        // the 32 a row-per-lane mapping touches) and the matching operand-layout stores are bank-conflict free (the 8
+        // lanes of a 128-bit phase hit 8 different rows of one core matrix).
+        // Flat (tile, chunk) iteration over a register ring of kDepth chunks: the raw global loads of chunk i+kDepth
+        // are issued as soon as slot i has been consumed, so kDepth chunks per thread are always in flight; the gather
+        // front-end's transform runs at CONSUME time so it never waits on a load it has just issued, and the gather
+        // index of the next tile is fetched a whole tile ahead of the row pointer that depends on it.
+        constexpr int kDepth = 2;  // 17 warps x 120 registers: two chunks per thread in flight
+        const int r0 = warp * 16 + (lane & 7);  // my two rows: r0, r0 + 8
+        const int kg = lane >> 3;               // my two K-groups: kg, kg + 4
+        const uint32_t st_off = (uint32_t)kg * 2048u + (uint32_t)(2 * warp) * 128u + (uint32_t)(lane & 7) * 16u;
         const bool vec = ((reinterpret_cast<uintptr_t>(X) & 15u) == 0) && (prm.ldx % 4 == 0);
         const bool qvec = ((reinterpret_cast<uintptr_t>(prm.Q) & 15u) == 0) && (prm.ldq % 4 == 0);
         const int *__restrict__ gidx = prm.gidx;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const long long row = (long long)tile * 128 + r;
-            const bool rvalid = row < M;
-            const long long rowc = rvalid ? row : 0;
-            const float *xr;
-            const float *qr = nullptr;
-            if (gidx) {
-                const long long cloud = rowc / prm.g_rows_per_cloud;
-                xr = X + (cloud * prm.g_n + __ldg(gidx + rowc)) * prm.ldx;
-                if (prm.Q) qr = prm.Q + (rowc / prm.g_ns) * prm.ldq;
-            } else {
-                xr = X + rowc * prm.ldx;
+        const int nb = prm.n_blocks;
+        const int my_tiles = blockIdx.x < n_tiles ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+        const int total = my_tiles * nchunks;
+        int ld_tile = blockIdx.x, ld_c = 0;
+        const float *xr[2] = {X, X}, *qr[2] = {nullptr, nullptr};
+        bool rvalid[2] = {false, false};
+        int idx_next[2] = {0, 0};
+        auto fetch_idx = [&](int tile, int g) -> int {  // gather index of my row g in `tile` (0 when out of range)
+            const long long row = (long long)(tile / nb) * 128 + r0 + 8 * g;
+            return (kGather && tile < n_tiles && row < M) ? __ldg(gidx + row) : 0;
+        };
+        auto enter_tile = [&](int i0, int i1) {  // row pointers of ld_tile; prefetches the indices of the tile after it
+            const int idx_cur[2] = {i0, i1};
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                const long long row = (long long)(ld_tile / nb) * 128 + r0 + 8 * g;
+                rvalid[g] = ld_tile < n_tiles && row < M;
+                const long long rowc = rvalid[g] ? row : 0;
+                if (kGather) {
+                    const long long cloud = rowc / prm.g_rows_per_cloud;
+                    xr[g] = X + (cloud * prm.g_n + idx_cur[g]) * prm.ldx;
+                    qr[g] = prm.Q ? prm.Q + (rowc / prm.g_ns) * prm.ldq : nullptr;
+                    idx_next[g] = fetch_idx(ld_tile + gridDim.x, g);
+                } else {
+                    xr[g] = X + rowc * prm.ldx;
+                }
             }
-            const uint8_t *packed_t = packed;
-            if (!kResident && prm.rows_per_batch > 0)
-                packed_t = packed + ((long long)tile * 128 / prm.rows_per_batch) * prm.packed_batch_stride;
-            for (int c = 0; c < nchunks; ++c, ++it) {
-                const int s = it % n_stages;
-                const uint32_t ph = (it / n_stages) & 1;
-                // issue my loads before waiting for the stage: they only need registers
-                const int k0 = c * kDnKC + h * 16;
-                float4 v[4];
+        };
+        float4 xb[kDepth][4];
+        float4 qb[kGather ? kDepth : 1][4];
+        auto load_chunk = [&](float4 (&xv)[4], float4 (&qv)[4]) {  // raw loads of chunk (ld_tile, ld_c); advances the cursor
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int k = k0 + j * 4;
-                    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (rvalid) {
-                        v[j] = dn_load4(xr, k, K, vec);
-                        if (gidx) {
-                            if (qr) {
-                                const float4 q = dn_load4(qr, k, K, qvec);
-                                v[j].x = __fmaf_rn(prm.sign, q.x, v[j].x);
-                                v[j].y = __fmaf_rn(prm.sign, q.y, v[j].y);
-                                v[j].z = __fmaf_rn(prm.sign, q.z, v[j].z);
-                                v[j].w = __fmaf_rn(prm.sign, q.w, v[j].w);
-                            }
-                            v[j].x = fmaxf(v[j].x, 0.f);
-                            v[j].y = fmaxf(v[j].y, 0.f);
-                            v[j].z = fmaxf(v[j].z, 0.f);
-                            v[j].w = fmaxf(v[j].w, 0.f);
-                        }
+            for (int j = 0; j < 4; ++j) {  // j = 2*g + kh: row r0 + 8g, K-group kg + 4kh
+                const int g = j >> 1;
+                const int k = ld_c * kDnKC + (kg + 4 * (j & 1)) * 4;
+                xv[j] = (rvalid[g] && !(prm.dbg & 1)) ? dn_load4(xr[g], k, K, vec) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (kGather) qv[j] = (rvalid[g] && qr[g]) ? dn_load4(qr[g], k, K, qvec) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (++ld_c == nchunks) {
+                ld_c = 0;
+                ld_tile += gridDim.x;
+                enter_tile(idx_next[0], idx_next[1]);
+            }
+        };
+        enter_tile(fetch_idx(ld_tile, 0), fetch_idx(ld_tile, 1));
+#pragma unroll
+        for (int d = 0; d < kDepth; ++d)
+            if (d < total) load_chunk(xb[d], qb[kGather ? d : 0]);
+        uint32_t it = 0;  // global chunk counter -> stage / phase
+        int tile = blockIdx.x, c = 0;
+        const uint8_t *packed_t = packed;
+        for (int base = 0; base < total; base += kDepth) {
+#pragma unroll
+            for (int d = 0; d < kDepth; ++d) {
+                if (base + d < total) {
+                    const int s = it % n_stages;
+                    const uint32_t ph = (it / n_stages) & 1;
+                    if (!kResident && c == 0) {
+                        const int mt = tile / nb;
+                        packed_t = packed + (long long)(tile - mt * nb) * prm.packed_block_stride;
+                        if (prm.rows_per_batch > 0) packed_t += ((long long)mt * 128 / prm.rows_per_batch) * prm.packed_batch_stride;
                     }
-                }
-                mbar_wait(&s_empty[s], ph ^ 1);  // stage free (first pass: passes immediately)
-                uint8_t *st = smem + (size_t)s * stage_bytes;
+                    const bool trace = prm.dbg_buf && blockIdx.x == 0 && tid == 0 && it < 64;
+                    long long tq0 = 0, tq1 = 0, tq2 = 0, tq3 = 0;
+                    if (trace) tq0 = clock64();
+                    mbar_wait(&s_empty[s], ph ^ 1);  // stage free (first pass: passes immediately)
+                    if (trace) tq1 = clock64();
+                    uint8_t *st = smem + (size_t)s * stage_bytes;
+                    if (!kResident && tid == 0 && (prm.dbg & 2)) mbar_arrive(&s_full[s]);
+                    if (!kResident && tid == 0 && !(prm.dbg & 2)) {  // weight chunk: one TMA bulk copy of the pre-packed [hi | lo] planes
+                        mbar_arrive_expect_tx(&s_full[s], 2u * b_plane);
+                        bulk_g2s(smem_base + (uint32_t)s * stage_bytes + 2u * a_plane, packed_t + (size_t)c * 2u * b_plane,
+                                 2u * b_plane, &s_full[s]);
+                    }
+                    if (!(prm.dbg & 8))
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float4 hi = make_float4(tf32_round(v[j].x), tf32_round(v[j].y), tf32_round(v[j].z), tf32_round(v[j].w));
-                    const uint32_t o = (uint32_t)(h * 4 + j) * 2048u + row_off;
-                    *reinterpret_cast<float4 *>(st + o) = hi;
-                    // lo is rounded (not left to the tensor core's truncation): halves the error of the lo*w_hi term
-                    *reinterpret_cast<float4 *>(st + a_plane + o) =
-                        make_float4(tf32_round(__fsub_rn(v[j].x, hi.x)), tf32_round(__fsub_rn(v[j].y, hi.y)),
-                                    tf32_round(__fsub_rn(v[j].z, hi.z)), tf32_round(__fsub_rn(v[j].w, hi.w)));
+                    for (int j = 0; j < 4; ++j) {
+                        float4 v = xb[d][j];
+                        if (kGather) {  // relu(x + sign*q); q is zero when there is no Q (x + sign*0 == x exactly)
+                            const float4 q = qb[kGather ? d : 0][j];
+                            v.x = fmaxf(__fmaf_rn(prm.sign, q.x, v.x), 0.f);
+                            v.y = fmaxf(__fmaf_rn(prm.sign, q.y, v.y), 0.f);
+                            v.z = fmaxf(__fmaf_rn(prm.sign, q.z, v.z), 0.f);
+                            v.w = fmaxf(__fmaf_rn(prm.sign, q.w, v.w), 0.f);
+                        }
+                        const float4 hi = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
+                        const uint32_t o = st_off + (uint32_t)(j & 1) * 4u * 2048u + (uint32_t)(j >> 1) * 128u;
+                        *reinterpret_cast<float4 *>(st + o) = hi;
+                        // lo is rounded (not left to the tensor core's truncation): halves the error of the lo*w_hi term
+                        *reinterpret_cast<float4 *>(st + a_plane + o) =
+                            make_float4(tf32_round(__fsub_rn(v.x, hi.x)), tf32_round(__fsub_rn(v.y, hi.y)),
+                                        tf32_round(__fsub_rn(v.z, hi.z)), tf32_round(__fsub_rn(v.w, hi.w)));
+                    }
+                    if (trace) tq2 = clock64();
+                    if (!(prm.dbg & 16)) fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&s_full[s]);
+                    if (trace) {
+                        tq3 = clock64();
+                        long long *b = prm.dbg_buf + (size_t)it * 8;
+                        b[0] = tq0; b[1] = tq1; b[2] = tq2; b[3] = tq3;
+                    }
+                    if (base + d + kDepth < total) load_chunk(xb[d], qb[kGather ? d : 0]);  // refill the slot just consumed
+                    ++it;
+                    if (++c == nchunks) { c = 0; tile += gridDim.x; }
                 }
-                if (!kResident) {  // weight chunk: contiguous copy of the pre-packed [hi | lo] planes
-                    const float4 *src = reinterpret_cast<const float4 *>(packed_t + (size_t)c * dn_chunk_bytes(N));
-                    float4 *dst = reinterpret_cast<float4 *>(st + 2 * a_plane);
-                    const int n16 = (int)(2 * b_plane / 16);
-                    for (int e = tid; e < n16; e += kDnProducerWarps * 32) dst[e] = __ldg(src + e);
-                }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&s_full[s]);
             }
         }
     } else if (warp == kMmaWarp) {
@@ -237,6 +317,10 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
             const uint32_t idesc = make_idesc_tf32(128, npad);
             const uint32_t lboB = (uint32_t)(npad / 8) * 128u;
             uint32_t it = 0, tcount = 0;
+            if (kResident) {
+                mbar_wait(&s_wfull, 0);
+                tc_fence_after_sync();
+            }
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
                 const int a = tcount & 1;
                 const uint32_t aph = (tcount >> 1) & 1;
@@ -246,11 +330,16 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
                 for (int c = 0; c < nchunks; ++c, ++it) {
                     const int s = it % n_stages;
                     const uint32_t ph = (it / n_stages) & 1;
+                    const bool trace = prm.dbg_buf && blockIdx.x == 0 && it < 64;
+                    long long tm0 = 0, tm1 = 0;
+                    if (trace) tm0 = clock64();
                     mbar_wait(&s_full[s], ph);
+                    if (trace) tm1 = clock64();
                     tc_fence_after_sync();
                     const uint32_t ah = smem_base + (uint32_t)s * stage_bytes, al = ah + a_plane;
                     const uint32_t bh = kResident ? smem_base + w_base + (uint32_t)c * 2 * b_plane : ah + 2 * a_plane;
                     const uint32_t bl = bh + b_plane;
+                    if (!(prm.dbg & 4))
 #pragma unroll
                     for (int ks = 0; ks < kDnKC / 8; ++ks) {
                         const uint64_t dah = make_smem_desc(ah + ks * 2 * 2048u, 2048u, 128u);
@@ -262,53 +351,164 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
                         mma_tf32_ss(d, dah, dbh, idesc, 1);
                     }
                     mma_commit(&s_empty[s]);  // stage reusable once these MMAs have read it
+                    if (trace) {
+                        long long *b = prm.dbg_buf + 512 + (size_t)it * 8;
+                        b[0] = tm0; b[1] = tm1; b[2] = clock64();
+                    }
                 }
                 mma_commit(&s_tfull[a]);  // accumulator complete
             }
         }
     } else {
-        // ================= epilogue (4 warps -> TMEM lane quarters 0-3) =================
-        const int q = (warp - kDnProducerWarps) & 3;  // warp % 4 must equal the lane quarter it reads
-        const int r = q * 32 + lane;
+        // ================= epilogue (8 warps: two per TMEM lane quarter, alternating 16-column blocks) =================
+        const int ew = warp - kDnProducerWarps;
+        const int q = ew & 3;      // == warp % 4: the TMEM lane quarter this warp may read
+        const int half = ew >> 2;  // which of the quarter's two warps
         uint32_t tcount = 0;
-        const bool yvec = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(Y) & 15u) == 0) && (prm.ldy % 4 == 0);
+        const bool yvec = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(prm.Y) & 15u) == 0) && (prm.ldy % 4 == 0);
         const float *__restrict__ R1 = prm.R1;
         const float *__restrict__ R2 = prm.R2;
+        const bool r1vec = ((reinterpret_cast<uintptr_t>(R1) & 15u) == 0) && (prm.ldr1 % 4 == 0);
+        const bool r2vec = ((reinterpret_cast<uintptr_t>(R2) & 15u) == 0) && (prm.ldr2 % 4 == 0);
+        float *stg = s_epi[ew];
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
             const int a = tcount & 1;
             const uint32_t aph = (tcount >> 1) & 1;
             mbar_wait(&s_tfull[a], aph);
             tc_fence_after_sync();
-            const long long row = (long long)tile * 128 + r;
+            const int mt = tile / prm.n_blocks;
+            const long long row0 = (long long)mt * 128 + q * 32;  // first row of this warp's quarter
+            const long long row = row0 + lane;
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)a * 256u;
-            float *yr = Y + row * prm.ldy;
-            const float *r1 = R1 ? R1 + row * prm.ldr1 : nullptr;
-            const float *r2 = R2 ? R2 + row * prm.ldr2 : nullptr;
-            for (int c0 = 0; c0 < npad; c0 += 16) {
-                uint32_t v[32];
-                tmem_ld16(trow + c0, v);
-                tmem_ld_wait();
-                if (row < M) {
+            float *__restrict__ Y = prm.Y + (long long)(tile - mt * prm.n_blocks) * N;  // column block of this tile
+            if (prm.dbg & 64) {
+            } else if (kEpi == 1) {
+                // ---- weight-net epilogue: this warp's 32 rows are two points x 16 samples.  Lane (p, s) first builds
+                // its row of wn from the grouped xyz (both warps of the quarter write identical values); then, per
+                // 16-channel block, lane (p, channel) contracts the staged activations with wn over the 16 samples
+                // and writes its channel's 16 hidden units (64 B; a point's block is 1 KB contiguous).
+                float *wn = s_wn[kEpi == 1 ? q : 0];
+                {
+                    const long long rowc = row < M ? row : 0;
+                    const long long cloud = rowc / prm.g_rows_per_cloud;
+                    const float *ctr = prm.wn_xyz + (rowc / 16) * 3;
+                    const float *nbp = prm.wn_xyz + (cloud * prm.g_n + __ldg(prm.gidx + rowc)) * 3;
+                    const float gx = __fsub_rn(__ldg(nbp), __ldg(ctr)), gy = __fsub_rn(__ldg(nbp + 1), __ldg(ctr + 1)),
+                                gz = __fsub_rn(__ldg(nbp + 2), __ldg(ctr + 2));
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
+                    for (int t4 = 0; t4 < 16; t4 += 4) {
                         float o[4];
-                        const int col = c0 + j;
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            float x = __fadd_rn(__uint_as_float(v[j + u]), s_bias[col + u]);
-                            x = relu ? fmaxf(x, 0.f) : x;
-                            if (col + u < N) {
-                                if (r1) x = __fadd_rn(x, __ldg(r1 + col + u));
-                                if (r2) x = __fadd_rn(x, __ldg(r2 + col + u));
-                            }
-                            o[u] = x;
+                            const int t = t4 + u;
+                            float w = __fmaf_rn(gz, s_wnw[32 + t], __fmaf_rn(gy, s_wnw[16 + t], __fmul_rn(gx, s_wnw[t])));
+                            w = __fmul_rn(__fadd_rn(w, s_wnw[48 + t]), prm.wn_scale);
+                            o[u] = fmaxf(w, 0.f);
                         }
-                        if (col + 3 < N && yvec) {
-                            *reinterpret_cast<float4 *>(yr + col) = make_float4(o[0], o[1], o[2], o[3]);
-                        } else {
+                        *reinterpret_cast<float4 *>(wn + lane * 16 + t4) = make_float4(o[0], o[1], o[2], o[3]);
+                    }
+                }
+                const int p = lane >> 4, chq = (lane & 15) >> 2, tq = lane & 3;  // 4 channels x 4 hidden units per lane
+                for (int c0 = half * 16; c0 < npad; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld16(trow + c0, v);
+                    tmem_ld_wait();
 #pragma unroll
-                            for (int u = 0; u < 4; ++u)
-                                if (col + u < N) yr[col + u] = o[u];
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 bv = *reinterpret_cast<const float4 *>(s_bias + c0 + j);
+                        float4 o = make_float4(__fadd_rn(__uint_as_float(v[j]), bv.x), __fadd_rn(__uint_as_float(v[j + 1]), bv.y),
+                                               __fadd_rn(__uint_as_float(v[j + 2]), bv.z), __fadd_rn(__uint_as_float(v[j + 3]), bv.w));
+                        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                        *reinterpret_cast<float4 *>(stg + lane * kDnEpiStride + j) = o;
+                    }
+                    __syncwarp();
+                    float acc[4][4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) acc[i][t] = 0.f;
+#pragma unroll
+                    for (int sI = 0; sI < 16; ++sI) {
+                        const float4 g = *reinterpret_cast<const float4 *>(stg + (p * 16 + sI) * kDnEpiStride + 4 * chq);
+                        const float4 w = *reinterpret_cast<const float4 *>(wn + (p * 16 + sI) * 16 + 4 * tq);
+                        const float gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            acc[i][0] = __fmaf_rn(gv[i], w.x, acc[i][0]);
+                            acc[i][1] = __fmaf_rn(gv[i], w.y, acc[i][1]);
+                            acc[i][2] = __fmaf_rn(gv[i], w.z, acc[i][2]);
+                            acc[i][3] = __fmaf_rn(gv[i], w.w, acc[i][3]);
+                        }
+                    }
+                    const long long pt = row0 / 16 + p;
+                    const int ch = c0 + 4 * chq;
+                    if (row0 + p * 16 < M) {
+                        float *o = prm.Y + pt * prm.ldy + (long long)ch * 16 + 4 * tq;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (ch + i < N) *reinterpret_cast<float4 *>(o + i * 16) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+                    }
+                    __syncwarp();
+                }
+            } else if (yvec) {
+                // 16-column blocks: accumulator row -> registers -> (+bias, act) -> staged in shared memory -> written
+                // back 8 rows x 64 B per store instruction (full sectors); residuals are read with the same pattern
+                const int cq = lane & 3;  // float4 column inside the block
+                for (int c0 = half * 16; c0 < npad; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld16(trow + c0, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 bv = *reinterpret_cast<const float4 *>(s_bias + c0 + j);
+                        float4 o = make_float4(__fadd_rn(__uint_as_float(v[j]), bv.x), __fadd_rn(__uint_as_float(v[j + 1]), bv.y),
+                                               __fadd_rn(__uint_as_float(v[j + 2]), bv.z), __fadd_rn(__uint_as_float(v[j + 3]), bv.w));
+                        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                        *reinterpret_cast<float4 *>(stg + lane * kDnEpiStride + j) = o;
+                    }
+                    __syncwarp();
+                    const int col = c0 + cq * 4;
+                    if (col < N) {
+#pragma unroll
+                        for (int pass = 0; pass < 4; ++pass) {
+                            const int rr = pass * 8 + (lane >> 2);
+                            const long long grow = row0 + rr;
+                            if (grow < M) {
+                                float4 o = *reinterpret_cast<const float4 *>(stg + rr * kDnEpiStride + cq * 4);
+                                if (R1) {
+                                    const float4 t = dn_load4(R1 + grow * prm.ldr1, col, N, r1vec);
+                                    o.x = __fadd_rn(o.x, t.x); o.y = __fadd_rn(o.y, t.y); o.z = __fadd_rn(o.z, t.z); o.w = __fadd_rn(o.w, t.w);
+                                }
+                                if (R2) {
+                                    const float4 t = dn_load4(R2 + grow * prm.ldr2, col, N, r2vec);
+                                    o.x = __fadd_rn(o.x, t.x); o.y = __fadd_rn(o.y, t.y); o.z = __fadd_rn(o.z, t.z); o.w = __fadd_rn(o.w, t.w);
+                                }
+                                if (!(prm.dbg & 32)) *reinterpret_cast<float4 *>(Y + grow * prm.ldy + col) = o;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            } else {
+                // narrow / unaligned outputs (e.g. the 3-channel coordinate layers): one row per thread, scalar stores
+                float *yr = Y + row * prm.ldy;
+                const float *r1 = R1 ? R1 + row * prm.ldr1 : nullptr;
+                const float *r2 = R2 ? R2 + row * prm.ldr2 : nullptr;
+                for (int c0 = half * 16; c0 < npad; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld16(trow + c0, v);
+                    tmem_ld_wait();
+                    if (row < M) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int col = c0 + j;
+                            if (col < N) {
+                                float x = __fadd_rn(__uint_as_float(v[j]), s_bias[col]);
+                                x = relu ? fmaxf(x, 0.f) : x;
+                                if (r1) x = __fadd_rn(x, __ldg(r1 + col));
+                                if (r2) x = __fadd_rn(x, __ldg(r2 + col));
+                                yr[col] = x;
+                            }
                         }
                     }
                 }
@@ -351,6 +551,8 @@ extern "C" int dispu_dense_pack(int K, int N, const float *W, void *packed, disp
     return dispu_dense_pack_strided(K, N, W, N, 1, 1, 0, packed, 0, stream);
 }
 
+static long long *g_dense_dbg_buf = nullptr;  // development only (DISPU_DENSE_TRACE)
+
 extern "C" int dispu_dense_tf32x3_ex(const dispu_dense_args *a, dispu_stream_t stream) {
     DISPU_REQUIRE(a, DISPU_ENULL);
     const long long M = a->M;
@@ -370,13 +572,22 @@ extern "C" int dispu_dense_tf32x3_ex(const dispu_dense_args *a, dispu_stream_t s
         DISPU_REQUIRE(a->rows_per_batch % 128 == 0 && M % a->rows_per_batch == 0, DISPU_EUNSUPPORTED);
         DISPU_REQUIRE(a->packed_batch_stride % 16 == 0, DISPU_EINVAL);
     }
-    const long long n_tiles_ll = ceil_div64(M, 128);
+    const int n_blocks = a->n_blocks > 0 ? a->n_blocks : 1;
+    const bool wnet = a->wn_xyz != nullptr;
+    if (n_blocks > 1) DISPU_REQUIRE(a->packed_block_stride % 16 == 0 && ldy >= (long long)n_blocks * N, DISPU_EINVAL);
+    if (wnet) {
+        DISPU_REQUIRE(a->gather_idx && a->wn_w, DISPU_ENULL);
+        DISPU_REQUIRE(a->gather_ns == 16 && N % 32 == 0 && M % 128 == 0 && n_blocks == 1, DISPU_EUNSUPPORTED);
+        DISPU_REQUIRE((a->ldy > 0 ? a->ldy : (long long)N * 16) >= (long long)N * 16 && (a->ldy % 4) == 0 &&
+                          (reinterpret_cast<uintptr_t>(a->Y) & 15u) == 0, DISPU_EINVAL);
+    }
+    const long long n_tiles_ll = ceil_div64(M, 128) * n_blocks;
     DISPU_REQUIRE(n_tiles_ll <= 0x7fffffffLL, DISPU_EUNSUPPORTED);
     const int n_tiles = (int)n_tiles_ll;
     const int npad = dn_npad(N);
     const size_t a_stage = 2 * 128 * kDnKC * 4, b_chunk = 2 * (size_t)npad * kDnKC * 4;
     const size_t w_all = (size_t)dn_chunks(K) * b_chunk;
-    const bool resident = !batched && w_all + 2 * a_stage <= (size_t)kDnSmemBudget;
+    const bool resident = !batched && n_blocks == 1 && w_all + 2 * a_stage <= (size_t)kDnSmemBudget;
     int stages;
     size_t smem;
     if (resident) {
@@ -405,19 +616,33 @@ extern "C" int dispu_dense_tf32x3_ex(const dispu_dense_args *a, dispu_stream_t s
     p.R2 = a->R2; p.ldr2 = a->ldr2 > 0 ? a->ldr2 : N;
     p.rows_per_batch = batched ? a->rows_per_batch : 0;
     p.packed_batch_stride = a->packed_batch_stride;
+    p.n_blocks = n_blocks; p.packed_block_stride = a->packed_block_stride;
+    p.wn_xyz = a->wn_xyz; p.wn_w = a->wn_w; p.wn_b = a->wn_b; p.wn_scale = a->wn_scale;
+    if (wnet) p.ldy = a->ldy > 0 ? a->ldy : (long long)N * 16;
     p.n_tiles = n_tiles; p.n_stages = stages;
-    cudaError_t e;
-    count_launch();
-    if (resident) {
-        e = cudaFuncSetAttribute(dense_tf32x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        dense_tf32x3_kernel<true><<<grid, kDnThreads, smem, (cudaStream_t)stream>>>(p);
-    } else {
-        e = cudaFuncSetAttribute(dense_tf32x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        dense_tf32x3_kernel<false><<<grid, kDnThreads, smem, (cudaStream_t)stream>>>(p);
+    {
+        static const int dbg = [] { const char *e = getenv("DISPU_DENSE_DBG"); return e ? atoi(e) : 0; }();
+        p.dbg = dbg;
+        if (getenv("DISPU_DENSE_TRACE") && !g_dense_dbg_buf) cudaMalloc(&g_dense_dbg_buf, 1536 * sizeof(long long));
+        p.dbg_buf = g_dense_dbg_buf;
+        if (g_dense_dbg_buf) cudaMemsetAsync(g_dense_dbg_buf, 0, 1536 * sizeof(long long), (cudaStream_t)stream);
     }
-    return finish_launch();
+    count_launch();
+    auto launch = [&](auto kern) -> int {
+        const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        kern<<<grid, kDnThreads, smem, (cudaStream_t)stream>>>(p);
+        return finish_launch();
+    };
+    if (wnet) return resident ? launch(dense_tf32x3_kernel<true, true, 1>) : launch(dense_tf32x3_kernel<false, true, 1>);
+    if (resident) return p.gidx ? launch(dense_tf32x3_kernel<true, true, 0>) : launch(dense_tf32x3_kernel<true, false, 0>);
+    return p.gidx ? launch(dense_tf32x3_kernel<false, true, 0>) : launch(dense_tf32x3_kernel<false, false, 0>);
+}
+
+// development only: copy the clock64 trace of the last launch to the host (1536 int64)
+extern "C" int dispu_dense_debug_trace(long long *host_out) {
+    if (!g_dense_dbg_buf || !host_out) return DISPU_EUNSUPPORTED;
+    return (int)cudaMemcpy(host_out, g_dense_dbg_buf, 1536 * sizeof(long long), cudaMemcpyDeviceToHost);
 }
 
 extern "C" int dispu_dense_tf32x3(long long M, int K, int N, const float *X, const void *packed, const float *bias,

@@ -40,9 +40,10 @@ feature_knn_kernel(int n, int m, int c, int k, int skip, const float *__restrict
     extern __shared__ float fk_smem[];
     constexpr int kChunk = 32 * P;
     constexpr int kStride = kChunk + 1;  // odd stride: the transposing stores are conflict-free too
+    constexpr int kQ = P <= 8 ? 4 : 2;   // queries whose distances are in registers at once
     float *s_ft = fk_smem;                           // [c][kStride]
     float *s_r = s_ft + (size_t)c * kStride;         // [kChunk]
-    float *s_q = s_r + kChunk;                       // [warps][2][c]
+    float *s_q = s_r + kChunk;                       // [warps][kFkQueriesPerWarp][c]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cloud = blockIdx.y;
     const float *pts = points + (size_t)cloud * n * ldp;
@@ -73,78 +74,82 @@ feature_knn_kernel(int n, int m, int c, int k, int skip, const float *__restrict
         __syncthreads();
         if (q0 >= m) continue;
 #pragma unroll
-        for (int u0 = 0; u0 < kFkQueriesPerWarp; u0 += 2) {
+        for (int u0 = 0; u0 < kFkQueriesPerWarp; u0 += kQ) {
             if (q0 + u0 >= m) break;
-            // stage the two query vectors (second one clamps to a valid row; its result is discarded)
-            float *sq = s_q + (size_t)warp * 2 * c;
+            // stage the kQ query vectors (rows past m clamp to a valid row; their results are discarded)
+            float *sq = s_q + (size_t)warp * kFkQueriesPerWarp * c;
             __syncwarp();
-            for (int e = lane; e < 2 * c; e += 32) {
+            for (int e = lane; e < kQ * c; e += 32) {
                 const int w = e / c, l = e - w * c;
                 sq[e] = __ldg(qry + (size_t)min(q0 + u0 + w, m - 1) * ldq + l);
             }
             __syncwarp();
-            float rq0 = 0.f, rq1 = 0.f;
-            for (int l = 0; l < c; ++l) {
-                rq0 = __fmaf_rn(sq[l], sq[l], rq0);
-                rq1 = __fmaf_rn(sq[c + l], sq[c + l], rq1);
-            }
-            float d0[P], d1[P];
+            float rq[kQ];
 #pragma unroll
-            for (int t = 0; t < P; ++t) { d0[t] = 0.f; d1[t] = 0.f; }
+            for (int w = 0; w < kQ; ++w) rq[w] = 0.f;
             for (int l = 0; l < c; ++l) {
-                const float a0 = sq[l], a1 = sq[c + l];
+#pragma unroll
+                for (int w = 0; w < kQ; ++w) rq[w] = __fmaf_rn(sq[w * c + l], sq[w * c + l], rq[w]);
+            }
+            float d[kQ][P];
+#pragma unroll
+            for (int w = 0; w < kQ; ++w)
+#pragma unroll
+                for (int t = 0; t < P; ++t) d[w][t] = 0.f;
+            for (int l = 0; l < c; ++l) {
+                float a[kQ];
+#pragma unroll
+                for (int w = 0; w < kQ; ++w) a[w] = sq[w * c + l];
                 const float *col = s_ft + (size_t)l * kStride + lane;
 #pragma unroll
                 for (int t = 0; t < P; ++t) {
                     const float v = col[t * 32];
-                    d0[t] = __fmaf_rn(a0, v, d0[t]);
-                    d1[t] = __fmaf_rn(a1, v, d1[t]);
+#pragma unroll
+                    for (int w = 0; w < kQ; ++w) d[w][t] = __fmaf_rn(a[w], v, d[w][t]);
                 }
             }
 #pragma unroll
             for (int t = 0; t < P; ++t) {
                 const int p = t * 32 + lane;
                 const float rp = s_r[p];
-                d0[t] = p < tn ? __fadd_rn(__fmaf_rn(-2.f, d0[t], rq0), rp) : inf;
-                d1[t] = p < tn ? __fadd_rn(__fmaf_rn(-2.f, d1[t], rq1), rp) : inf;
-            }
 #pragma unroll
-            for (int w = 0; w < 2; ++w) {
-                const int u = u0 + w;
-                float cd = bd[u];  // carried entry of this lane (inf when none)
-                int ci = bi[u];
-                float nd = inf;
-                int ni = 0x7fffffff;
-                for (int r = 0; r < k; ++r) {
+                for (int w = 0; w < kQ; ++w) d[w][t] = p < tn ? __fadd_rn(__fmaf_rn(-2.f, d[w][t], rq[w]), rp) : inf;
+            }
+            // k rounds of warp arg-min; the kQ queries' rounds are independent chains issued back to back
+            float cd[kQ], nd[kQ];
+            int ci[kQ], ni[kQ];
+#pragma unroll
+            for (int w = 0; w < kQ; ++w) { cd[w] = bd[u0 + w]; ci[w] = bi[u0 + w]; nd[w] = inf; ni[w] = 0x7fffffff; }
+            for (int r = 0; r < k; ++r) {
+#pragma unroll
+                for (int w = 0; w < kQ; ++w) {
                     // lane-local minimum; strict '<' keeps the carried entry (lower index) and the lower slot on ties
-                    float lm = cd;
+                    float lm = cd[w];
                     int lt = -1;
 #pragma unroll
-                    for (int t = 0; t < P; ++t) {
-                        const float v = w == 0 ? d0[t] : d1[t];
-                        if (v < lm) { lm = v; lt = t; }
-                    }
-                    const int gi = lt < 0 ? ci : t0 + lt * 32 + lane;
+                    for (int t = 0; t < P; ++t)
+                        if (d[w][t] < lm) { lm = d[w][t]; lt = t; }
+                    const int gi = lt < 0 ? ci[w] : t0 + lt * 32 + lane;
                     const unsigned key = ord_key(lm);
                     const unsigned kmin = __reduce_min_sync(kFull, key);
                     const unsigned imin = __reduce_min_sync(kFull, key == kmin ? (unsigned)gi : 0xffffffffu);
                     const bool win = key == kmin && (unsigned)gi == imin;
                     const int wl = __ffs(__ballot_sync(kFull, win)) - 1;
                     const float dmin = __shfl_sync(kFull, lm, wl);
-                    if (lane == r) { nd = dmin; ni = (int)imin; }
+                    if (lane == r) { nd[w] = dmin; ni[w] = (int)imin; }
                     if (win && lane == wl) {
                         if (lt < 0) {
-                            cd = inf;
+                            cd[w] = inf;
                         } else {
 #pragma unroll
                             for (int t = 0; t < P; ++t)
-                                if (t == lt) { if (w == 0) d0[t] = inf; else d1[t] = inf; }
+                                if (t == lt) d[w][t] = inf;
                         }
                     }
                 }
-                bd[u] = nd;
-                bi[u] = ni;
             }
+#pragma unroll
+            for (int w = 0; w < kQ; ++w) { bd[u0 + w] = nd[w]; bi[u0 + w] = ni[w]; }
         }
     }
 #pragma unroll
@@ -176,15 +181,19 @@ edge_proj_kernel(long long rows, int c, const float *__restrict__ feat, int ldf,
     float *s_f = s_b + kEcProjW;                   // [64][c+1]
     const int tid = threadIdx.x;
     const int fs = c + 1;
-    for (int e = tid; e < c * kEcProjW; e += kEcThreads) {
-        const int l = e / kEcProjW, o = e - l * kEcProjW;
+    if (tid < 2 * kEcProjW) {  // thread -> fixed output column o (so a fixed source matrix), rows l0, l0+2, ...: plain strided loads
+        const int o = tid % kEcProjW, l0 = tid / kEcProjW;
         const int part = o / kEcG, oc = o - part * kEcG;
-        float v;
-        if (part == 0) v = __ldg(w0 + (size_t)(c + l) * kEcG + oc);
-        else if (part == 1) v = __fsub_rn(__ldg(w0 + (size_t)l * kEcG + oc), __ldg(w0 + (size_t)(c + l) * kEcG + oc));
-        else if (part == 2) v = __ldg(w1 + (size_t)(kEcG + l) * kEcG + oc);
-        else v = __ldg(w2 + (size_t)(2 * kEcG + l) * kEcG + oc);
-        s_w[e] = v;
+        const float *src = part == 0 ? w0 + (size_t)c * kEcG : part == 1 ? w0 : part == 2 ? w1 + (size_t)kEcG * kEcG
+                                                                                         : w2 + (size_t)2 * kEcG * kEcG;
+        if (part == 1) {
+#pragma unroll 4
+            for (int l = l0; l < c; l += 2)
+                s_w[l * kEcProjW + o] = __fsub_rn(__ldg(src + (size_t)l * kEcG + oc), __ldg(src + (size_t)(c + l) * kEcG + oc));
+        } else {
+#pragma unroll 8
+            for (int l = l0; l < c; l += 2) s_w[l * kEcProjW + o] = __ldg(src + (size_t)l * kEcG + oc);
+        }
     }
     for (int o = tid; o < kEcProjW; o += kEcThreads) {
         const int part = o / kEcG, oc = o - part * kEcG;
@@ -225,22 +234,34 @@ edge_proj_kernel(long long rows, int c, const float *__restrict__ feat, int ldf,
     }
 }
 
-// y += x . W   (x: 24 values, W: 24x24 row-major as float4 rows in shared memory), two edges share the weight loads
-__device__ __forceinline__ void ec_matvec2(const float4 *__restrict__ w4, const float (&xa)[kEcG], const float (&xb)[kEcG],
-                                           float (&ya)[kEcG], float (&yb)[kEcG]) {
+// Packed FP32 pairs (FFMA2: one issue slot, two IEEE fma.rn results — bit-identical to two __fmaf_rn).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+// y += x . W for two edges at once (x: 24 values each, W: 24x24 row-major in shared memory read as 16-byte broadcasts;
+// y kept as 12 packed column pairs per edge)
+__device__ __forceinline__ void ec_matvec2(const ulonglong2 *__restrict__ w2, const float (&xa)[kEcG], const float (&xb)[kEcG],
+                                           f32x2 (&ya)[kEcG / 2], f32x2 (&yb)[kEcG / 2]) {
 #pragma unroll
     for (int i = 0; i < kEcG; ++i) {
+        const f32x2 xa2 = pack2(xa[i], xa[i]), xb2 = pack2(xb[i], xb[i]);
 #pragma unroll
         for (int q = 0; q < kEcG / 4; ++q) {
-            const float4 w = w4[i * (kEcG / 4) + q];
-            ya[4 * q + 0] = __fmaf_rn(xa[i], w.x, ya[4 * q + 0]);
-            ya[4 * q + 1] = __fmaf_rn(xa[i], w.y, ya[4 * q + 1]);
-            ya[4 * q + 2] = __fmaf_rn(xa[i], w.z, ya[4 * q + 2]);
-            ya[4 * q + 3] = __fmaf_rn(xa[i], w.w, ya[4 * q + 3]);
-            yb[4 * q + 0] = __fmaf_rn(xb[i], w.x, yb[4 * q + 0]);
-            yb[4 * q + 1] = __fmaf_rn(xb[i], w.y, yb[4 * q + 1]);
-            yb[4 * q + 2] = __fmaf_rn(xb[i], w.z, yb[4 * q + 2]);
-            yb[4 * q + 3] = __fmaf_rn(xb[i], w.w, yb[4 * q + 3]);
+            const ulonglong2 w = w2[i * (kEcG / 4) + q];  // columns 4q..4q+3 of row i
+            ya[2 * q] = fma2(xa2, w.x, ya[2 * q]);
+            ya[2 * q + 1] = fma2(xa2, w.y, ya[2 * q + 1]);
+            yb[2 * q] = fma2(xb2, w.x, yb[2 * q]);
+            yb[2 * q + 1] = fma2(xb2, w.y, yb[2 * q + 1]);
         }
     }
 }
@@ -253,8 +274,20 @@ __device__ __forceinline__ void ec_load24(const float *__restrict__ p, float (&v
         v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
     }
 }
+__device__ __forceinline__ void ec_load24x2(const float *__restrict__ p, f32x2 (&a)[kEcG / 2], f32x2 (&b)[kEcG / 2]) {
+    const ulonglong2 *p2 = reinterpret_cast<const ulonglong2 *>(p);
+#pragma unroll
+    for (int q = 0; q < kEcG / 4; ++q) {
+        const ulonglong2 t = __ldg(p2 + q);
+        a[2 * q] = t.x; a[2 * q + 1] = t.y;
+        b[2 * q] = t.x; b[2 * q + 1] = t.y;
+    }
+}
 
-// 8 lanes per point, two edges per lane per pass (k = 16: one pass).  out row = [max y2 | max y1 | max y0 | f_i].
+// 8 lanes per point, two edges per lane per pass (k <= 16: a single pass, kSingle, with no running maximum held in
+// registers).  The per-edge 24x24 products run on packed FFMA2.  out row = [max y2 | max y1 | max y0 | f_i].
+constexpr int kEcLanes = 8;
+template <bool kSingle>
 __global__ void __launch_bounds__(kEcThreads, 1)
 edge_mlp_max_kernel(long long rows, int n, int c, int k, const float *__restrict__ proj, const int *__restrict__ idx,
                     const float *__restrict__ w1, const float *__restrict__ w2, const float *__restrict__ feat, int ldf,
@@ -267,8 +300,8 @@ edge_mlp_max_kernel(long long rows, int n, int c, int k, const float *__restrict
         s_w2b[e] = __ldg(w2 + kEcG * kEcG + e);    // W2[g:2g]   (multiplies y0)
     }
     __syncthreads();
-    const int t = tid & 7;
-    const long long row = (long long)blockIdx.x * (kEcThreads / 8) + (tid >> 3);
+    const int t = tid & (kEcLanes - 1);
+    const long long row = (long long)blockIdx.x * (kEcThreads / kEcLanes) + (tid / kEcLanes);
     const bool valid = row < rows;
     const long long rowc = valid ? row : rows - 1;  // keep every lane in the shuffles
     const long long cloud = rowc / n;
@@ -276,12 +309,15 @@ edge_mlp_max_kernel(long long rows, int n, int c, int k, const float *__restrict
     const int *irow = idx + rowc * (long long)k;
     const float neg_inf = __int_as_float(0xff800000);
     float m0[kEcG], m1[kEcG], m2[kEcG];
+    if (!kSingle) {
 #pragma unroll
-    for (int o = 0; o < kEcG; ++o) { m0[o] = neg_inf; m1[o] = neg_inf; m2[o] = neg_inf; }
-
-    for (int s0 = t; s0 < k; s0 += 16) {
-        const int s1 = (s0 + 8 < k) ? s0 + 8 : s0;  // odd tail: the duplicate edge does not change the max
-        const int ja = __ldg(irow + s0), jb = __ldg(irow + s1);
+        for (int o = 0; o < kEcG; ++o) { m0[o] = neg_inf; m1[o] = neg_inf; m2[o] = neg_inf; }
+    }
+    for (int s0 = t; s0 < (kSingle ? t + 1 : k); s0 += 2 * kEcLanes) {
+        // second edge of the pair; past the end it repeats a valid edge (the maximum is unchanged)
+        const int sa = kSingle ? min(s0, k - 1) : s0;
+        const int sb = min(s0 + kEcLanes, k - 1);
+        const int ja = __ldg(irow + sa), jb = __ldg(irow + sb);
         float ya0[kEcG], yb0[kEcG];
         {
             float pc[kEcG];
@@ -294,30 +330,39 @@ edge_mlp_max_kernel(long long rows, int n, int c, int k, const float *__restrict
                 yb0[o] = fmaxf(__fadd_rn(yb0[o], pc[o]), 0.f);
             }
         }
-        float ya2[kEcG], yb2[kEcG];
-        ec_load24(prow + 3 * kEcG, ya2);
+        f32x2 ya2[kEcG / 2], yb2[kEcG / 2], ya1[kEcG / 2], yb1[kEcG / 2];
+        ec_load24x2(prow + 3 * kEcG, ya2, yb2);
+        ec_matvec2(reinterpret_cast<const ulonglong2 *>(s_w2b), ya0, yb0, ya2, yb2);
+        ec_load24x2(prow + 2 * kEcG, ya1, yb1);
+        ec_matvec2(reinterpret_cast<const ulonglong2 *>(s_w1a), ya0, yb0, ya1, yb1);
+        float xa1[kEcG], xb1[kEcG];
 #pragma unroll
-        for (int o = 0; o < kEcG; ++o) yb2[o] = ya2[o];
-        ec_matvec2(reinterpret_cast<const float4 *>(s_w2b), ya0, yb0, ya2, yb2);
-        float ya1[kEcG], yb1[kEcG];
-        ec_load24(prow + 2 * kEcG, ya1);
-#pragma unroll
-        for (int o = 0; o < kEcG; ++o) yb1[o] = ya1[o];
-        ec_matvec2(reinterpret_cast<const float4 *>(s_w1a), ya0, yb0, ya1, yb1);
+        for (int o = 0; o < kEcG / 2; ++o) {
+            unpack2(ya1[o], xa1[2 * o], xa1[2 * o + 1]);
+            unpack2(yb1[o], xb1[2 * o], xb1[2 * o + 1]);
+        }
 #pragma unroll
         for (int o = 0; o < kEcG; ++o) {
-            m0[o] = fmaxf(m0[o], fmaxf(ya0[o], yb0[o]));
-            ya1[o] = fmaxf(ya1[o], 0.f);
-            yb1[o] = fmaxf(yb1[o], 0.f);
-            m1[o] = fmaxf(m1[o], fmaxf(ya1[o], yb1[o]));
+            xa1[o] = fmaxf(xa1[o], 0.f);
+            xb1[o] = fmaxf(xb1[o], 0.f);
+            const float v0 = fmaxf(ya0[o], yb0[o]), v1 = fmaxf(xa1[o], xb1[o]);
+            m0[o] = kSingle ? v0 : fmaxf(m0[o], v0);
+            m1[o] = kSingle ? v1 : fmaxf(m1[o], v1);
         }
-        ec_matvec2(reinterpret_cast<const float4 *>(s_w2a), ya1, yb1, ya2, yb2);
+        ec_matvec2(reinterpret_cast<const ulonglong2 *>(s_w2a), xa1, xb1, ya2, yb2);
 #pragma unroll
-        for (int o = 0; o < kEcG; ++o) m2[o] = fmaxf(m2[o], fmaxf(ya2[o], yb2[o]));
+        for (int o = 0; o < kEcG / 2; ++o) {
+            float a0, a1, b0, b1;
+            unpack2(ya2[o], a0, a1);
+            unpack2(yb2[o], b0, b1);
+            const float v0 = fmaxf(a0, b0), v1 = fmaxf(a1, b1);
+            m2[2 * o] = kSingle ? v0 : fmaxf(m2[2 * o], v0);
+            m2[2 * o + 1] = kSingle ? v1 : fmaxf(m2[2 * o + 1], v1);
+        }
     }
     // max over the 8 lanes of the point
 #pragma unroll
-    for (int off = 1; off < 8; off <<= 1) {
+    for (int off = 1; off < kEcLanes; off <<= 1) {
 #pragma unroll
         for (int o = 0; o < kEcG; ++o) {
             m0[o] = fmaxf(m0[o], __shfl_xor_sync(kFull, m0[o], off));
@@ -335,7 +380,7 @@ edge_mlp_max_kernel(long long rows, int n, int c, int k, const float *__restrict
         if (((q + 12) & 7) == t) o4[q + 12] = make_float4(m0[4 * q], m0[4 * q + 1], m0[4 * q + 2], m0[4 * q + 3]);
     }
     const float4 *f4 = reinterpret_cast<const float4 *>(feat + row * (long long)ldf);
-    for (int q = t; q < c / 4; q += 8) o4[3 * kEcG / 4 + q] = __ldg(f4 + q);
+    for (int q = t; q < c / 4; q += kEcLanes) o4[3 * kEcG / 4 + q] = __ldg(f4 + q);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -414,7 +459,7 @@ using namespace dispu;
 template <int P>
 static int launch_feature_knn(int b, int n, int m, int c, int k, int skip, const float *points, int ldp, const float *queries,
                               int ldq, float *dist, int *idx, cudaStream_t stream) {
-    const size_t smem = ((size_t)c * (32 * P + 1) + 32 * P + (size_t)kFkWarps * 2 * c) * sizeof(float);
+    const size_t smem = ((size_t)c * (32 * P + 1) + 32 * P + (size_t)kFkWarps * kFkQueriesPerWarp * c) * sizeof(float);
     if (smem > 220 * 1024) return DISPU_EUNSUPPORTED;
     cudaError_t e = cudaFuncSetAttribute(feature_knn_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -433,7 +478,7 @@ extern "C" int dispu_feature_knn(int b, int n, int m, int c, int k, int skip, co
     if (b == 0 || m == 0) return DISPU_OK;
     DISPU_REQUIRE(points && queries && idx, DISPU_ENULL);
     // largest chunk (32*P candidates) that covers the cloud and whose transposed features fit in shared memory
-    auto fits = [&](int P) { return ((size_t)c * (32 * P + 1) + 32 * P + (size_t)kFkWarps * 2 * c) * sizeof(float) <= 220 * 1024; };
+    auto fits = [&](int P) { return ((size_t)c * (32 * P + 1) + 32 * P + (size_t)kFkWarps * kFkQueriesPerWarp * c) * sizeof(float) <= 220 * 1024; };
     if (n > 512 && fits(32)) return launch_feature_knn<32>(b, n, m, c, k, skip, points, ldp, queries, ldq, dist, idx, stream);
     if (n > 256 && fits(16)) return launch_feature_knn<16>(b, n, m, c, k, skip, points, ldp, queries, ldq, dist, idx, stream);
     return launch_feature_knn<8>(b, n, m, c, k, skip, points, ldp, queries, ldq, dist, idx, stream);
@@ -465,8 +510,11 @@ extern "C" int dispu_dense_conv(int b, int n, int c, int k, int growth, const fl
     count_launch(2);
     edge_proj_kernel<<<(unsigned)ceil_div64(rows, kEcProjRows), kEcThreads, smem, stream>>>(rows, c, feat, ldf, w0, b0, w1, b1,
                                                                                           w2, b2, proj);
-    edge_mlp_max_kernel<<<(unsigned)ceil_div64(rows, kEcThreads / 8), kEcThreads, 0, stream>>>(rows, n, c, k, proj, idx, w1, w2,
-                                                                                             feat, ldf, out, ldo);
+    const unsigned g2 = (unsigned)ceil_div64(rows, kEcThreads / kEcLanes);
+    if (k <= 2 * kEcLanes)
+        edge_mlp_max_kernel<true><<<g2, kEcThreads, 0, stream>>>(rows, n, c, k, proj, idx, w1, w2, feat, ldf, out, ldo);
+    else
+        edge_mlp_max_kernel<false><<<g2, kEcThreads, 0, stream>>>(rows, n, c, k, proj, idx, w1, w2, feat, ldf, out, ldo);
     return finish_launch();
 }
 

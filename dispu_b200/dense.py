@@ -17,7 +17,9 @@ class PackedLinear:
     straight into its slot of a concatenated tensor.  `gather=(idx, Q, sign)`: the operand rows are
     relu(x[b, idx[b,i,s], :] + sign*Q[b,i,:]) (x is the per-point table (b,n,K), idx (b,m,ns), Q (b,m,K) or None),
     i.e. GroupPoint + centre term + ReLU fused into the load.  `residuals`: up to two (..., N) tensors added after
-    the activation."""
+    the activation.  `weightnet=(xyz, Ww, bw, scale)` (with gather, ns = 16): the layer output G (b,m,16,N) is not
+    written; the result is (b,m,N*16) = flatten(transpose(G) . relu(((xyz[idx]-xyz) . Ww + bw) * scale)), PointShuffle2's
+    weight net + transposed product (Common/ops.py:1062-1067) fused into the epilogue."""
 
     def __init__(self, weight, bias=None):
         weight = req(weight, torch.float32, 2, "weight")
@@ -29,7 +31,7 @@ class PackedLinear:
         self.packed = torch.empty((nbytes,), dtype=torch.uint8, device=weight.device)
         call("dispu_dense_pack", self.K, self.N, ptr(weight), ptr(self.packed), stream_ptr())
 
-    def __call__(self, x, relu=False, out=None, gather=None, residuals=()):
+    def __call__(self, x, relu=False, out=None, gather=None, residuals=(), weightnet=None):
         if x.shape[-1] != self.K:
             raise ValueError(f"PackedLinear expects last dim {self.K}, got {tuple(x.shape)}")
         a = _lib.DenseArgs()
@@ -51,6 +53,15 @@ class PackedLinear:
             a.sign = float(sign)
             M = b * m * ns
             oshape = (b, m, ns, self.N)
+            if weightnet is not None:
+                xyz, ww, bw, scale = weightnet
+                xyz = req(xyz, torch.float32, 3, "xyz")
+                ww = req(ww, torch.float32, 2, "Ww")
+                if ns != 16 or tuple(ww.shape) != (3, 16) or tuple(xyz.shape) != (b, m, 3) or x.shape[1] != m:
+                    raise ValueError("weightnet: needs ns == 16, Ww (3,16), xyz (b,m,3) and support == query points")
+                self._wn_keep = (xyz, ww, bw)
+                a.wn_xyz, a.wn_w, a.wn_b, a.wn_scale = ptr(xyz), ptr(ww), ptr(bw), float(scale)
+                oshape = (b, m, self.N * 16)
         else:
             M = xm
             oshape = (*x.shape[:-1], self.N)
@@ -58,7 +69,10 @@ class PackedLinear:
         if out is None:
             out = torch.empty(oshape, dtype=torch.float32, device=x.device)
         yp, ym, ldy = rows(out, "out")
-        if ym != M or out.shape[-1] != self.N:
+        if weightnet is not None:
+            if ym * 16 != M or out.shape[-1] != self.N * 16:
+                raise ValueError("weightnet: out must be (b,m,N*16)")
+        elif ym != M or out.shape[-1] != self.N:
             raise ValueError(f"out: expected {M} rows of {self.N}, got {tuple(out.shape)}")
         a.Y, a.ldy = yp, ldy
         for i, r in enumerate(residuals):
@@ -94,17 +108,21 @@ class BatchedOperand:
              batch_stride, ptr(self.packed), self.stride, stream_ptr())
         return self
 
-    def matmul(self, x, out=None, relu=False):
-        """x (batch, rows, K) [row-strided ok] -> out (batch, rows, N); rows % 128 == 0."""
+    def matmul(self, x, out=None, relu=False, n_blocks=1):
+        """x (B, rows, K) [row-strided ok] -> out (B, rows, n_blocks*N); rows % 128 == 0.  With n_blocks > 1 this object
+        holds B*n_blocks operands, operand (i*n_blocks + j) producing columns [j*N, (j+1)*N) of cloud i."""
         a = _lib.DenseArgs()
         xp, xm, ldx = rows(x, "x")
-        if x.dim() != 3 or x.shape[0] != self.batch or x.shape[2] != self.K:
-            raise ValueError("BatchedOperand.matmul: x must be (batch, rows, K)")
+        if x.dim() != 3 or x.shape[0] * n_blocks != self.batch or x.shape[2] != self.K:
+            raise ValueError("BatchedOperand.matmul: x must be (batch / n_blocks, rows, K)")
         if out is None:
-            out = torch.empty((self.batch, x.shape[1], self.N), dtype=torch.float32, device=x.device)
+            out = torch.empty((x.shape[0], x.shape[1], n_blocks * self.N), dtype=torch.float32, device=x.device)
         yp, ym, ldy = rows(out, "out")
+        if ym != xm or out.shape[-1] != n_blocks * self.N:
+            raise ValueError("BatchedOperand.matmul: out shape mismatch")
         a.M, a.K, a.N, a.X, a.ldx = xm, self.K, self.N, xp, ldx
         a.packed, a.relu, a.Y, a.ldy = ptr(self.packed), 1 if relu else 0, yp, ldy
-        a.rows_per_batch, a.packed_batch_stride = x.shape[1], self.stride
+        a.rows_per_batch, a.packed_batch_stride = x.shape[1], n_blocks * self.stride
+        a.n_blocks, a.packed_block_stride = n_blocks, self.stride
         call("dispu_dense_tf32x3_ex", C.byref(a), stream_ptr())
         return out

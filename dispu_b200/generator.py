@@ -53,24 +53,6 @@ class DispuOps:
         return tf_grouping.group_affine_relu(P, Q, idx, sign)
 
 
-def _lib_dense_args():
-    from . import _lib
-    return _lib.DenseArgs()
-
-
-def _batched_matmul(a, x, op, j, nb, out):
-    """out (b,rows,N) = x (b,rows,K) . W_{b*nb + j}: one column block of a per-cloud product (see BatchedOperand)."""
-    import ctypes as C
-    from ._t import call, ptr, rows, stream_ptr
-    xp, xm, ldx = rows(x, "x")
-    yp, ym, ldy = rows(out, "out")
-    a.M, a.K, a.N, a.X, a.ldx = xm, op.K, op.N, xp, ldx
-    a.packed, a.relu, a.Y, a.ldy = ptr(op.packed) + j * op.stride, 0, yp, ldy
-    a.rows_per_batch, a.packed_batch_stride = x.shape[1], nb * op.stride
-    call("dispu_dense_tf32x3_ex", C.byref(a), stream_ptr())
-    return out
-
-
 def _xavier(gen, cin, cout, device, fan_in=None, fan_out=None):
     fi = cin if fan_in is None else fan_in
     fo = cout if fan_out is None else fan_out
@@ -88,6 +70,7 @@ class Generator:
         # fused: the whole forward on this library's kernels with no concat / slice / gather intermediates
         # (forward_fused); default = whenever the CUDA backend, hoisting and the tensor-core layers are all on
         self.fused = fused
+        self.fuse_weightnet = False
         self._bufs = {}
         self._packed = {}
         self.hoist = hoist  # use the fused / hoisted grouped-layer formulation when the backend offers it
@@ -342,19 +325,22 @@ class Generator:
         if m % 256:
             raise ValueError("forward_fused: 4*n must be a multiple of 256")
         kop = BatchedOperand(b * nb, 64, 256, dev).pack(kv, 0, 1, 128, 256 * 128)
-        att = torch.empty((b, m, m), dtype=torch.float32, device=dev)
-        a = _lib_dense_args()
-        for j in range(nb):
-            _batched_matmul(a, q, kop, j, nb, att[..., j * 256:(j + 1) * 256])
+        att = kop.matmul(q, n_blocks=nb)  # (b,m,m), one launch: column block j = keys [256j, 256j+256)
         att = torch.softmax(att, dim=-1)
         vop = BatchedOperand(b, m, 64, dev).pack(kv, 64, 128, 1, m * 128)
         nonlocal_pt = self._fx(vop.matmul(att), "nl_back")
         # local cell: conv0 hoisted to per-point products, gathered + ReLU'd inside conv1's operand load
         pm = self._fx(xf, "_f_psp", act=False)       # (b,m,128) = x_j(Wa+Wb) + f_j Wc + b
         qm = self._fx(coarse, "_f_psq", act=False)   # (b,m,128) = x_i Wa
-        gf = self._fx(pm, "conv1", gather=(idx, qm, -1.0))  # (b,m,16,128)
+        # conv1 with the gather fused into its operand load (relu(conv0) is never materialised), then the weight net +
+        # transposed product.  PackedLinear also offers both in ONE kernel (weightnet=...); on B200 the two-kernel form
+        # is faster (the fused epilogue competes with the MMAs for shared-memory bandwidth), so it is the default here.
         ww, bw = P["wconv0"]
-        H = O.weightnet_aggregate(coarse, idx, gf, ww, bw, 1.0 / math.sqrt(1.0 + BN_EPS))  # (b,m,2048)
+        if self.fuse_weightnet:
+            H = self._fx(pm, "conv1", gather=(idx, qm, -1.0), weightnet=(coarse, ww, bw, 1.0 / math.sqrt(1.0 + BN_EPS)))
+        else:
+            gf = self._fx(pm, "conv1", gather=(idx, qm, -1.0))  # (b,m,16,128)
+            H = O.weightnet_aggregate(coarse, idx, gf, ww, bw, 1.0 / math.sqrt(1.0 + BN_EPS))  # (b,m,2048)
         # skip connection: max over the group commutes with the centre shift
         self.ops.group_max(xf, idx, out=mxz[..., 0:132])
         mxz[..., 132:135].copy_(coarse)

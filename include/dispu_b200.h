@@ -211,7 +211,14 @@ int dispu_dense_tf32x3(long long M, int K, int N, const float *X, const void *pa
  *   - R1 / R2: residuals added AFTER the activation, Y = act(X.W + b) + R1 + R2 (tf.add at Common/ops.py:1074-1077);
  *   - batched weights: rows [i*rows_per_batch, (i+1)*rows_per_batch) multiply the packed weight at
  *     packed + i*packed_batch_stride bytes (per-cloud operands such as q.k^T and att.v of PointNonLocalCell,
- *     Common/ops.py:326-339); rows_per_batch must be a multiple of 128. */
+ *     Common/ops.py:326-339); rows_per_batch must be a multiple of 128;
+ *   - column blocks (n_blocks > 1): Y[:, j*N:(j+1)*N] = X . W_j with W_j at packed + j*packed_block_stride (after the
+ *     batch offset), one launch for an output wider than 256 columns (q.k^T: 1024 keys = 4 blocks);
+ *   - weight-net epilogue (wn_xyz != NULL; needs the gather front-end with gather_ns == 16): the layer output G is
+ *     never written; instead Y[r/16][ch*16+t] = sum_s G[16*(r/16)+s][ch] * wn[s][t] with
+ *     wn[s][t] = relu(((xyz[cloud, gather_idx[r]] - xyz[r/16]) . wn_w[:,t] + wn_b[t]) * wn_scale): conv1 of PointShuffle2
+ *     fused with weight_net_hidden and the transposed product (Common/ops.py:1055-1067).  Y is (M/16, 16*N), ldy its
+ *     row stride (0 = dense), wn_w (3,16), wn_b (16) or NULL. */
 typedef struct dispu_dense_args {
     long long M;
     int K, N;
@@ -234,6 +241,11 @@ typedef struct dispu_dense_args {
     long long ldr2;
     long long rows_per_batch;
     long long packed_batch_stride;
+    int n_blocks;                   /* > 1: column blocks, see below */
+    long long packed_block_stride;
+    const float *wn_xyz;            /* non-NULL: weight-net epilogue, see below */
+    const float *wn_w, *wn_b;
+    float wn_scale;
 } dispu_dense_args;
 int dispu_dense_tf32x3_ex(const dispu_dense_args *args, dispu_stream_t stream);
 /* Pack W[k][n] = src[k*stride_k + n*stride_n] for `batch` operands (source advances by w_batch_stride floats,

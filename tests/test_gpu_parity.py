@@ -682,8 +682,47 @@ def test_generator_fused_equals_reference_op_sequence():
         c2, f2 = g1(x)  # persistent buffers: a second call gives the same bits
         c0, f0 = Generator(device=dev, hoist=False, tc=False)(x)
         ch, fh = Generator(device=dev, fused=False)(x)  # previous hoisted formulation
+        g3 = Generator(device=dev)
+        g3.fuse_weightnet = True  # conv1 + weight net + transposed product in one kernel
+        cw, fw = g3(x)
     assert torch.equal(c1, c2) and torch.equal(f1, f2)
-    for a, bb in ((c1, c0), (f1, f0), (c1, ch), (f1, fh)):
+    for a, bb in ((c1, c0), (f1, f0), (c1, ch), (f1, fh), (c1, cw), (f1, fw)):
         err = (a - bb).abs()
         assert float(err.median()) < 1e-5
         assert float((err > 1e-3).float().mean()) < 0.02
+
+
+def test_dense_ex_column_blocks_and_weightnet_epilogue(rng):
+    """(1) n_blocks: one launch for q.k^T with 512 keys = 2 column blocks of 256, per-cloud operands;
+    (2) weight-net epilogue: conv1 + weight_net_hidden + transposed product (Common/ops.py:1055-1067) in one kernel
+    vs the oracle's weightnet_aggregate applied to the separately computed layer output."""
+    import dispu_b200.ops as OPS
+    from dispu_b200.dense import BatchedOperand, PackedLinear
+    b, rows_ = 3, 512
+    kv = rng.standard_normal((b, rows_, 128)).astype(np.float32)
+    q = rng.standard_normal((b, rows_, 64)).astype(np.float32)
+    nb = rows_ // 256
+    kop = BatchedOperand(b * nb, 64, 256, dev).pack(T(kv), 0, 1, 128, 256 * 128)
+    S = kop.matmul(T(q), n_blocks=nb).cpu().numpy()
+    assert S.shape == (b, rows_, rows_)
+    np.testing.assert_allclose(S, np.einsum("bik,bjk->bij", q.astype(np.float64), kv[..., :64].astype(np.float64)), rtol=1e-5, atol=1e-4)
+    # weight-net epilogue
+    b, m, ns, K, N = 2, 192, 16, 128, 128
+    xyz = unit_ball(rng, b, m)
+    _, idx = O.knn(ns, xyz, xyz)
+    Pm = rng.standard_normal((b, m, K)).astype(np.float32)
+    Q = rng.standard_normal((b, m, K)).astype(np.float32)
+    w = (rng.standard_normal((K, N)) / np.sqrt(K)).astype(np.float32)
+    bias = (rng.standard_normal(N) / 4).astype(np.float32)
+    Ww = rng.standard_normal((3, 16)).astype(np.float32)
+    bw = (rng.standard_normal(16) / 4).astype(np.float32)
+    sc = float(1.0 / np.sqrt(1.0 + 1e-3))
+    lin = PackedLinear(T(w), T(bias))
+    Gt = lin(T(Pm), relu=True, gather=(T(idx), T(Q), -1.0))  # (b,m,16,N): the unfused layer output
+    want = O.weightnet_aggregate(xyz, idx, Gt.cpu().numpy(), Ww, bw, sc)
+    got = lin(T(Pm), relu=True, gather=(T(idx), T(Q), -1.0), weightnet=(T(xyz), T(Ww), T(bw), sc))
+    assert got.shape == (b, m, N * 16)
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-5, atol=2e-5)
+    # and it matches the standalone aggregation kernel on the same G
+    sep = OPS.weightnet_aggregate(T(xyz), T(idx), Gt, T(Ww), T(bw), sc)
+    np.testing.assert_allclose(got.cpu().numpy(), sep.cpu().numpy(), rtol=1e-6, atol=1e-6)
