@@ -46,6 +46,8 @@ SIGNATURES = {
     "dispu_group_affine_relu": ([_i, _i, _i, _i, _i, _p, _p, C.c_float, _p, _p, _p], _i),
     "dispu_selection_sort": ([_i, _i, _i, _i, _p, _p, _p, _p], _i),
     "dispu_knn": ([_i, _i, _i, _i, _p, _p, _p, _p, _p], _i),
+    "dispu_knn_large_workspace_bytes": ([_i, _i, _i], _sz),
+    "dispu_knn_large": ([_i, _i, _i, _i, _p, _p, _p, _p, _p, _sz, _p], _i),
     "dispu_three_nn": ([_i, _i, _i, _p, _p, _p, _p, _p], _i),
     "dispu_three_interpolate": ([_i, _i, _i, _i, _p, _p, _p, _p, _p], _i),
     "dispu_three_interpolate_grad": ([_i, _i, _i, _i, _p, _p, _p, _p, _p], _i),
@@ -56,6 +58,8 @@ SIGNATURES = {
     "dispu_chamfer": ([_i, _i, _p, _i, _p, _p, _p, _p, _p, _sz, _p], _i),
     "dispu_repulsion_workspace_bytes": ([_i, _i], _sz),
     "dispu_repulsion_loss": ([_i, _i, _i, C.c_float, _p, _p, _p, _p, _sz, _p], _i),
+    "dispu_uniform_workspace_bytes": ([_i, _i, _i], _sz),
+    "dispu_uniform_loss_term": ([_i, _i, _i, _i, C.c_float, _p, _p, _p, _p, _sz, _p], _i),
     "dispu_dense_packed_bytes": ([_i, _i], _sz),
     "dispu_dense_pack": ([_i, _i, _p, _p, _p], _i),
     "dispu_dense_tf32x3": ([C.c_longlong, _i, _i, _p, _p, _p, _i, _p, _p], _i),

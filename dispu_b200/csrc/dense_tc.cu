@@ -154,10 +154,12 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int npad = dn_npad(N);
     const int nchunks = dn_chunks(K);
-    const uint32_t a_plane = 128u * kDnKC * 4u;  // 16 KB per plane
     const uint32_t b_plane = (uint32_t)npad * kDnKC * 4u;
-    const uint32_t stage_bytes = kResident ? 2 * a_plane : 2 * a_plane + 2 * b_plane;  // A_hi | A_lo [| B_hi | B_lo]
-    const uint32_t w_base = (uint32_t)n_stages * stage_bytes;                           // resident weights live here
+    const uint32_t stage_bytes = kResident ? 0u : 2 * b_plane;  // [B_hi | B_lo] of one K-chunk; the A operand lives in TMEM
+    const uint32_t w_base = (uint32_t)n_stages * stage_bytes;   // resident weights live here
+    // TMEM columns: accumulators at [0, 256) (two buffers of <= 128 columns, or one of 256), A-operand ring at
+    // [256, 512): stage s holds the chunk's 32 K-columns as TF32 hi at 256 + 64 s and lo at 256 + 64 s + 32
+    const int acc_bufs = npad <= 128 ? 2 : 1;
     const uint32_t smem_base = smem_u32(smem);
     constexpr int kMmaWarp = kDnProducerWarps + kDnEpiWarps;
 
@@ -188,18 +190,18 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
 
     if (warp < kDnProducerWarps) {
         // ================= producers =================
-        // Mapping: warp w owns rows 16w..16w+15 of the tile; lane l covers row 16w + (l&7) [+8] and the 16-byte K-groups
-        // (l>>3) [+4] of the chunk, i.e. one load instruction reads 8 rows x 64 contiguous bytes (8 L1 lines instead of
-        // the 32 a row-per-lane mapping touches) and the matching operand-layout stores are bank-conflict free (the 8
-        // lanes of a 128-bit phase hit 8 different rows of one core matrix).
+        // Thread (r, h): row r = tid & 127 of the tile (= TMEM lane r: tcgen05.st can only write the issuing warp's
+        // lane quarter, warp % 4) and K-columns 16h..16h+15 of the chunk.  The A operand is written STRAIGHT INTO TENSOR
+        // MEMORY (TS-form tcgen05.mma): no shared-memory A planes, no generic->async proxy fence, and the tensor core
+        // reads only the B operand from shared memory — the SS form spent most of the SM's shared-memory bandwidth
+        // re-reading A three times per K-step.
         // Flat (tile, chunk) iteration over a register ring of kDepth chunks: the raw global loads of chunk i+kDepth
-        // are issued as soon as slot i has been consumed, so kDepth chunks per thread are always in flight; the gather
-        // front-end's transform runs at CONSUME time so it never waits on a load it has just issued, and the gather
-        // index of the next tile is fetched a whole tile ahead of the row pointer that depends on it.
-        constexpr int kDepth = 2;  // 17 warps x 120 registers: two chunks per thread in flight
-        const int r0 = warp * 16 + (lane & 7);  // my two rows: r0, r0 + 8
-        const int kg = lane >> 3;               // my two K-groups: kg, kg + 4
-        const uint32_t st_off = (uint32_t)kg * 2048u + (uint32_t)(2 * warp) * 128u + (uint32_t)(lane & 7) * 16u;
+        // are issued as soon as slot i has been consumed; the gather front-end's transform runs at CONSUME time so it
+        // never waits on a load it has just issued, and the gather index of the next tile is fetched a whole tile
+        // ahead of the row pointer that depends on it.
+        constexpr int kDepth = 2;
+        const int r = tid & 127, h = tid >> 7;
+        const uint32_t tm_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 256u + (uint32_t)h * 16u;
         const bool vec = ((reinterpret_cast<uintptr_t>(X) & 15u) == 0) && (prm.ldx % 4 == 0);
         const bool qvec = ((reinterpret_cast<uintptr_t>(prm.Q) & 15u) == 0) && (prm.ldq % 4 == 0);
         const int *__restrict__ gidx = prm.gidx;
@@ -207,47 +209,43 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
         const int my_tiles = blockIdx.x < n_tiles ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
         const int total = my_tiles * nchunks;
         int ld_tile = blockIdx.x, ld_c = 0;
-        const float *xr[2] = {X, X}, *qr[2] = {nullptr, nullptr};
-        bool rvalid[2] = {false, false};
-        int idx_next[2] = {0, 0};
-        auto fetch_idx = [&](int tile, int g) -> int {  // gather index of my row g in `tile` (0 when out of range)
-            const long long row = (long long)(tile / nb) * 128 + r0 + 8 * g;
+        const float *xr = X, *qr = nullptr;
+        bool rvalid = false;
+        int idx_next = 0;
+        auto fetch_idx = [&](int tile) -> int {  // gather index of my row in `tile` (0 when out of range)
+            const long long row = (long long)(tile / nb) * 128 + r;
             return (kGather && tile < n_tiles && row < M) ? __ldg(gidx + row) : 0;
         };
-        auto enter_tile = [&](int i0, int i1) {  // row pointers of ld_tile; prefetches the indices of the tile after it
-            const int idx_cur[2] = {i0, i1};
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {
-                const long long row = (long long)(ld_tile / nb) * 128 + r0 + 8 * g;
-                rvalid[g] = ld_tile < n_tiles && row < M;
-                const long long rowc = rvalid[g] ? row : 0;
-                if (kGather) {
-                    const long long cloud = rowc / prm.g_rows_per_cloud;
-                    xr[g] = X + (cloud * prm.g_n + idx_cur[g]) * prm.ldx;
-                    qr[g] = prm.Q ? prm.Q + (rowc / prm.g_ns) * prm.ldq : nullptr;
-                    idx_next[g] = fetch_idx(ld_tile + gridDim.x, g);
-                } else {
-                    xr[g] = X + rowc * prm.ldx;
-                }
+        auto enter_tile = [&](int idx_cur) {  // row pointers of ld_tile; prefetches the index of the tile after it
+            const long long row = (long long)(ld_tile / nb) * 128 + r;
+            rvalid = ld_tile < n_tiles && row < M;
+            const long long rowc = rvalid ? row : 0;
+            if (kGather) {
+                const long long cloud = rowc / prm.g_rows_per_cloud;
+                xr = X + (cloud * prm.g_n + idx_cur) * prm.ldx;
+                qr = prm.Q ? prm.Q + (rowc / prm.g_ns) * prm.ldq : nullptr;
+                idx_next = fetch_idx(ld_tile + gridDim.x);
+            } else {
+                xr = X + rowc * prm.ldx;
             }
         };
         float4 xb[kDepth][4];
         float4 qb[kGather ? kDepth : 1][4];
         auto load_chunk = [&](float4 (&xv)[4], float4 (&qv)[4]) {  // raw loads of chunk (ld_tile, ld_c); advances the cursor
+            const int k0 = ld_c * kDnKC + h * 16;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {  // j = 2*g + kh: row r0 + 8g, K-group kg + 4kh
-                const int g = j >> 1;
-                const int k = ld_c * kDnKC + (kg + 4 * (j & 1)) * 4;
-                xv[j] = (rvalid[g] && !(prm.dbg & 1)) ? dn_load4(xr[g], k, K, vec) : make_float4(0.f, 0.f, 0.f, 0.f);
-                if (kGather) qv[j] = (rvalid[g] && qr[g]) ? dn_load4(qr[g], k, K, qvec) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < 4; ++j) {
+                const int k = k0 + j * 4;
+                xv[j] = (rvalid && !(prm.dbg & 1)) ? dn_load4(xr, k, K, vec) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (kGather) qv[j] = (rvalid && qr) ? dn_load4(qr, k, K, qvec) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
             if (++ld_c == nchunks) {
                 ld_c = 0;
                 ld_tile += gridDim.x;
-                enter_tile(idx_next[0], idx_next[1]);
+                enter_tile(idx_next);
             }
         };
-        enter_tile(fetch_idx(ld_tile, 0), fetch_idx(ld_tile, 1));
+        enter_tile(fetch_idx(ld_tile));
 #pragma unroll
         for (int d = 0; d < kDepth; ++d)
             if (d < total) load_chunk(xb[d], qb[kGather ? d : 0]);
@@ -265,46 +263,44 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
                         packed_t = packed + (long long)(tile - mt * nb) * prm.packed_block_stride;
                         if (prm.rows_per_batch > 0) packed_t += ((long long)mt * 128 / prm.rows_per_batch) * prm.packed_batch_stride;
                     }
-                    const bool trace = prm.dbg_buf && blockIdx.x == 0 && tid == 0 && it < 64;
-                    long long tq0 = 0, tq1 = 0, tq2 = 0, tq3 = 0;
-                    if (trace) tq0 = clock64();
                     mbar_wait(&s_empty[s], ph ^ 1);  // stage free (first pass: passes immediately)
-                    if (trace) tq1 = clock64();
-                    uint8_t *st = smem + (size_t)s * stage_bytes;
+                    tc_fence_after_sync();
                     if (!kResident && tid == 0 && (prm.dbg & 2)) mbar_arrive(&s_full[s]);
                     if (!kResident && tid == 0 && !(prm.dbg & 2)) {  // weight chunk: one TMA bulk copy of the pre-packed [hi | lo] planes
                         mbar_arrive_expect_tx(&s_full[s], 2u * b_plane);
-                        bulk_g2s(smem_base + (uint32_t)s * stage_bytes + 2u * a_plane, packed_t + (size_t)c * 2u * b_plane,
-                                 2u * b_plane, &s_full[s]);
+                        bulk_g2s(smem_base + (uint32_t)s * stage_bytes, packed_t + (size_t)c * 2u * b_plane, 2u * b_plane, &s_full[s]);
                     }
-                    if (!(prm.dbg & 8))
+                    if (!(prm.dbg & 8)) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float4 v = xb[d][j];
-                        if (kGather) {  // relu(x + sign*q); q is zero when there is no Q (x + sign*0 == x exactly)
-                            const float4 q = qb[kGather ? d : 0][j];
-                            v.x = fmaxf(__fmaf_rn(prm.sign, q.x, v.x), 0.f);
-                            v.y = fmaxf(__fmaf_rn(prm.sign, q.y, v.y), 0.f);
-                            v.z = fmaxf(__fmaf_rn(prm.sign, q.z, v.z), 0.f);
-                            v.w = fmaxf(__fmaf_rn(prm.sign, q.w, v.w), 0.f);
+                        for (int j2 = 0; j2 < 2; ++j2) {  // 8 columns at a time
+                            uint32_t hi8[8], lo8[8];
+#pragma unroll
+                            for (int jj = 0; jj < 2; ++jj) {
+                                float4 v = xb[d][2 * j2 + jj];
+                                if (kGather) {  // relu(x + sign*q); q is zero when there is no Q (x + sign*0 == x exactly)
+                                    const float4 q = qb[kGather ? d : 0][2 * j2 + jj];
+                                    v.x = fmaxf(__fmaf_rn(prm.sign, q.x, v.x), 0.f);
+                                    v.y = fmaxf(__fmaf_rn(prm.sign, q.y, v.y), 0.f);
+                                    v.z = fmaxf(__fmaf_rn(prm.sign, q.z, v.z), 0.f);
+                                    v.w = fmaxf(__fmaf_rn(prm.sign, q.w, v.w), 0.f);
+                                }
+                                const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    const float hh = tf32_round(vv[u]);
+                                    hi8[4 * jj + u] = __float_as_uint(hh);
+                                    // lo is rounded (not left to the tensor core's truncation): halves the error of the lo*w_hi term
+                                    lo8[4 * jj + u] = __float_as_uint(tf32_round(__fsub_rn(vv[u], hh)));
+                                }
+                            }
+                            tmem_st8(tm_row + (uint32_t)s * 64u + (uint32_t)j2 * 8u, hi8);
+                            tmem_st8(tm_row + (uint32_t)s * 64u + 32u + (uint32_t)j2 * 8u, lo8);
                         }
-                        const float4 hi = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
-                        const uint32_t o = st_off + (uint32_t)(j & 1) * 4u * 2048u + (uint32_t)(j >> 1) * 128u;
-                        *reinterpret_cast<float4 *>(st + o) = hi;
-                        // lo is rounded (not left to the tensor core's truncation): halves the error of the lo*w_hi term
-                        *reinterpret_cast<float4 *>(st + a_plane + o) =
-                            make_float4(tf32_round(__fsub_rn(v.x, hi.x)), tf32_round(__fsub_rn(v.y, hi.y)),
-                                        tf32_round(__fsub_rn(v.z, hi.z)), tf32_round(__fsub_rn(v.w, hi.w)));
+                        tmem_st_wait();  // my part of the A operand has landed in tensor memory
                     }
-                    if (trace) tq2 = clock64();
-                    if (!(prm.dbg & 16)) fence_proxy_async_smem();
+                    tc_fence_before_sync();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&s_full[s]);
-                    if (trace) {
-                        tq3 = clock64();
-                        long long *b = prm.dbg_buf + (size_t)it * 8;
-                        b[0] = tq0; b[1] = tq1; b[2] = tq2; b[3] = tq3;
-                    }
                     if (base + d + kDepth < total) load_chunk(xb[d], qb[kGather ? d : 0]);  // refill the slot just consumed
                     ++it;
                     if (++c == nchunks) { c = 0; tile += gridDim.x; }
@@ -322,39 +318,29 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
                 tc_fence_after_sync();
             }
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
-                const int a = tcount & 1;
-                const uint32_t aph = (tcount >> 1) & 1;
-                mbar_wait(&s_tempty[a], aph ^ 1);  // accumulator drained by the epilogue (first two tiles: immediate)
+                const int a = acc_bufs == 2 ? (tcount & 1) : 0;
+                const uint32_t aph = acc_bufs == 2 ? ((tcount >> 1) & 1) : (tcount & 1);
+                mbar_wait(&s_tempty[a], aph ^ 1);  // accumulator drained by the epilogue (first use: immediate)
                 tc_fence_after_sync();
-                const uint32_t d = tmem_base + (uint32_t)a * 256u;
+                const uint32_t d = tmem_base + (uint32_t)a * 128u;
                 for (int c = 0; c < nchunks; ++c, ++it) {
                     const int s = it % n_stages;
                     const uint32_t ph = (it / n_stages) & 1;
-                    const bool trace = prm.dbg_buf && blockIdx.x == 0 && it < 64;
-                    long long tm0 = 0, tm1 = 0;
-                    if (trace) tm0 = clock64();
                     mbar_wait(&s_full[s], ph);
-                    if (trace) tm1 = clock64();
                     tc_fence_after_sync();
-                    const uint32_t ah = smem_base + (uint32_t)s * stage_bytes, al = ah + a_plane;
-                    const uint32_t bh = kResident ? smem_base + w_base + (uint32_t)c * 2 * b_plane : ah + 2 * a_plane;
+                    const uint32_t ta = tmem_base + 256u + (uint32_t)s * 64u;  // A hi columns of this stage (lo at +32)
+                    const uint32_t bh = kResident ? smem_base + w_base + (uint32_t)c * 2 * b_plane : smem_base + (uint32_t)s * stage_bytes;
                     const uint32_t bl = bh + b_plane;
                     if (!(prm.dbg & 4))
 #pragma unroll
                     for (int ks = 0; ks < kDnKC / 8; ++ks) {
-                        const uint64_t dah = make_smem_desc(ah + ks * 2 * 2048u, 2048u, 128u);
-                        const uint64_t dal = make_smem_desc(al + ks * 2 * 2048u, 2048u, 128u);
                         const uint64_t dbh = make_smem_desc(bh + ks * 2 * lboB, lboB, 128u);
                         const uint64_t dbl = make_smem_desc(bl + ks * 2 * lboB, lboB, 128u);
-                        mma_tf32_ss(d, dal, dbh, idesc, (c | ks) != 0);
-                        mma_tf32_ss(d, dah, dbl, idesc, 1);
-                        mma_tf32_ss(d, dah, dbh, idesc, 1);
+                        mma_tf32_ts(d, ta + 32u + ks * 8u, dbh, idesc, (c | ks) != 0);  // a_lo * b_hi
+                        mma_tf32_ts(d, ta + ks * 8u, dbl, idesc, 1);                    // a_hi * b_lo
+                        mma_tf32_ts(d, ta + ks * 8u, dbh, idesc, 1);                    // a_hi * b_hi
                     }
                     mma_commit(&s_empty[s]);  // stage reusable once these MMAs have read it
-                    if (trace) {
-                        long long *b = prm.dbg_buf + 512 + (size_t)it * 8;
-                        b[0] = tm0; b[1] = tm1; b[2] = clock64();
-                    }
                 }
                 mma_commit(&s_tfull[a]);  // accumulator complete
             }
@@ -372,14 +358,14 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
         const bool r2vec = ((reinterpret_cast<uintptr_t>(R2) & 15u) == 0) && (prm.ldr2 % 4 == 0);
         float *stg = s_epi[ew];
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
-            const int a = tcount & 1;
-            const uint32_t aph = (tcount >> 1) & 1;
+            const int a = acc_bufs == 2 ? (tcount & 1) : 0;
+            const uint32_t aph = acc_bufs == 2 ? ((tcount >> 1) & 1) : (tcount & 1);
             mbar_wait(&s_tfull[a], aph);
             tc_fence_after_sync();
             const int mt = tile / prm.n_blocks;
             const long long row0 = (long long)mt * 128 + q * 32;  // first row of this warp's quarter
             const long long row = row0 + lane;
-            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)a * 256u;
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)a * 128u;
             float *__restrict__ Y = prm.Y + (long long)(tile - mt * prm.n_blocks) * N;  // column block of this tile
             if (prm.dbg & 64) {
             } else if (kEpi == 1) {
@@ -585,20 +571,18 @@ extern "C" int dispu_dense_tf32x3_ex(const dispu_dense_args *a, dispu_stream_t s
     DISPU_REQUIRE(n_tiles_ll <= 0x7fffffffLL, DISPU_EUNSUPPORTED);
     const int n_tiles = (int)n_tiles_ll;
     const int npad = dn_npad(N);
-    const size_t a_stage = 2 * 128 * kDnKC * 4, b_chunk = 2 * (size_t)npad * kDnKC * 4;
+    const size_t b_chunk = 2 * (size_t)npad * kDnKC * 4;
     const size_t w_all = (size_t)dn_chunks(K) * b_chunk;
-    const bool resident = !batched && n_blocks == 1 && w_all + 2 * a_stage <= (size_t)kDnSmemBudget;
-    int stages;
-    size_t smem;
-    if (resident) {
-        stages = (int)(((size_t)kDnSmemBudget - w_all) / a_stage);
+    // the A operand is staged in tensor memory (4 ring slots of 64 columns); shared memory holds only weights
+    const bool resident = !batched && n_blocks == 1 && w_all <= (size_t)kDnSmemBudget;
+    int stages = kDnMaxStages;
+    size_t smem = w_all;
+    if (!resident) {
+        stages = (int)((size_t)kDnSmemBudget / b_chunk);
         if (stages > kDnMaxStages) stages = kDnMaxStages;
-        smem = stages * a_stage + w_all;
-    } else {
-        stages = (int)((size_t)kDnSmemBudget / (a_stage + b_chunk));
-        if (stages > kDnMaxStages) stages = kDnMaxStages;
-        smem = stages * (a_stage + b_chunk);
+        smem = stages * b_chunk;
     }
+    if (smem < 1024) smem = 1024;
     int dev = 0, sms = kNumSMs;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -67,9 +67,73 @@ repulsion_finalize_kernel(int nparts, long long count, const float *__restrict__
     }
 }
 
+// One percentage term of get_uniform_loss (Common/loss_utils.py:238-269), fused after FPS + ball query:
+//     g = group_point(pcd, idx) (b,npoint,nsample,3); per group the 2-NN of every grouped point INSIDE the group
+//     (knn_point(2, g, g): the smallest is the point itself), u = sqrt(|d2 + 1e-8|),
+//     term = mean over (b,npoint,nsample) of (u - expect_len)^2 / (expect_len + 1e-8).
+// One thread per grouped point scans its group's nsample entries (padding repeats included, exactly like top_k on
+// the materialised (nsample,nsample) matrix) and keeps the two smallest squared distances.
+__global__ void __launch_bounds__(kRepThreads)
+uniform_partial_kernel(long long total, int n, int m_ns, int ns, float expect_len, const float *__restrict__ pcd,
+                       const int *__restrict__ idx, float *__restrict__ partials) {
+    __shared__ float s_red[kRepThreads / 32];
+    const long long e = (long long)blockIdx.x * kRepThreads + threadIdx.x;  // (b, j, s)
+    float acc = 0.f;
+    if (e < total) {
+        const long long cloud = e / m_ns;
+        const long long grp = e / ns;
+        const int *row = idx + grp * ns;
+        const float *c = pcd + (cloud * n + __ldg(idx + e)) * 3;
+        const float cx = __ldg(c), cy = __ldg(c + 1), cz = __ldg(c + 2);
+        const float inf = __int_as_float(0x7f800000);
+        float d0 = inf, d1 = inf;
+        for (int s = 0; s < ns; ++s) {
+            const float *q = pcd + (cloud * n + __ldg(row + s)) * 3;
+            const float gx = __fsub_rn(__ldg(q), cx), gy = __fsub_rn(__ldg(q + 1), cy), gz = __fsub_rn(__ldg(q + 2), cz);
+            float d = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
+            if (d < d0) { const float t = d0; d0 = d; d = t; }
+            if (d < d1) d1 = d;
+        }
+        if (ns < 2) d1 = 0.f;
+        const float u = __fsqrt_rn(fabsf(__fadd_rn(d1, 1e-8f)));
+        const float t = __fsub_rn(u, expect_len);
+        acc = __fdiv_rn(__fmul_rn(t, t), __fadd_rn(expect_len, 1e-8f));
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < kRepThreads / 32; ++w) t += s_red[w];
+        partials[blockIdx.x] = t;
+    }
+}
+
 }  // namespace dispu
 
 using namespace dispu;
+
+extern "C" size_t dispu_uniform_workspace_bytes(int b, int npoint, int nsample) {
+    if (b <= 0 || npoint <= 0 || nsample <= 0) return 0;
+    return sizeof(float) * (size_t)ceil_div64((long long)b * npoint * nsample, kRepThreads);
+}
+
+extern "C" int dispu_uniform_loss_term(int b, int n, int npoint, int nsample, float expect_len, const float *pcd,
+                                       const int *idx, float *out, void *workspace, size_t workspace_bytes,
+                                       dispu_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DISPU_REQUIRE(b > 0 && n > 0 && npoint > 0 && nsample > 0, DISPU_EINVAL);
+    DISPU_REQUIRE(pcd && idx && out, DISPU_ENULL);
+    DISPU_REQUIRE(workspace && workspace_bytes >= dispu_uniform_workspace_bytes(b, npoint, nsample), DISPU_EWORKSPACE);
+    const long long total = (long long)b * npoint * nsample;
+    const int nparts = (int)ceil_div64(total, kRepThreads);
+    count_launch(2);
+    uniform_partial_kernel<<<nparts, kRepThreads, 0, stream>>>(total, n, npoint * nsample, nsample, expect_len, pcd, idx,
+                                                               reinterpret_cast<float *>(workspace));
+    repulsion_finalize_kernel<<<1, 256, 0, stream>>>(nparts, total, reinterpret_cast<float *>(workspace), out);
+    return finish_launch();
+}
 
 extern "C" size_t dispu_repulsion_workspace_bytes(int b, int n) {
     if (b <= 0 || n <= 0) return 0;

@@ -70,3 +70,35 @@ def get_repulsion_loss(pred, nsample=20, radius=0.07, knn=False, use_l1=False, h
     ws = _workspace(nbytes, pred.device)
     call("dispu_repulsion_loss", b, n, nsample, float(h), ptr(pred), ptr(idx), ptr(out), ptr(ws), ws.numel(), stream_ptr())
     return out[0]
+
+
+def get_uniform_loss(pcd, percentages=(0.004, 0.006, 0.008, 0.010, 0.012), radius=1.0):
+    """loss_utils.py:238-269.  pcd (b,n,3) -> scalar tensor.  Per percentage: FPS(5 % of n) -> ball query
+    (r = sqrt(p*radius), nsample = int(n*p)) -> one fused pass for the in-group nearest-neighbour statistic
+    (no (b,npoint,nsample,3) tensor, no (nsample,nsample) distance matrices, no top_k)."""
+    import math
+    from .tf_grouping import query_ball_point
+    from .tf_sampling import farthest_point_sample, gather_point
+    pcd = req(pcd, torch.float32, 3, "pcd")
+    b, n, _ = pcd.shape
+    npoint = int(n * 0.05)
+    if npoint <= 0:
+        raise ValueError("get_uniform_loss needs at least 20 points per cloud")
+    new_xyz = gather_point(pcd, farthest_point_sample(npoint, pcd))  # the same seeds for every percentage
+    total = None
+    for p in percentages:
+        nsample = int(n * p)
+        if nsample <= 0:
+            raise ValueError("get_uniform_loss: int(n*p) must be positive")
+        r = math.sqrt(p * radius)
+        disk_area = math.pi * (radius ** 2) * p / nsample
+        expect_len = math.sqrt(disk_area)
+        idx, _ = query_ball_point(r, nsample, pcd, new_xyz)
+        out = torch.empty((2,), dtype=torch.float32, device=pcd.device)
+        nbytes = int(_lib.lib().dispu_uniform_workspace_bytes(b, npoint, nsample))
+        ws = _workspace(nbytes, pcd.device)
+        call("dispu_uniform_loss_term", b, n, npoint, nsample, float(expect_len), ptr(pcd), ptr(idx), ptr(out), ptr(ws),
+             ws.numel(), stream_ptr())
+        term = out[0] * math.pow(p * 100, 2)
+        total = term if total is None else total + term
+    return total / len(percentages)

@@ -117,7 +117,12 @@ def knn(k, xyz1, xyz2):
     m = xyz2.shape[1]
     dist = torch.empty((b, m, k), dtype=torch.float32, device=xyz1.device)
     idx = torch.empty((b, m, k), dtype=torch.int32, device=xyz1.device)
-    call("dispu_knn", b, n, m, k, ptr(xyz1), ptr(xyz2), ptr(dist), ptr(idx), stream_ptr())
+    if k > 64:  # patch extraction sizes (k = 256): radix-select kernel, scratch from the torch allocator
+        nbytes = int(_lib.lib().dispu_knn_large_workspace_bytes(b, n, m))
+        ws = _workspace(nbytes, xyz1.device)
+        call("dispu_knn_large", b, n, m, k, ptr(xyz1), ptr(xyz2), ptr(dist), ptr(idx), ptr(ws), ws.numel(), stream_ptr())
+    else:
+        call("dispu_knn", b, n, m, k, ptr(xyz1), ptr(xyz2), ptr(dist), ptr(idx), stream_ptr())
     return dist, idx
 
 

@@ -121,6 +121,14 @@ int dispu_selection_sort(int b, int n, int m, int k, const float *dist, int *out
 int dispu_knn(int b, int n, int m, int k, const float *xyz1, const float *xyz2, float *dist, int *idx,
               dispu_stream_t stream);
 
+/* The same search for large k (64 < k <= 1024): the kNN patch extraction of the inference driver (DisPU/model.py:331 ->
+ * Common/pc_util.py:83-91 extract_knn_patch, sklearn NearestNeighbors with k = patch_num_point = 256 on the host).
+ * Radix select + ordered compaction + bitonic sort per query; ascending distance, ties to the lower index.
+ * workspace: dispu_knn_large_workspace_bytes(b,n,m) bytes. */
+size_t dispu_knn_large_workspace_bytes(int b, int n, int m);
+int dispu_knn_large(int b, int n, int m, int k, const float *xyz1, const float *xyz2, float *dist, int *idx,
+                    void *workspace, size_t workspace_bytes, dispu_stream_t stream);
+
 /* ---- tf_ops/interpolation (the reference has CPU-only kernels here) --------------------- */
 
 /* ThreeNN.  threenn_cpu tf_interpolate.cpp:60-103 (op :157-187): xyz1 (b,n,3) unknown,
@@ -167,6 +175,16 @@ int dispu_chamfer(int b, int n_gt, const float *gt, int n_pred, const float *pre
 size_t dispu_repulsion_workspace_bytes(int b, int n);
 int dispu_repulsion_loss(int b, int n, int nsample, float h, const float *pred, const int *idx, float *out,
                          void *workspace, size_t workspace_bytes, dispu_stream_t stream);
+
+/* One percentage term of get_uniform_loss (Common/loss_utils.py:238-269), fused after FPS + ball query:
+ * idx (b,npoint,nsample) = QueryBallPoint(sqrt(p), nsample, pcd, gather(pcd, FPS(npoint))); per grouped point the
+ * distance u = sqrt(|d2 + 1e-8|) to its nearest other entry of the same group (knn_point(2, g, g)[:, :, 1]);
+ * out[0] = mean over (b,npoint,nsample) of (u - expect_len)^2 / (expect_len + 1e-8), out[1] = the sum.
+ * The caller scales by (100 p)^2 and averages the terms (loss_utils.py:264-268).
+ * workspace: dispu_uniform_workspace_bytes(b,npoint,nsample). */
+size_t dispu_uniform_workspace_bytes(int b, int npoint, int nsample);
+int dispu_uniform_loss_term(int b, int n, int npoint, int nsample, float expect_len, const float *pcd, const int *idx,
+                            float *out, void *workspace, size_t workspace_bytes, dispu_stream_t stream);
 
 /* ---- Common/pointnet_util.py set abstraction --------------------------------------------- */
 

@@ -654,3 +654,32 @@ int orc_weightnet_aggregate(int b, int m, int ns, int C, int T, const float *xyz
     free(wn);
     return 0;
 }
+
+/* get_uniform_loss, one percentage term — Common/loss_utils.py:238-269 given the ball-query idx
+ * (b,npoint,nsample): per group g = pcd[idx]; knn_point(2, g, g) (tf_grouping.py:116-141: unfused squared
+ * distances, top_k over ALL nsample entries so the first hit is the point itself and padding repeats count);
+ * u = sqrt(|d2 + 1e-8|); mean over (b,npoint,nsample) of (u - e)^2 / (e + 1e-8). */
+int orc_uniform_loss_term(int b, int n, int npoint, int nsample, float expect_len, const float *pcd, const int *idx,
+                          float *loss) {
+    double acc = 0.0;
+    for (int i = 0; i < b; ++i)
+        for (int j = 0; j < npoint; ++j) {
+            const int *row = idx + ((size_t)i * npoint + j) * nsample;
+            for (int s = 0; s < nsample; ++s) {
+                const float *c = pcd + ((size_t)i * n + row[s]) * 3;
+                float d0 = INFINITY, d1 = INFINITY;
+                for (int t = 0; t < nsample; ++t) {
+                    const float *q = pcd + ((size_t)i * n + row[t]) * 3;
+                    float d = d2_cpu(q[0] - c[0], q[1] - c[1], q[2] - c[2]);
+                    if (d < d0) { float tf = d0; d0 = d; d = tf; }
+                    if (d < d1) d1 = d;
+                }
+                if (nsample < 2) d1 = 0.0f;
+                float u = sqrtf(fabsf(d1 + 1e-8f));
+                float tt = u - expect_len;
+                acc += (double)((tt * tt) / (expect_len + 1e-8f));
+            }
+        }
+    *loss = (float)(acc / ((double)b * npoint * nsample));
+    return 0;
+}

@@ -308,3 +308,31 @@ def weightnet_aggregate(xyz, idx, G, Ww, bw, bn_scale):
     rc = lib().orc_weightnet_aggregate(b, m, ns, Cc, T, _p(xyz), _p(idx), _p(G), _p(Ww), _p(bw), float(bn_scale), _p(out))
     assert rc == 0, rc
     return out
+
+
+def uniform_loss_term(pcd, idx, expect_len):
+    """One percentage term of get_uniform_loss (loss_utils.py:238-269) given the ball-query idx (b,npoint,nsample)."""
+    pcd, idx = _f(pcd), _i(idx)
+    b, n, _ = pcd.shape
+    out = C.c_float()
+    lib().orc_uniform_loss_term.argtypes = [C.c_int] * 4 + [C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = lib().orc_uniform_loss_term(b, n, idx.shape[1], idx.shape[2], float(expect_len), _p(pcd), _p(idx), C.byref(out))
+    assert rc == 0, rc
+    return np.float32(out.value)
+
+
+def get_uniform_loss(pcd, percentages=(0.004, 0.006, 0.008, 0.010, 0.012), radius=1.0):
+    """loss_utils.py:238-269 composed from the oracle ops."""
+    import math
+    pcd = _f(pcd)
+    b, n, _ = pcd.shape
+    npoint = int(n * 0.05)
+    new_xyz = gather_point(pcd, farthest_point_sample(npoint, pcd))
+    tot = 0.0
+    for p in percentages:
+        nsample = int(n * p)
+        r = math.sqrt(p * radius)
+        expect_len = math.sqrt(math.pi * radius ** 2 * p / nsample)
+        idx, _ = query_ball_point(r, nsample, pcd, new_xyz)
+        tot += float(uniform_loss_term(pcd, idx, expect_len)) * math.pow(p * 100, 2)
+    return np.float32(tot / len(percentages))

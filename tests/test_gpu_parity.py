@@ -726,3 +726,83 @@ def test_dense_ex_column_blocks_and_weightnet_epilogue(rng):
     # and it matches the standalone aggregation kernel on the same G
     sep = OPS.weightnet_aggregate(T(xyz), T(idx), Gt, T(Ww), T(bw), sc)
     np.testing.assert_allclose(got.cpu().numpy(), sep.cpu().numpy(), rtol=1e-6, atol=1e-6)
+
+
+# ---------------------------------------------------------------- §8(f) next rows: uniform loss, patch pipeline, metrics
+@pytest.mark.parametrize("n,m,k", [(2048, 24, 256), (1000, 7, 65), (4096, 48, 256), (300, 5, 300), (5000, 3, 1024)])
+def test_knn_large_k_bit_exact(rng, n, m, k):
+    """dispu_knn_large (radix select) vs the oracle's kNN: indices and distances bit-exact, ties to the lower index."""
+    xyz = unit_ball(rng, 2, n)
+    q = xyz[:, :m].copy()
+    want_d, want_i = O.knn(k, xyz, q)
+    d, i = G.knn(k, T(xyz), T(q))
+    assert np.array_equal(i.cpu().numpy(), want_i)
+    assert np.array_equal(d.cpu().numpy(), want_d)
+
+
+def test_knn_large_k_ties(rng):
+    xyz = lattice(rng, 1, 3000, q=5)  # thousands of exactly equal distances across the selection threshold
+    q = xyz[:, :16].copy()
+    want_d, want_i = O.knn(256, xyz, q)
+    d, i = G.knn(256, T(xyz), T(q))
+    assert np.array_equal(i.cpu().numpy(), want_i)
+    assert np.array_equal(d.cpu().numpy(), want_d)
+
+
+@pytest.mark.parametrize("b,n", [(2, 1024), (1, 4096)])
+def test_uniform_loss(rng, b, n):
+    """get_uniform_loss (loss_utils.py:238-269): FPS + ball query + fused in-group 2-NN statistic vs the oracle."""
+    pcd = unit_ball(rng, b, n)
+    want = O.get_uniform_loss(pcd)
+    got = float(LU.get_uniform_loss(T(pcd)))
+    assert abs(got - float(want)) <= 1e-5 * max(1.0, abs(float(want)))
+
+
+def test_inference_patch_pipeline(rng):
+    """Model.pc_prediction / Model.test (DisPU/model.py:315-381) batched on the device: seeds and patches equal the
+    oracle's FPS / kNN, the output has N*ratio distinct points and is reproducible bit for bit."""
+    from dispu_b200 import inference as INF
+    from dispu_b200.generator import Generator
+    n = 2048
+    pc = unit_ball(rng, 1, n)[0]
+    pc = (pc / np.linalg.norm(pc, axis=1, keepdims=True)).astype(np.float32)  # a sphere surface
+    tpc = T(pc)
+    gen = Generator(device=dev)
+    pcn, _, _ = INF.normalize_point_cloud(tpc)
+    patches, pred, coarse = INF.pc_prediction(gen, pcn.contiguous())
+    seed_num = int(n / 256 * 3)
+    pcn_np = pcn.cpu().numpy()
+    seeds = O.farthest_point_sample(seed_num, pcn_np[None])[0]
+    _, want_idx = O.knn(256, pcn_np[None], pcn_np[None, seeds])
+    assert patches.shape == (seed_num, 256, 3) and pred.shape == (seed_num, 1024, 3) and coarse.shape == pred.shape
+    assert np.array_equal(patches.cpu().numpy(), pcn_np[want_idx[0]])
+    out = INF.upsample(gen, tpc, final_ratio=4)
+    out2 = INF.upsample(gen, tpc, final_ratio=4)
+    assert out.shape == (4 * n, 3) and torch.equal(out, out2) and bool(torch.isfinite(out).all())
+    # .xyz round trip in the reference's text format (np.savetxt '%.6f' / np.loadtxt)
+    import os
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "sphere_X4.xyz")
+        INF.save_xyz(path, out)
+        back = INF.load_xyz(path, dev)
+        assert back.shape == out.shape and float((back - out).abs().max()) <= 5.1e-7 + 1e-6 * float(out.abs().max())
+
+
+def test_evaluate_metrics(rng):
+    """evaluate.py:34-39,153-165: CD / HD of two normalised clouds vs the oracle's NnDistance."""
+    from dispu_b200 import evaluate as EV
+    gt = unit_ball(rng, 1, 4096)[0] * 3.0 + 1.5
+    pred = (gt[rng.permutation(4096)[:3000]] + rng.normal(0, 0.01, (3000, 3))).astype(np.float32)
+
+    def norm(x):
+        c = x.mean(0, keepdims=True)
+        y = x - c
+        return (y / np.sqrt((y ** 2).sum(-1, keepdims=True)).max()).astype(np.float32)
+    m = EV.chamfer_hausdorff_metric(T(pred), T(gt))
+    pn = EV.normalize_point_cloud(T(pred))[0].cpu().numpy()
+    gn = EV.normalize_point_cloud(T(gt))[0].cpu().numpy()
+    np.testing.assert_allclose(pn, norm(pred), atol=1e-6)
+    d1, _, d2, _ = O.nn_distance(pn[None], gn[None])
+    assert abs(m["CD"] - float(d1.mean() + d2.mean())) <= 1e-5 * float(d1.mean() + d2.mean()) + 1e-9
+    assert abs(m["hausdorff"] - float(d1.max() + d2.max())) <= 1e-6
