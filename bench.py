@@ -491,6 +491,8 @@ def main():
         run_reference(args, rank, world)
         return
     if world > 1:
+        # stdout carries exactly ONE JSON line: NCCL's own banner / debug output (NCCL_DEBUG=VERSION|INFO) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
