@@ -30,7 +30,7 @@ constexpr int kDnMaxStages = 4;
 constexpr int kDnProducerWarps = 8;
 constexpr int kDnEpiWarps = 8;      // two per TMEM lane quarter, alternating 16-column blocks
 constexpr int kDnThreads = (kDnProducerWarps + kDnEpiWarps + 1) * 32;  // producers | epilogue | MMA issuer
-constexpr int kDnSmemBudget = 196 * 1024;  // + <= 29 KB static (epilogue staging, weight-net rows, bias, barriers) <= 227 KB
+constexpr int kDnSmemBudget = 192 * 1024;  // + <= 29 KB static (epilogue staging, weight-net rows, bias, barriers) <= 227 KB
 
 __host__ __device__ __forceinline__ int dn_npad(int N) { return (N + 15) & ~15; }
 __host__ __device__ __forceinline__ int dn_chunks(int K) { return (K + kDnKC - 1) / kDnKC; }
@@ -41,14 +41,16 @@ __host__ __device__ __forceinline__ size_t dn_chunk_bytes(int N) { return (size_
 // layout, zero padded in K and N.  blockIdx.y = batch (source and destination advance by their batch strides).
 __global__ void __launch_bounds__(256)
 dense_pack_kernel(int K, int N, const float *__restrict__ W, long long sk, long long sn, long long w_batch_stride,
-                  uint8_t *__restrict__ packed, long long packed_batch_stride) {
+                  uint8_t *__restrict__ packed, long long packed_batch_stride, int parts) {
     const int npad = dn_npad(N);
-    const int chunk = blockIdx.x;
+    const int per_chunk = npad * kDnKC;
+    const int chunk = blockIdx.x / parts;  // `parts` CTAs share one K-chunk
+    const int part = blockIdx.x - chunk * parts;
     W += (long long)blockIdx.y * w_batch_stride;
     uint8_t *hi = packed + (long long)blockIdx.y * packed_batch_stride + (size_t)chunk * dn_chunk_bytes(N);
     uint8_t *lo = hi + (size_t)npad * kDnKC * 4;
     const bool k_fast = sk < sn;  // walk the contiguous source axis with consecutive threads
-    for (int e = threadIdx.x; e < npad * kDnKC; e += 256) {
+    for (int e = part * 256 + threadIdx.x; e < per_chunk; e += 256 * parts) {
         int kk, nn;
         if (k_fast) { nn = e / kDnKC; kk = e - nn * kDnKC; }
         else { kk = e / npad; nn = e - kk * npad; }
@@ -103,11 +105,18 @@ struct DenseParams {
     int dbg;  // development only (DISPU_DENSE_DBG): 1 = no A loads, 2 = no weight TMA, 4 = no MMA issue; results are garbage
 };
 
-// four consecutive floats k..k+3 of a row (zero beyond K)
+// four consecutive floats k..k+3 of a row (zero beyond K).  kWide: the vector path asks L2 for the whole 256-byte
+// block — a streamed row's next K-chunk sits in the same block, so it is already L2-resident when the ring reaches it
+// (not used for gathered rows, whose table lives in L2 anyway).
+template <bool kWide = false>
 __device__ __forceinline__ float4 dn_load4(const float *__restrict__ row, int k, int K, bool vec) {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (vec && k + 3 < K) {
-        v = __ldg(reinterpret_cast<const float4 *>(row + k));
+        if (kWide) {
+            asm("ld.global.nc.L2::256B.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(row + k));
+        } else {
+            v = __ldg(reinterpret_cast<const float4 *>(row + k));
+        }
     } else {
         if (k < K) v.x = __ldg(row + k);
         if (k + 1 < K) v.y = __ldg(row + k + 1);
@@ -146,7 +155,7 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t s_full[kDnMaxStages], s_empty[kDnMaxStages], s_tfull[2], s_tempty[2], s_wfull;
     __shared__ uint32_t s_tmem;
-    __shared__ __align__(16) float s_bias[256];
+    __shared__ __align__(16) float s_bias[1024];  // bias of every column block (n_blocks * N <= 1024 when a bias is given)
     __shared__ __align__(16) float s_epi[kDnEpiWarps][32 * kDnEpiStride];
     __shared__ __align__(16) float s_wn[kEpi == 1 ? 4 : 1][kEpi == 1 ? 32 * 16 : 4];  // weight-net rows of each epilogue warp
     __shared__ float s_wnw[64];                                                          // wn_w (3x16) | wn_b (16)
@@ -181,7 +190,10 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
         }
     }
     if (warp == kMmaWarp) tmem_alloc(&s_tmem, 512);
-    for (int e = tid; e < 256; e += kDnThreads) s_bias[e] = (bias && e < N) ? __ldg(bias + e) : 0.f;
+    for (int e = tid; e < 1024; e += kDnThreads) {  // block j's bias at s_bias[j*npad + col]
+        const int j = e / npad, col = e - j * npad;
+        s_bias[e] = (bias && j < prm.n_blocks && col < N) ? __ldg(bias + (size_t)j * N + col) : 0.f;
+    }
     if (kEpi == 1 && tid < 64) s_wnw[tid] = tid < 48 ? __ldg(prm.wn_w + tid) : (prm.wn_b ? __ldg(prm.wn_b + tid - 48) : 0.f);
     tc_fence_before_sync();
     __syncthreads();
@@ -209,7 +221,7 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
         const int my_tiles = blockIdx.x < n_tiles ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
         const int total = my_tiles * nchunks;
         int ld_tile = blockIdx.x, ld_c = 0;
-        const float *xr = X, *qr = nullptr;
+        const float *xr = X;
         bool rvalid = false;
         int idx_next = 0;
         auto fetch_idx = [&](int tile) -> int {  // gather index of my row in `tile` (0 when out of range)
@@ -223,32 +235,58 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
             if (kGather) {
                 const long long cloud = rowc / prm.g_rows_per_cloud;
                 xr = X + (cloud * prm.g_n + idx_cur) * prm.ldx;
-                qr = prm.Q ? prm.Q + (rowc / prm.g_ns) * prm.ldq : nullptr;
                 idx_next = fetch_idx(ld_tile + gridDim.x);
             } else {
                 xr = X + rowc * prm.ldx;
             }
         };
         float4 xb[kDepth][4];
-        float4 qb[kGather ? kDepth : 1][4];
-        auto load_chunk = [&](float4 (&xv)[4], float4 (&qv)[4]) {  // raw loads of chunk (ld_tile, ld_c); advances the cursor
+        float4 qb[4];  // the centre term of the gather front-end: ONE chunk ahead (its rows are shared by g_ns
+                       // consecutive operand rows, so these are L1/L2 hits and need no deeper ring)
+        // The register ring keeps only 2 chunks (32 KB per SM) in flight — too little to cover HBM latency — so the
+        // lines the ring will ask for LATER are pulled into L2 ahead of time with prefetch.global.L2 (no registers, no
+        // shared memory): kPf chunks ahead inside a row, and the head of my row in the next tile when a tile starts.
+        constexpr int kPf = 8;
+        auto prefetch_l2 = [&](const float *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); };
+        auto prefetch_row_head = [&](const float *rowp, int from) {  // lines from..kPf-1 of a row, split between the two halves
+            for (int cc = from + h; cc < nchunks && cc < kPf; cc += 2) prefetch_l2(rowp + cc * kDnKC);
+        };
+        auto load_q = [&](int tile_q, int c_q) {  // centre-term loads of chunk (tile_q, c_q)
+            const long long row = (long long)(tile_q / nb) * 128 + r;
+            const bool ok = kGather && prm.Q && tile_q < n_tiles && row < M;
+            const float *qrow = ok ? prm.Q + (row / prm.g_ns) * prm.ldq : prm.Q;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                qb[j] = ok ? dn_load4(qrow, c_q * kDnKC + h * 16 + j * 4, K, qvec) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        auto load_chunk = [&](float4 (&xv)[4]) {  // raw loads of chunk (ld_tile, ld_c); advances the cursor
             const int k0 = ld_c * kDnKC + h * 16;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int k = k0 + j * 4;
-                xv[j] = (rvalid && !(prm.dbg & 1)) ? dn_load4(xr, k, K, vec) : make_float4(0.f, 0.f, 0.f, 0.f);
-                if (kGather) qv[j] = (rvalid && qr) ? dn_load4(qr, k, K, qvec) : make_float4(0.f, 0.f, 0.f, 0.f);
+                xv[j] = (rvalid && !(prm.dbg & 1)) ? dn_load4<!kGather>(xr, k, K, vec) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+            if (!kGather && rvalid && ld_c + kPf < nchunks && ((ld_c + kPf) & 1) == h) prefetch_l2(xr + (ld_c + kPf) * kDnKC);
             if (++ld_c == nchunks) {
                 ld_c = 0;
                 ld_tile += gridDim.x;
                 enter_tile(idx_next);
+                if (rvalid && !kGather) {  // (a gather source is a small table that lives in L2 anyway)
+                    const long long nrow = (long long)((ld_tile + (int)gridDim.x) / nb) * 128 + r;
+                    if (ld_tile + (int)gridDim.x < n_tiles && nrow < M) prefetch_row_head(X + nrow * prm.ldx, 0);
+                }
             }
         };
         enter_tile(fetch_idx(ld_tile));
+        if (!kGather) {  // the rest of my first row and my row of this CTA's second tile
+            if (rvalid) prefetch_row_head(xr, kDepth);
+            const long long nrow = (long long)((ld_tile + (int)gridDim.x) / nb) * 128 + r;
+            if (ld_tile + (int)gridDim.x < n_tiles && nrow < M) prefetch_row_head(X + nrow * prm.ldx, 0);
+        }
 #pragma unroll
         for (int d = 0; d < kDepth; ++d)
-            if (d < total) load_chunk(xb[d], qb[kGather ? d : 0]);
+            if (d < total) load_chunk(xb[d]);
+        if (kGather) load_q(blockIdx.x, 0);
         uint32_t it = 0;  // global chunk counter -> stage / phase
         int tile = blockIdx.x, c = 0;
         const uint8_t *packed_t = packed;
@@ -263,8 +301,12 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
                         packed_t = packed + (long long)(tile - mt * nb) * prm.packed_block_stride;
                         if (prm.rows_per_batch > 0) packed_t += ((long long)mt * 128 / prm.rows_per_batch) * prm.packed_batch_stride;
                     }
+                    const bool ptrace = prm.dbg_buf && blockIdx.x == 0 && tid == 0 && it < 64;
+                    long long tq0 = 0, tq1 = 0, tq2 = 0;
+                    if (ptrace) tq0 = clock64();
                     mbar_wait(&s_empty[s], ph ^ 1);  // stage free (first pass: passes immediately)
                     tc_fence_after_sync();
+                    if (ptrace) tq1 = clock64();
                     if (!kResident && tid == 0 && (prm.dbg & 2)) mbar_arrive(&s_full[s]);
                     if (!kResident && tid == 0 && !(prm.dbg & 2)) {  // weight chunk: one TMA bulk copy of the pre-packed [hi | lo] planes
                         mbar_arrive_expect_tx(&s_full[s], 2u * b_plane);
@@ -278,7 +320,7 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
                             for (int jj = 0; jj < 2; ++jj) {
                                 float4 v = xb[d][2 * j2 + jj];
                                 if (kGather) {  // relu(x + sign*q); q is zero when there is no Q (x + sign*0 == x exactly)
-                                    const float4 q = qb[kGather ? d : 0][2 * j2 + jj];
+                                    const float4 q = qb[2 * j2 + jj];
                                     v.x = fmaxf(__fmaf_rn(prm.sign, q.x, v.x), 0.f);
                                     v.y = fmaxf(__fmaf_rn(prm.sign, q.y, v.y), 0.f);
                                     v.z = fmaxf(__fmaf_rn(prm.sign, q.z, v.z), 0.f);
@@ -296,14 +338,20 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
                             tmem_st8(tm_row + (uint32_t)s * 64u + (uint32_t)j2 * 8u, hi8);
                             tmem_st8(tm_row + (uint32_t)s * 64u + 32u + (uint32_t)j2 * 8u, lo8);
                         }
+                        if (ptrace) tq2 = clock64();
                         tmem_st_wait();  // my part of the A operand has landed in tensor memory
                     }
                     tc_fence_before_sync();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&s_full[s]);
-                    if (base + d + kDepth < total) load_chunk(xb[d], qb[kGather ? d : 0]);  // refill the slot just consumed
+                    if (ptrace) {
+                        long long *b = prm.dbg_buf + (size_t)it * 8;
+                        b[0] = tq0; b[1] = tq1; b[2] = tq2; b[3] = clock64();
+                    }
+                    if (base + d + kDepth < total) load_chunk(xb[d]);  // refill the slot just consumed
                     ++it;
                     if (++c == nchunks) { c = 0; tile += gridDim.x; }
+                    if (kGather) load_q(tile, c);  // centre term of the chunk consumed next
                 }
             }
         }
@@ -367,6 +415,7 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
             const long long row = row0 + lane;
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)a * 128u;
             float *__restrict__ Y = prm.Y + (long long)(tile - mt * prm.n_blocks) * N;  // column block of this tile
+            const float *sb = s_bias + (tile - mt * prm.n_blocks) * npad;
             if (prm.dbg & 64) {
             } else if (kEpi == 1) {
                 // ---- weight-net epilogue: this warp's 32 rows are two points x 16 samples.  Lane (p, s) first builds
@@ -401,7 +450,7 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
-                        const float4 bv = *reinterpret_cast<const float4 *>(s_bias + c0 + j);
+                        const float4 bv = *reinterpret_cast<const float4 *>(sb + c0 + j);
                         float4 o = make_float4(__fadd_rn(__uint_as_float(v[j]), bv.x), __fadd_rn(__uint_as_float(v[j + 1]), bv.y),
                                                __fadd_rn(__uint_as_float(v[j + 2]), bv.z), __fadd_rn(__uint_as_float(v[j + 3]), bv.w));
                         if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
@@ -442,17 +491,23 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
                 const int cq = lane & 3;  // float4 column inside the block
                 for (int c0 = half * 16; c0 < npad; c0 += 32) {
                     uint32_t v[32];
+                    const int eit = (int)tcount * (npad / 32) + c0 / 32;
+                    const bool trace = prm.dbg_buf && blockIdx.x == 0 && ew == 0 && lane == 0 && eit < 64;
+                    long long te0 = 0, te1 = 0, te2 = 0;
+                    if (trace) te0 = clock64();
                     tmem_ld16(trow + c0, v);
                     tmem_ld_wait();
+                    if (trace) te1 = clock64();
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
-                        const float4 bv = *reinterpret_cast<const float4 *>(s_bias + c0 + j);
+                        const float4 bv = *reinterpret_cast<const float4 *>(sb + c0 + j);
                         float4 o = make_float4(__fadd_rn(__uint_as_float(v[j]), bv.x), __fadd_rn(__uint_as_float(v[j + 1]), bv.y),
                                                __fadd_rn(__uint_as_float(v[j + 2]), bv.z), __fadd_rn(__uint_as_float(v[j + 3]), bv.w));
                         if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
                         *reinterpret_cast<float4 *>(stg + lane * kDnEpiStride + j) = o;
                     }
                     __syncwarp();
+                    if (trace) te2 = clock64();
                     const int col = c0 + cq * 4;
                     if (col < N) {
 #pragma unroll
@@ -474,6 +529,10 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
                         }
                     }
                     __syncwarp();
+                    if (trace) {
+                        long long *b = prm.dbg_buf + 1024 + (size_t)eit * 8;
+                        b[0] = te0; b[1] = te1; b[2] = te2; b[3] = clock64();
+                    }
                 }
             } else {
                 // narrow / unaligned outputs (e.g. the 3-channel coordinate layers): one row per thread, scalar stores
@@ -489,7 +548,7 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
                         for (int j = 0; j < 16; ++j) {
                             const int col = c0 + j;
                             if (col < N) {
-                                float x = __fadd_rn(__uint_as_float(v[j]), s_bias[col]);
+                                float x = __fadd_rn(__uint_as_float(v[j]), sb[col]);
                                 x = relu ? fmaxf(x, 0.f) : x;
                                 if (r1) x = __fadd_rn(x, __ldg(r1 + col));
                                 if (r2) x = __fadd_rn(x, __ldg(r2 + col));
@@ -528,8 +587,11 @@ extern "C" int dispu_dense_pack_strided(int K, int N, const float *W, long long 
     DISPU_REQUIRE(batch == 1 || packed_batch_stride >= (long long)dispu_dense_packed_bytes(K, N), DISPU_EINVAL);
     DISPU_REQUIRE(packed_batch_stride % 16 == 0, DISPU_EINVAL);
     count_launch();
-    dense_pack_kernel<<<dim3(dn_chunks(K), batch), 256, 0, (cudaStream_t)stream>>>(
-        K, N, W, stride_k, stride_n, w_batch_stride, reinterpret_cast<uint8_t *>(packed), packed_batch_stride);
+    // a few CTAs per chunk so even a two-chunk operand fills the machine
+    int parts = (dn_npad(N) * kDnKC + 1023) / 1024;
+    if (parts > 8) parts = 8;
+    dense_pack_kernel<<<dim3(dn_chunks(K) * parts, batch), 256, 0, (cudaStream_t)stream>>>(
+        K, N, W, stride_k, stride_n, w_batch_stride, reinterpret_cast<uint8_t *>(packed), packed_batch_stride, parts);
     return finish_launch();
 }
 
@@ -561,6 +623,7 @@ extern "C" int dispu_dense_tf32x3_ex(const dispu_dense_args *a, dispu_stream_t s
     const int n_blocks = a->n_blocks > 0 ? a->n_blocks : 1;
     const bool wnet = a->wn_xyz != nullptr;
     if (n_blocks > 1) DISPU_REQUIRE(a->packed_block_stride % 16 == 0 && ldy >= (long long)n_blocks * N, DISPU_EINVAL);
+    if (a->bias) DISPU_REQUIRE((long long)n_blocks * dn_npad(N) <= 1024, DISPU_EUNSUPPORTED);
     if (wnet) {
         DISPU_REQUIRE(a->gather_idx && a->wn_w, DISPU_ENULL);
         DISPU_REQUIRE(a->gather_ns == 16 && N % 32 == 0 && M % 128 == 0 && n_blocks == 1, DISPU_EUNSUPPORTED);

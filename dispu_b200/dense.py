@@ -126,3 +126,41 @@ class BatchedOperand:
         a.n_blocks, a.packed_block_stride = n_blocks, self.stride
         call("dispu_dense_tf32x3_ex", C.byref(a), stream_ptr())
         return out
+
+
+class BlockedLinear:
+    """Several layers that share their input, run as ONE launch: weights[j] (K, N) with a common N <= 256 (pad narrower
+    layers with zero columns), optional biases[j] (N,).  __call__(x (..., K)) -> (..., len(weights)*N), block j in
+    columns [j*N, (j+1)*N) — e.g. PointShuffle2's key|value, query and hoisted conv0 products of the same features."""
+
+    def __init__(self, weights, biases=None):
+        ws = [req(w, torch.float32, 2, "weight") for w in weights]
+        self.nb = len(ws)
+        self.K, self.N = ws[0].shape
+        if any(tuple(w.shape) != (self.K, self.N) for w in ws) or self.N > 256:
+            raise ValueError("BlockedLinear: weights must share one (K, N <= 256) shape")
+        stacked = torch.stack(ws).contiguous()
+        nb_bytes = int(_lib.lib().dispu_dense_packed_bytes(self.K, self.N))
+        self.stride = (nb_bytes + 15) // 16 * 16
+        self.packed = torch.empty((self.nb * self.stride,), dtype=torch.uint8, device=stacked.device)
+        call("dispu_dense_pack_strided", self.K, self.N, ptr(stacked), self.N, 1, self.nb, self.K * self.N, ptr(self.packed),
+             self.stride, stream_ptr())
+        self.bias = None
+        if biases is not None and any(b is not None for b in biases):
+            self.bias = torch.cat([torch.zeros((self.N,), device=stacked.device) if b is None else b.float() for b in biases]).contiguous()
+
+    def __call__(self, x, relu=False, out=None):
+        if x.shape[-1] != self.K:
+            raise ValueError(f"BlockedLinear expects last dim {self.K}")
+        a = _lib.DenseArgs()
+        xp, xm, ldx = rows(x, "x")
+        if out is None:
+            out = torch.empty((*x.shape[:-1], self.nb * self.N), dtype=torch.float32, device=x.device)
+        yp, ym, ldy = rows(out, "out")
+        if ym != xm or out.shape[-1] != self.nb * self.N:
+            raise ValueError("BlockedLinear: out shape mismatch")
+        a.M, a.K, a.N, a.X, a.ldx = xm, self.K, self.N, xp, ldx
+        a.packed, a.bias, a.relu, a.Y, a.ldy = ptr(self.packed), ptr(self.bias), 1 if relu else 0, yp, ldy
+        a.n_blocks, a.packed_block_stride = self.nb, self.stride
+        call("dispu_dense_tf32x3_ex", C.byref(a), stream_ptr())
+        return out

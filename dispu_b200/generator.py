@@ -21,6 +21,7 @@ The default backend is the CUDA one below; bench.py supplies a CPU backend for t
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 
@@ -70,7 +71,7 @@ class Generator:
         # fused: the whole forward on this library's kernels with no concat / slice / gather intermediates
         # (forward_fused); default = whenever the CUDA backend, hoisting and the tensor-core layers are all on
         self.fused = fused
-        self.fuse_weightnet = False
+        self.fuse_weightnet = os.environ.get("DISPU_FUSE_WEIGHTNET", "0") == "1"
         self._bufs = {}
         self._packed = {}
         self.hoist = hoist  # use the fused / hoisted grouped-layer formulation when the backend offers it
@@ -319,18 +320,30 @@ class Generator:
         # ---- PointShuffle2 (ops.py:1012-1087)
         idx = self.ops.knn3d(16, coarse, coarse)
         # non-local cell (PointNonLocalCell ops.py:302-346): q.k^T and att.v as batched tcgen05 products
-        kv = self._fx(coarse_feat, "nl_kv", act=False)       # (b,m,128): key | value
-        q = self._fx(coarse_feat, "_f_query", act=False)     # (b,m,64), pre-scaled by 1/sqrt(64)
+        # key|value and query share their input [0 | xyz | coarse_feat]: ONE launch, two 128-column blocks (the 4 xyz
+        # columns get zero weights, the query is zero-padded to 128).  The hoisted conv0 product pm keeps its own dense
+        # (b,m,128) tensor: conv1 gathers its rows 16x each and a compact table stays L2-resident.
+        blk = self._packed.get("_f_kvq")
+        if blk is None:
+            from .dense import BlockedLinear
+            wkv, bkv = P["nl_kv"]
+            wq, bq = P["_f_query"]
+            z4 = torch.zeros((4, 128), device=dev)
+            wq128 = torch.cat([wq, torch.zeros((wq.shape[0], 64), device=dev)], dim=1)
+            bq128 = torch.cat([bq, torch.zeros((64,), device=dev)])
+            blk = self._packed["_f_kvq"] = BlockedLinear([torch.cat([z4, wkv]), torch.cat([z4, wq128])], [bkv, bq128])
+        kvq = blk(xf)                  # (b,m,256): key | value | query (pre-scaled by 1/sqrt(64)) | 0
+        q = kvq[..., 128:192]
+        pm = self._fx(xf, "_f_psp", act=False)  # (b,m,128) = x_j(Wa+Wb) + f_j Wc + b
         nb = m // 256
         if m % 256:
             raise ValueError("forward_fused: 4*n must be a multiple of 256")
-        kop = BatchedOperand(b * nb, 64, 256, dev).pack(kv, 0, 1, 128, 256 * 128)
+        kop = BatchedOperand(b * nb, 64, 256, dev).pack(kvq, 0, 1, 256, 256 * 256)
         att = kop.matmul(q, n_blocks=nb)  # (b,m,m), one launch: column block j = keys [256j, 256j+256)
         att = torch.softmax(att, dim=-1)
-        vop = BatchedOperand(b, m, 64, dev).pack(kv, 64, 128, 1, m * 128)
+        vop = BatchedOperand(b, m, 64, dev).pack(kvq, 64, 256, 1, m * 256)
         nonlocal_pt = self._fx(vop.matmul(att), "nl_back")
         # local cell: conv0 hoisted to per-point products, gathered + ReLU'd inside conv1's operand load
-        pm = self._fx(xf, "_f_psp", act=False)       # (b,m,128) = x_j(Wa+Wb) + f_j Wc + b
         qm = self._fx(coarse, "_f_psq", act=False)   # (b,m,128) = x_i Wa
         # conv1 with the gather fused into its operand load (relu(conv0) is never materialised), then the weight net +
         # transposed product.  PackedLinear also offers both in ONE kernel (weightnet=...); on B200 the two-kernel form

@@ -230,8 +230,9 @@ int dispu_dense_tf32x3(long long M, int K, int N, const float *X, const void *pa
  *   - batched weights: rows [i*rows_per_batch, (i+1)*rows_per_batch) multiply the packed weight at
  *     packed + i*packed_batch_stride bytes (per-cloud operands such as q.k^T and att.v of PointNonLocalCell,
  *     Common/ops.py:326-339); rows_per_batch must be a multiple of 128;
- *   - column blocks (n_blocks > 1): Y[:, j*N:(j+1)*N] = X . W_j with W_j at packed + j*packed_block_stride (after the
- *     batch offset), one launch for an output wider than 256 columns (q.k^T: 1024 keys = 4 blocks);
+ *   - column blocks (n_blocks > 1): Y[:, j*N:(j+1)*N] = act(X . W_j + bias[j*N:(j+1)*N]) with W_j at
+ *     packed + j*packed_block_stride (after the batch offset): one launch for an output wider than 256 columns
+ *     (q.k^T: 1024 keys = 4 blocks) or for several layers that share their input (n_blocks * N <= 1024 with a bias);
  *   - weight-net epilogue (wn_xyz != NULL; needs the gather front-end with gather_ns == 16): the layer output G is
  *     never written; instead Y[r/16][ch*16+t] = sum_s G[16*(r/16)+s][ch] * wn[s][t] with
  *     wn[s][t] = relu(((xyz[cloud, gather_idx[r]] - xyz[r/16]) . wn_w[:,t] + wn_b[t]) * wn_scale): conv1 of PointShuffle2

@@ -14,7 +14,7 @@ from dispu_b200 import _lib  # noqa: E402
 from dispu_b200.dense import PackedLinear  # noqa: E402
 
 dev = torch.device("cuda", 0)
-for (M, K, N) in [(32768, 2048, 256), (524288, 128, 128), (32768, 256, 256)]:
+for (M, K, N) in [(32768, 2048, 256), (524288, 128, 128), (32768, 1024, 64)]:
     x = torch.randn((M, K), device=dev)
     lin = PackedLinear(torch.randn((K, N), device=dev) / K ** 0.5, torch.zeros((N,), device=dev))
     y = torch.empty((M, N), device=dev)
@@ -27,7 +27,7 @@ for (M, K, N) in [(32768, 2048, 256), (524288, 128, 128), (32768, 256, 256)]:
     p, m, e = buf[:512].reshape(64, 8), buf[512:1024].reshape(64, 8), buf[1024:].reshape(64, 8)
     t0 = p[0, 0]
     print(f"== M{M} K{K} N{N}")
-    print("producer it: start(rel) wait_empty convert+sts fence+arrive | MMA: wait_full issue+commit | period")
+    print("producer it: start(rel) wait_empty convert+tmem_st fence+arrive | MMA: wait_full issue+commit | period")
     for i in range(0, 24):
         if p[i, 0] == 0:
             break
