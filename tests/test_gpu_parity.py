@@ -683,7 +683,7 @@ def test_generator_fused_equals_reference_op_sequence():
         c0, f0 = Generator(device=dev, hoist=False, tc=False)(x)
         ch, fh = Generator(device=dev, fused=False)(x)  # previous hoisted formulation
         g3 = Generator(device=dev)
-        g3.fuse_weightnet = True  # conv1 + weight net + transposed product in one kernel
+        g3.fuse_weightnet = not g1.fuse_weightnet  # the other form of conv1 + weight net + transposed product
         cw, fw = g3(x)
     assert torch.equal(c1, c2) and torch.equal(f1, f2)
     for a, bb in ((c1, c0), (f1, f0), (c1, ch), (f1, fh), (c1, cw), (f1, fw)):
