@@ -100,6 +100,101 @@ nn_distance_kernel(int n, int m, const float *__restrict__ xyz1, const float *__
     }
 }
 
+// ---- minimum-only search for the fused Chamfer/Hausdorff path ------------------------------------------------
+// chamfer()/hausdorff_loss() consume only the distances, so the arg-min bookkeeping (a compare and two selects per
+// pair) is dead weight there.  Candidates are staged as x / y / z arrays so that two neighbouring candidates load as
+// one 64-bit pair, and the whole distance runs on packed FP32 (sub/mul/fma .f32x2: one issue slot, two IEEE results,
+// bit-identical to d2_ref_gpu per half); the running minimum is one FMNMX per candidate.  NaN semantics of the
+// reference (candidate 0 initialises unconditionally, later NaNs never win) are kept by handling candidate 0 apart.
+typedef unsigned long long nn_f32x2;
+__device__ __forceinline__ nn_f32x2 nn_pack(float lo, float hi) {
+    nn_f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ nn_f32x2 nn_sub2(nn_f32x2 a, nn_f32x2 b) {
+    nn_f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ nn_f32x2 nn_mul2(nn_f32x2 a, nn_f32x2 b) {
+    nn_f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ nn_f32x2 nn_fma2(nn_f32x2 a, nn_f32x2 b, nn_f32x2 c) {
+    nn_f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+__global__ void __launch_bounds__(kNnThreads)
+nn_min_reduce_kernel(int n, int m, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
+                     float2 *__restrict__ partials, int chunks) {
+    __shared__ __align__(16) float s_x[kNnTile + 2], s_y[kNnTile + 2], s_z[kNnTile + 2];
+    __shared__ float s_red[2][kNnThreads / 32];
+    const int cloud = blockIdx.y, dir = blockIdx.z;
+    const int nq = dir == 0 ? n : m, nc = dir == 0 ? m : n;
+    if ((int)blockIdx.x * kNnThreads >= nq) {  // this direction has fewer query chunks
+        if (threadIdx.x == 0 && (int)blockIdx.x < chunks)
+            partials[((size_t)cloud * 2 + dir) * chunks + blockIdx.x] = make_float2(0.f, -1.f);
+        return;
+    }
+    const float *qs = (dir == 0 ? xyz1 : xyz2) + (size_t)cloud * nq * 3;
+    const float *cs = (dir == 0 ? xyz2 : xyz1) + (size_t)cloud * nc * 3;
+    const int j = blockIdx.x * kNnThreads + threadIdx.x;
+    const bool active = j < nq;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    if (active) {
+        qx = __ldg(qs + (size_t)j * 3); qy = __ldg(qs + (size_t)j * 3 + 1); qz = __ldg(qs + (size_t)j * 3 + 2);
+    }
+    const nn_f32x2 qx2 = nn_pack(qx, qx), qy2 = nn_pack(qy, qy), qz2 = nn_pack(qz, qz);
+    // candidate 0 apart (tf_nndistance_g.cu:29 initialises with it unconditionally)
+    const float d0 = d2_ref_gpu(__fsub_rn(__ldg(cs), qx), __fsub_rn(__ldg(cs + 1), qy), __fsub_rn(__ldg(cs + 2), qz));
+    float best = __int_as_float(0x7f800000);
+    for (int t0 = 0; t0 < nc; t0 += kNnTile) {
+        const int tn = min(kNnTile, nc - t0);
+        const int tn2 = (tn + 1) & ~1;  // odd tail: the last candidate is staged twice (the minimum is unchanged)
+        __syncthreads();
+        for (int e = threadIdx.x; e < tn2; e += kNnThreads) {
+            const float *p = cs + (size_t)(t0 + min(e, tn - 1)) * 3;
+            s_x[e] = __ldg(p); s_y[e] = __ldg(p + 1); s_z[e] = __ldg(p + 2);
+        }
+        __syncthreads();
+        const nn_f32x2 *x2 = reinterpret_cast<const nn_f32x2 *>(s_x), *y2 = reinterpret_cast<const nn_f32x2 *>(s_y),
+                       *z2 = reinterpret_cast<const nn_f32x2 *>(s_z);
+#pragma unroll 8
+        for (int e = 0; e < tn2 / 2; ++e) {
+            const nn_f32x2 dx = nn_sub2(x2[e], qx2), dy = nn_sub2(y2[e], qy2), dz = nn_sub2(z2[e], qz2);
+            const nn_f32x2 d = nn_fma2(dz, dz, nn_fma2(dx, dx, nn_mul2(dy, dy)));
+            float da, db;
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(da), "=f"(db) : "l"(d));
+            best = fminf(best, fminf(da, db));
+        }
+    }
+    // reference semantics: the result is d0 if d0 is NaN, else the minimum (fminf drops later NaNs, like '<' does)
+    best = (d0 != d0) ? d0 : fminf(best, d0);
+    float s = active ? best : 0.f;
+    float mx = active ? best : -1.f;  // distances are >= 0
+    s = warp_sum(s);
+    mx = warp_max(mx);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        s_red[0][warp] = s;
+        s_red[1][warp] = mx;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float ts = 0.f, tm = -1.f;
+#pragma unroll
+        for (int w = 0; w < kNnThreads / 32; ++w) {
+            ts += s_red[0][w];
+            tm = fmaxf(tm, s_red[1][w]);
+        }
+        partials[((size_t)cloud * 2 + dir) * chunks + blockIdx.x] = make_float2(ts, tm);
+    }
+}
+
 // partials (b,2,chunks) -> per_cloud (b,2) and out[4]; one CTA, fixed order.
 __global__ void __launch_bounds__(256)
 chamfer_finalize_kernel(int b, int n_gt, int n_pred, int chunks, const float2 *__restrict__ partials,
@@ -216,8 +311,7 @@ extern "C" int dispu_chamfer(int b, int n_gt, const float *gt, int n_pred, const
     float *scratch = reinterpret_cast<float *>(partials + (size_t)b * 2 * chunks);
     count_launch(2);
     // nn_distance(gt, pred): dists_forward belongs to gt (loss_utils.py:51)
-    nn_distance_kernel<true><<<dim3(chunks, b, 2), kNnThreads, 0, stream>>>(n_gt, n_pred, gt, pred, nullptr, nullptr,
-                                                                            nullptr, nullptr, partials, chunks);
+    nn_min_reduce_kernel<<<dim3(chunks, b, 2), kNnThreads, 0, stream>>>(n_gt, n_pred, gt, pred, partials, chunks);
     chamfer_finalize_kernel<<<1, 256, 0, stream>>>(b, n_gt, n_pred, chunks, partials, radius, out, per_cloud, scratch);
     return finish_launch();
 }
