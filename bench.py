@@ -461,8 +461,13 @@ def dominant_kernel_roofline(gen, d_inp, d_gt, stream, flush, reps=10):
               "all": detail}
     if name == "dense_tf32x3_kernel":
         achieved = top["flops"] / top["ms"] / 1e9
-        return {"bound": "tensor", "kernel": "dense_tf32x3_kernel (tcgen05.mma kind::tf32, 3xTF32, FP32 accumulate in TMEM)",
-                "achieved": achieved, "peak": bf16_peak, "unit": "TFLOP/s", "frac": achieved / bf16_peak, "traffic": None,
+        traffic = None  # DRAM bytes per launch from the committed ncu --set full capture of the same step
+        tp = os.path.join(ROOT, "profiles", "r01_dense_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        return {"bound": "tensor", "kernel": "dense_tf32x3_kernel (tcgen05.mma kind::tf32 TS form, 3xTF32, A operand + FP32 accumulators in TMEM)",
+                "achieved": achieved, "peak": bf16_peak, "unit": "TFLOP/s", "frac": achieved / bf16_peak, "traffic": traffic,
+                "traffic_source": "profiles/r01_dense_traffic.json (ncu dram__bytes_read+write, average over the step's dense launches)",
                 "peak_source": which + " dense bf16 burst",
                 "algorithmic_flops_per_launch": top["flops"] / top["launches"],
                 "note": "algorithmic FLOPs = 2*M*K*N of the fp32 contraction; the kernel issues 3x that on the tensor pipe at the TF32 "
