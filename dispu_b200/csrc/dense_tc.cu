@@ -329,10 +329,10 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
                                 const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                                 for (int u = 0; u < 4; ++u) {
-                                    const float hh = tf32_round(vv[u]);
+                                    const float hh = tf32_round_finite(vv[u]);
                                     hi8[4 * jj + u] = __float_as_uint(hh);
                                     // lo is rounded (not left to the tensor core's truncation): halves the error of the lo*w_hi term
-                                    lo8[4 * jj + u] = __float_as_uint(tf32_round(__fsub_rn(vv[u], hh)));
+                                    lo8[4 * jj + u] = __float_as_uint(tf32_round_finite(__fsub_rn(vv[u], hh)));
                                 }
                             }
                             tmem_st8(tm_row + (uint32_t)s * 64u + (uint32_t)j2 * 8u, hi8);
@@ -457,23 +457,28 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
                         *reinterpret_cast<float4 *>(stg + lane * kDnEpiStride + j) = o;
                     }
                     __syncwarp();
-                    float acc[4][4];
+                    // 4 channels x 4 hidden units per lane on packed FFMA2: acc2[i][h] = (t = 2h, 2h+1) of channel i
+                    unsigned long long acc2[4][2];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) acc[i][t] = 0.f;
+                    for (int i = 0; i < 4; ++i) { acc2[i][0] = 0ull; acc2[i][1] = 0ull; }
 #pragma unroll
                     for (int sI = 0; sI < 16; ++sI) {
                         const float4 g = *reinterpret_cast<const float4 *>(stg + (p * 16 + sI) * kDnEpiStride + 4 * chq);
-                        const float4 w = *reinterpret_cast<const float4 *>(wn + (p * 16 + sI) * 16 + 4 * tq);
+                        const ulonglong2 w = *reinterpret_cast<const ulonglong2 *>(wn + (p * 16 + sI) * 16 + 4 * tq);
                         const float gv[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            acc[i][0] = __fmaf_rn(gv[i], w.x, acc[i][0]);
-                            acc[i][1] = __fmaf_rn(gv[i], w.y, acc[i][1]);
-                            acc[i][2] = __fmaf_rn(gv[i], w.z, acc[i][2]);
-                            acc[i][3] = __fmaf_rn(gv[i], w.w, acc[i][3]);
+                            unsigned long long g2;
+                            asm("mov.b64 %0, {%1, %1};" : "=l"(g2) : "f"(gv[i]));
+                            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[i][0]) : "l"(g2), "l"(w.x));
+                            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[i][1]) : "l"(g2), "l"(w.y));
                         }
+                    }
+                    float acc[4][4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[i][0]), "=f"(acc[i][1]) : "l"(acc2[i][0]));
+                        asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[i][2]), "=f"(acc[i][3]) : "l"(acc2[i][1]));
                     }
                     const long long pt = row0 / 16 + p;
                     const int ch = c0 + 4 * chq;

@@ -139,6 +139,10 @@ __device__ __forceinline__ float tf32_round(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
+// Same rounding for FINITE inputs in two integer instructions (cvt.rna compiles to a compare + predicated add + mask
+// because it has to keep inf/NaN intact): add half a TF32 ulp to the magnitude bits, clear the 13 dropped bits.
+// Values within half a TF32 ulp of FLT_MAX overflow to inf, exactly as round-to-nearest does.
+__device__ __forceinline__ float tf32_round_finite(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 
 // byte offset of element (row r, column k) of a K-major operand with `rows` rows
 __host__ __device__ __forceinline__ uint32_t op_offset(int rows, int r, int k) {
