@@ -23,6 +23,7 @@ class DenseArgs(C.Structure):
         ("Q", _p), ("ldq", _ll), ("sign", C.c_float), ("R1", _p), ("ldr1", _ll), ("R2", _p), ("ldr2", _ll),
         ("rows_per_batch", _ll), ("packed_batch_stride", _ll), ("n_blocks", _i), ("packed_block_stride", _ll),
         ("wn_xyz", _p), ("wn_w", _p), ("wn_b", _p), ("wn_scale", C.c_float),
+        ("stat_out", _p), ("stat_in", _p), ("n_stat", _i),
     ]
 
 

@@ -100,6 +100,14 @@ struct DenseParams {
     // wn[s][t] = relu(((xyz[cloud, gidx[row]] - xyz[row/16]) . wn_w[:,t] + wn_b[t]) * wn_scale)
     const float *wn_xyz, *wn_w, *wn_b;
     float wn_scale;
+    // softmax over a row that spans several column blocks / launches, without a softmax pass:
+    //   stat_out: the epilogue also writes per (row, column block, warp half) the maximum of the values it stores
+    //             -> stat_out[(row * n_blocks + block) * 2 + half];
+    //   stat_in : the producers turn every operand element x of row r into exp(x - M_r), M_r = max of the n_stat partial
+    //             maxima stat_in[r * n_stat ...], and sum what they produce; the epilogue divides the row by that sum.
+    float *stat_out;
+    const float *stat_in;
+    int n_stat;
     int n_tiles, n_stages;
     long long *dbg_buf;  // development only: clock64 samples of CTA 0 (3 roles x 64 iterations x 8 slots)
     int dbg;  // development only (DISPU_DENSE_DBG): 1 = no A loads, 2 = no weight TMA, 4 = no MMA issue; results are garbage
@@ -159,6 +167,7 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
     __shared__ __align__(16) float s_epi[kDnEpiWarps][32 * kDnEpiStride];
     __shared__ __align__(16) float s_wn[kEpi == 1 ? 4 : 1][kEpi == 1 ? 32 * 16 : 4];  // weight-net rows of each epilogue warp
     __shared__ float s_wnw[64];                                                          // wn_w (3x16) | wn_b (16)
+    __shared__ float s_rsum[2][128][2];  // softmax operand mode: row sums of the two K-halves, per tile parity
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int npad = dn_npad(N);
@@ -289,6 +298,9 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
         if (kGather) load_q(blockIdx.x, 0);
         uint32_t it = 0;  // global chunk counter -> stage / phase
         int tile = blockIdx.x, c = 0;
+        float sm_ml2 = 0.f, sm_sum = 0.f;  // softmax operand mode: max * log2(e) of the row, running sum of my half of the row
+        bool sm_ok = false;
+        uint32_t ptile = 0;                // tiles this CTA has produced (parity selects the row-sum buffer)
         const uint8_t *packed_t = packed;
         for (int base = 0; base < total; base += kDepth) {
 #pragma unroll
@@ -300,6 +312,18 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
                         const int mt = tile / nb;
                         packed_t = packed + (long long)(tile - mt * nb) * prm.packed_block_stride;
                         if (prm.rows_per_batch > 0) packed_t += ((long long)mt * 128 / prm.rows_per_batch) * prm.packed_batch_stride;
+                    }
+                    if (prm.stat_in && c == 0) {  // row maximum (times log2 e) of my row of the tile consumed next
+                        const long long row = (long long)(tile / nb) * 128 + r;
+                        float mx = 0.f;
+                        sm_ok = row < M;
+                        if (sm_ok) {
+                            const float *st = prm.stat_in + row * prm.n_stat;
+                            mx = __ldg(st);
+                            for (int i = 1; i < prm.n_stat; ++i) mx = fmaxf(mx, __ldg(st + i));
+                        }
+                        sm_ml2 = __fmul_rn(mx, 1.4426950408889634f);
+                        sm_sum = 0.f;
                     }
                     const bool ptrace = prm.dbg_buf && blockIdx.x == 0 && tid == 0 && it < 64;
                     long long tq0 = 0, tq1 = 0, tq2 = 0;
@@ -326,7 +350,16 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
                                     v.z = fmaxf(__fmaf_rn(prm.sign, q.z, v.z), 0.f);
                                     v.w = fmaxf(__fmaf_rn(prm.sign, q.w, v.w), 0.f);
                                 }
-                                const float vv[4] = {v.x, v.y, v.z, v.w};
+                                float vv[4] = {v.x, v.y, v.z, v.w};
+                                if (!kGather && prm.stat_in) {  // exp(x - max) = 2^(x log2e - max log2e); rows past M stay zero
+#pragma unroll
+                                    for (int u = 0; u < 4; ++u) {
+                                        float e2;
+                                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(__fmaf_rn(vv[u], 1.4426950408889634f, -sm_ml2)));
+                                        vv[u] = sm_ok ? e2 : 0.f;
+                                        sm_sum = __fadd_rn(sm_sum, vv[u]);
+                                    }
+                                }
 #pragma unroll
                                 for (int u = 0; u < 4; ++u) {
                                     const float hh = tf32_round_finite(vv[u]);
@@ -341,6 +374,7 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
                         if (ptrace) tq2 = clock64();
                         tmem_st_wait();  // my part of the A operand has landed in tensor memory
                     }
+                    if (prm.stat_in && c == nchunks - 1) s_rsum[ptile & 1][r][h] = sm_sum;  // published by the arrive below
                     tc_fence_before_sync();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&s_full[s]);
@@ -350,7 +384,7 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
                     }
                     if (base + d + kDepth < total) load_chunk(xb[d]);  // refill the slot just consumed
                     ++it;
-                    if (++c == nchunks) { c = 0; tile += gridDim.x; }
+                    if (++c == nchunks) { c = 0; tile += gridDim.x; ++ptile; }
                     if (kGather) load_q(tile, c);  // centre term of the chunk consumed next
                 }
             }
@@ -416,6 +450,11 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)a * 128u;
             float *__restrict__ Y = prm.Y + (long long)(tile - mt * prm.n_blocks) * N;  // column block of this tile
             const float *sb = s_bias + (tile - mt * prm.n_blocks) * npad;
+            float rscale = 1.f;  // softmax operand mode: 1 / (sum of my row's exponentials), applied to the raw accumulator
+            if (prm.stat_in) {
+                const float t = __fadd_rn(s_rsum[tcount & 1][q * 32 + lane][0], s_rsum[tcount & 1][q * 32 + lane][1]);
+                rscale = t > 0.f ? __fdividef(1.f, t) : 0.f;
+            }
             if (prm.dbg & 64) {
             } else if (kEpi == 1) {
                 // ---- weight-net epilogue: this warp's 32 rows are two points x 16 samples.  Lane (p, s) first builds
@@ -494,6 +533,7 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
                 // 16-column blocks: accumulator row -> registers -> (+bias, act) -> staged in shared memory -> written
                 // back 8 rows x 64 B per store instruction (full sectors); residuals are read with the same pattern
                 const int cq = lane & 3;  // float4 column inside the block
+                float run_m = -__int_as_float(0x7f800000);  // row maximum of what this warp stores (stat_out)
                 for (int c0 = half * 16; c0 < npad; c0 += 32) {
                     uint32_t v[32];
                     const int eit = (int)tcount * (npad / 32) + c0 / 32;
@@ -506,10 +546,12 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
                         const float4 bv = *reinterpret_cast<const float4 *>(sb + c0 + j);
-                        float4 o = make_float4(__fadd_rn(__uint_as_float(v[j]), bv.x), __fadd_rn(__uint_as_float(v[j + 1]), bv.y),
-                                               __fadd_rn(__uint_as_float(v[j + 2]), bv.z), __fadd_rn(__uint_as_float(v[j + 3]), bv.w));
+                        float4 o = make_float4(__fmaf_rn(__uint_as_float(v[j]), rscale, bv.x), __fmaf_rn(__uint_as_float(v[j + 1]), rscale, bv.y),
+                                               __fmaf_rn(__uint_as_float(v[j + 2]), rscale, bv.z), __fmaf_rn(__uint_as_float(v[j + 3]), rscale, bv.w));
                         if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
                         *reinterpret_cast<float4 *>(stg + lane * kDnEpiStride + j) = o;
+                        if (prm.stat_out && c0 + j < N)  // running maximum of the columns this warp stores (N % 4 == 0 here)
+                            run_m = fmaxf(run_m, fmaxf(fmaxf(o.x, o.y), fmaxf(o.z, o.w)));
                     }
                     __syncwarp();
                     if (trace) te2 = clock64();
@@ -539,6 +581,8 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
                         b[0] = te0; b[1] = te1; b[2] = te2; b[3] = clock64();
                     }
                 }
+                if (prm.stat_out && row < M)
+                    prm.stat_out[(row * prm.n_blocks + (tile - mt * prm.n_blocks)) * 2 + half] = run_m;
             } else {
                 // narrow / unaligned outputs (e.g. the 3-channel coordinate layers): one row per thread, scalar stores
                 float *yr = Y + row * prm.ldy;
@@ -553,7 +597,7 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
                         for (int j = 0; j < 16; ++j) {
                             const int col = c0 + j;
                             if (col < N) {
-                                float x = __fadd_rn(__uint_as_float(v[j]), sb[col]);
+                                float x = __fmaf_rn(__uint_as_float(v[j]), rscale, sb[col]);
                                 x = relu ? fmaxf(x, 0.f) : x;
                                 if (r1) x = __fadd_rn(x, __ldg(r1 + col));
                                 if (r2) x = __fadd_rn(x, __ldg(r2 + col));
@@ -635,6 +679,8 @@ extern "C" int dispu_dense_tf32x3_ex(const dispu_dense_args *a, dispu_stream_t s
         DISPU_REQUIRE((a->ldy > 0 ? a->ldy : (long long)N * 16) >= (long long)N * 16 && (a->ldy % 4) == 0 &&
                           (reinterpret_cast<uintptr_t>(a->Y) & 15u) == 0, DISPU_EINVAL);
     }
+    if (a->stat_out) DISPU_REQUIRE(!wnet && N % 4 == 0 && ldy % 4 == 0 && (reinterpret_cast<uintptr_t>(a->Y) & 15u) == 0, DISPU_EUNSUPPORTED);
+    if (a->stat_in) DISPU_REQUIRE(!a->gather_idx && a->n_stat > 0 && K % 32 == 0, DISPU_EUNSUPPORTED);
     const long long n_tiles_ll = ceil_div64(M, 128) * n_blocks;
     DISPU_REQUIRE(n_tiles_ll <= 0x7fffffffLL, DISPU_EUNSUPPORTED);
     const int n_tiles = (int)n_tiles_ll;
@@ -670,6 +716,9 @@ extern "C" int dispu_dense_tf32x3_ex(const dispu_dense_args *a, dispu_stream_t s
     p.packed_batch_stride = a->packed_batch_stride;
     p.n_blocks = n_blocks; p.packed_block_stride = a->packed_block_stride;
     p.wn_xyz = a->wn_xyz; p.wn_w = a->wn_w; p.wn_b = a->wn_b; p.wn_scale = a->wn_scale;
+    p.stat_out = reinterpret_cast<float *>(a->stat_out);
+    p.stat_in = reinterpret_cast<const float *>(a->stat_in);
+    p.n_stat = a->n_stat;
     if (wnet) p.ldy = a->ldy > 0 ? a->ldy : (long long)N * 16;
     p.n_tiles = n_tiles; p.n_stages = stages;
     {

@@ -108,9 +108,11 @@ class BatchedOperand:
              batch_stride, ptr(self.packed), self.stride, stream_ptr())
         return self
 
-    def matmul(self, x, out=None, relu=False, n_blocks=1):
+    def matmul(self, x, out=None, relu=False, n_blocks=1, stats_out=None, softmax_stats=None):
         """x (B, rows, K) [row-strided ok] -> out (B, rows, n_blocks*N); rows % 128 == 0.  With n_blocks > 1 this object
-        holds B*n_blocks operands, operand (i*n_blocks + j) producing columns [j*N, (j+1)*N) of cloud i."""
+        holds B*n_blocks operands, operand (i*n_blocks + j) producing columns [j*N, (j+1)*N) of cloud i.
+        stats_out: (B, rows, 2*n_blocks) float32 tensor that receives per-row partial maxima of the written values;
+        softmax_stats: such a tensor for x — the product is then softmax(x, -1) . W without a softmax pass."""
         a = _lib.DenseArgs()
         xp, xm, ldx = rows(x, "x")
         if x.dim() != 3 or x.shape[0] * n_blocks != self.batch or x.shape[2] != self.K:
@@ -124,6 +126,14 @@ class BatchedOperand:
         a.packed, a.relu, a.Y, a.ldy = ptr(self.packed), 1 if relu else 0, yp, ldy
         a.rows_per_batch, a.packed_batch_stride = x.shape[1], n_blocks * self.stride
         a.n_blocks, a.packed_block_stride = n_blocks, self.stride
+        if stats_out is not None:
+            if not stats_out.is_contiguous() or stats_out.numel() != xm * 2 * n_blocks or stats_out.dtype != torch.float32:
+                raise ValueError("stats_out must be a contiguous float32 (B, rows, 2*n_blocks) tensor")
+            a.stat_out = ptr(stats_out)
+        if softmax_stats is not None:
+            if not softmax_stats.is_contiguous() or softmax_stats.dtype != torch.float32 or softmax_stats.numel() % xm:
+                raise ValueError("softmax_stats must be a contiguous float32 (B, rows, n_stat) tensor")
+            a.stat_in, a.n_stat = ptr(softmax_stats), softmax_stats.numel() // xm
         call("dispu_dense_tf32x3_ex", C.byref(a), stream_ptr())
         return out
 

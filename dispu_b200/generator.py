@@ -339,10 +339,14 @@ class Generator:
         if m % 256:
             raise ValueError("forward_fused: 4*n must be a multiple of 256")
         kop = BatchedOperand(b * nb, 64, 256, dev).pack(kvq, 0, 1, 256, 256 * 256)
-        att = kop.matmul(q, n_blocks=nb)  # (b,m,m), one launch: column block j = keys [256j, 256j+256)
-        att = torch.softmax(att, dim=-1)
+        # scores (b,m,m) in one launch (column block j = keys [256j, 256j+256)); its epilogue also leaves per-row
+        # partial maxima; the second product applies exp(x - max) while loading its operand, sums it, and divides in its
+        # epilogue: no softmax pass, the normalised attention matrix is never written
+        stats = torch.empty((b, m, 2 * nb), dtype=torch.float32, device=dev)
+        scores = kop.matmul(q, n_blocks=nb, stats_out=stats)
         vop = BatchedOperand(b, m, 64, dev).pack(kvq, 64, 256, 1, m * 256)
-        nonlocal_pt = self._fx(vop.matmul(att), "nl_back")
+        att_v = vop.matmul(scores, softmax_stats=stats)
+        nonlocal_pt = self._fx(att_v, "nl_back")
         # local cell: conv0 hoisted to per-point products, gathered + ReLU'd inside conv1's operand load
         qm = self._fx(coarse, "_f_psq", act=False)   # (b,m,128) = x_i Wa
         # conv1 with the gather fused into its operand load AND the weight net + transposed product fused into its epilogue:

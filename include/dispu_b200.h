@@ -233,6 +233,11 @@ int dispu_dense_tf32x3(long long M, int K, int N, const float *X, const void *pa
  *   - column blocks (n_blocks > 1): Y[:, j*N:(j+1)*N] = act(X . W_j + bias[j*N:(j+1)*N]) with W_j at
  *     packed + j*packed_block_stride (after the batch offset): one launch for an output wider than 256 columns
  *     (q.k^T: 1024 keys = 4 blocks) or for several layers that share their input (n_blocks * N <= 1024 with a bias);
+ *   - softmax without a softmax pass (PointNonLocalCell, Common/ops.py:326-339: softmax(q.k^T) . v): the launch that
+ *     writes the scores also writes, per row and per (column block, warp half), the maximum of the values it stored:
+ *     stat_out is (M, 2*n_blocks) float; the launch that consumes the scores as its X operand gets stat_in = that
+ *     array and n_stat = 2*n_blocks: its producers turn every element into exp(x - max_row) while loading and sum
+ *     them, its epilogue divides the row by the sum (K % 32 == 0).  The normalised attention matrix is never written.
  *   - weight-net epilogue (wn_xyz != NULL; needs the gather front-end with gather_ns == 16): the layer output G is
  *     never written; instead Y[r/16][ch*16+t] = sum_s G[16*(r/16)+s][ch] * wn[s][t] with
  *     wn[s][t] = relu(((xyz[cloud, gather_idx[r]] - xyz[r/16]) . wn_w[:,t] + wn_b[t]) * wn_scale): conv1 of PointShuffle2
@@ -265,6 +270,9 @@ typedef struct dispu_dense_args {
     const float *wn_xyz;            /* non-NULL: weight-net epilogue, see below */
     const float *wn_w, *wn_b;
     float wn_scale;
+    void *stat_out;                 /* softmax statistics written by the epilogue, see below */
+    const void *stat_in;            /* softmax applied to the operand rows by the producers, see below */
+    int n_stat;
 } dispu_dense_args;
 int dispu_dense_tf32x3_ex(const dispu_dense_args *args, dispu_stream_t stream);
 /* Pack W[k][n] = src[k*stride_k + n*stride_n] for `batch` operands (source advances by w_batch_stride floats,

@@ -827,3 +827,26 @@ def test_generator_two_stage_16x_fused_vs_op_sequence():
         err = (a - bb).abs()
         assert float(err.median()) < 1e-5
         assert float((err > 1e-3).float().mean()) < 0.02
+
+
+def test_dense_ex_fused_softmax(rng):
+    """softmax(q.k^T) . v with the softmax folded into the two products (statistics from the first epilogue, exp and
+    normalisation in the second launch's operand load) vs a float64 softmax; 512 keys = 2 column blocks."""
+    from dispu_b200.dense import BatchedOperand
+    b, rows_ = 2, 512
+    kv = rng.standard_normal((b, rows_, 128)).astype(np.float32)
+    q = (rng.standard_normal((b, rows_, 64)) * 0.7).astype(np.float32)
+    nb = rows_ // 256
+    tkv = T(kv)
+    kop = BatchedOperand(b * nb, 64, 256, dev).pack(tkv, 0, 1, 128, 256 * 128)
+    stats = torch.empty((b, rows_, 2 * nb), dtype=torch.float32, device=dev)
+    scores = kop.matmul(T(q), n_blocks=nb, stats_out=stats)
+    vop = BatchedOperand(b, rows_, 64, dev).pack(tkv, 64, 128, 1, rows_ * 128)
+    got = vop.matmul(scores, softmax_stats=stats).cpu().numpy()
+    S = np.einsum("bik,bjk->bij", q.astype(np.float64), kv[..., :64].astype(np.float64))
+    P = np.exp(S - S.max(-1, keepdims=True))
+    P /= P.sum(-1, keepdims=True)
+    want = P @ kv[..., 64:].astype(np.float64)
+    np.testing.assert_allclose(got, want, rtol=2e-5, atol=2e-5)
+    # the partial maxima merge to the exact row maximum
+    np.testing.assert_allclose(stats.cpu().numpy().max(-1), S.max(-1), rtol=1e-5, atol=1e-5)
