@@ -73,6 +73,7 @@ class Generator:
         self.fused = fused
         self.fuse_weightnet = os.environ.get("DISPU_FUSE_WEIGHTNET", "1") == "1"
         self._bufs = {}
+        self._dup_idx = {}
         self._packed = {}
         self.hoist = hoist  # use the fused / hoisted grouped-layer formulation when the backend offers it
         self.device = torch.device(device)
@@ -311,9 +312,15 @@ class Generator:
             O.dense_conv(prep, [P[f"layer{blk}_l{i}"] for i in range(3)], out=feat[..., lo:lo + 120])
         # ---- duplicate_up (ops.py:1152-1199): the tiled features share one product; copy r adds its grid term
         h = self._fx(feat, "_f_up1", act=False)  # (b,n,256)
-        net = torch.relu_(h.unsqueeze(1) + P["_f_grid"].view(1, self.up_ratio, 1, -1)).view(b, m, -1)
+        # relu(h[i] + grid term of copy r) is exactly the gather front-end of the next layer (operand row (r, i) =
+        # relu(h[i] + g[r])), so the tiled (b,4n,256) tensor is never built either
+        key = (b, n, str(dev))
+        if key not in self._dup_idx:
+            self._dup_idx[key] = (torch.arange(n, dtype=torch.int32, device=dev).repeat(b, self.up_ratio).contiguous().view(b, self.up_ratio, n),
+                                  P["_f_grid"].repeat(b, 1).contiguous().view(b, self.up_ratio, -1))
+        dup_idx, dup_q = self._dup_idx[key]
         coarse_feat = xf[..., 4:132]
-        self._fx(net, "up_conv2", out=coarse_feat)
+        self._fx(h, "up_conv2", gather=(dup_idx, dup_q, 1.0), out=coarse_feat.view(b, self.up_ratio, n, 128))
         # ---- coarse coordinate_regressor
         coarse = self._fx(self._fx(self._fx(coarse_feat, "coarse_fc0"), "coarse_fc1"), "coarse_fc2", act=False)
         xf[..., 1:4].copy_(coarse)
