@@ -418,7 +418,7 @@ def dominant_kernel_roofline(gen, d_inp, d_gt, stream, flush, reps=10):
         if nm == "dispu_feature_knn":
             c = int(key.split(" ")[1].split(",")[3])
             return b * n_in * (4 * c + 4 * kk)
-        if nm == "dispu_dense_conv":
+        if nm in ("dispu_dense_conv", "dispu_dense_conv_knn"):
             c = int(key.split(" ")[1].split(",")[2])
             return b * n_in * (4 * c + 4 * kk + 4 * (72 + c))
         return None

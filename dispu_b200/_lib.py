@@ -69,6 +69,7 @@ SIGNATURES = {
     "dispu_feature_knn": ([_i, _i, _i, _i, _i, _i, _p, _i, _p, _i, _p, _p, _p], _i),
     "dispu_dense_conv_workspace_bytes": ([_i, _i], _sz),
     "dispu_dense_conv": ([_i, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _sz, _p], _i),
+    "dispu_dense_conv_knn": ([_i, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _sz, _p], _i),
     "dispu_weightnet_aggregate": ([_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, C.c_float, _p, _p], _i),
     "dispu_sa_mlp": ([_i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _p], _i),
 }

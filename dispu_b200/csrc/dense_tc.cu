@@ -557,20 +557,22 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
                     if (trace) te2 = clock64();
                     const int col = c0 + cq * 4;
                     if (col < N) {
+                        // all residual loads of the block first (independent, in flight together), then add + store
+                        float4 r1v[4], r2v[4];
+#pragma unroll
+                        for (int pass = 0; pass < 4; ++pass) {
+                            const long long grow = row0 + pass * 8 + (lane >> 2);
+                            r1v[pass] = (R1 && grow < M) ? dn_load4(R1 + grow * prm.ldr1, col, N, r1vec) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            r2v[pass] = (R2 && grow < M) ? dn_load4(R2 + grow * prm.ldr2, col, N, r2vec) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
 #pragma unroll
                         for (int pass = 0; pass < 4; ++pass) {
                             const int rr = pass * 8 + (lane >> 2);
                             const long long grow = row0 + rr;
                             if (grow < M) {
                                 float4 o = *reinterpret_cast<const float4 *>(stg + rr * kDnEpiStride + cq * 4);
-                                if (R1) {
-                                    const float4 t = dn_load4(R1 + grow * prm.ldr1, col, N, r1vec);
-                                    o.x = __fadd_rn(o.x, t.x); o.y = __fadd_rn(o.y, t.y); o.z = __fadd_rn(o.z, t.z); o.w = __fadd_rn(o.w, t.w);
-                                }
-                                if (R2) {
-                                    const float4 t = dn_load4(R2 + grow * prm.ldr2, col, N, r2vec);
-                                    o.x = __fadd_rn(o.x, t.x); o.y = __fadd_rn(o.y, t.y); o.z = __fadd_rn(o.z, t.z); o.w = __fadd_rn(o.w, t.w);
-                                }
+                                if (R1) { o.x = __fadd_rn(o.x, r1v[pass].x); o.y = __fadd_rn(o.y, r1v[pass].y); o.z = __fadd_rn(o.z, r1v[pass].z); o.w = __fadd_rn(o.w, r1v[pass].w); }
+                                if (R2) { o.x = __fadd_rn(o.x, r2v[pass].x); o.y = __fadd_rn(o.y, r2v[pass].y); o.z = __fadd_rn(o.z, r2v[pass].z); o.w = __fadd_rn(o.w, r2v[pass].w); }
                                 if (!(prm.dbg & 32)) *reinterpret_cast<float4 *>(Y + grow * prm.ldy + col) = o;
                             }
                         }

@@ -22,6 +22,15 @@
 
 namespace dispu {
 
+constexpr int kEcG = 24;            // growth rate of the live generator (DisPU/generator.py:36)
+constexpr int kEcProjW = 4 * kEcG;  // pn | pc | t1 | t2
+
+// Optional tail of the feature-kNN kernel: the EdgeConv projection of the CTA's own 32 query points (see edge_proj_kernel).
+struct EcProjArgs {
+    const float *w0, *b0, *w1, *b1, *w2, *b2;
+    float *proj;  // (b*n, 96); nullptr = no projection
+};
+
 // ------------------------------------------------------------------------------------------------------------------
 // feature kNN
 constexpr int kFkWarps = 8;
@@ -36,8 +45,9 @@ __device__ __forceinline__ unsigned ord_key(float f) {
 template <int P>
 __global__ void __launch_bounds__(kFkWarps * 32)
 feature_knn_kernel(int n, int m, int c, int k, int skip, const float *__restrict__ points, int ldp,
-                   const float *__restrict__ queries, int ldq, float *__restrict__ dist, int *__restrict__ idx) {
-    extern __shared__ float fk_smem[];
+                   const float *__restrict__ queries, int ldq, float *__restrict__ dist, int *__restrict__ idx,
+                   const EcProjArgs pj) {
+    extern __shared__ __align__(16) float fk_smem[];
     constexpr int kChunk = 32 * P;
     constexpr int kStride = kChunk + 1;  // odd stride: the transposing stores are conflict-free too
     constexpr int kQ = P <= 8 ? 4 : 2;   // queries whose distances are in registers at once
@@ -161,12 +171,60 @@ feature_knn_kernel(int n, int m, int c, int k, int skip, const float *__restrict
             idx[o] = bi[u];
         }
     }
+    if (pj.proj == nullptr) return;
+    // ---- EdgeConv projection of this CTA's 32 query points (queries == points here): saves the separate projection
+    // launch of dispu_dense_conv.  Same derived weights and the same accumulation order as edge_proj_kernel.
+    __syncthreads();  // every warp is done with the staged features: reuse the region for [c][96] weights + 96 biases
+    float *s_w = fk_smem, *s_b = fk_smem + (size_t)c * kEcProjW;
+    const int tid = threadIdx.x;
+    if (tid < 2 * kEcProjW) {
+        const int o = tid % kEcProjW, l0 = tid / kEcProjW;
+        const int part = o / kEcG, oc = o - part * kEcG;
+        const float *src = part == 0 ? pj.w0 + (size_t)c * kEcG : part == 1 ? pj.w0 : part == 2 ? pj.w1 + (size_t)kEcG * kEcG
+                                                                                               : pj.w2 + (size_t)2 * kEcG * kEcG;
+        if (part == 1) {
+#pragma unroll 4
+            for (int l = l0; l < c; l += 2)
+                s_w[l * kEcProjW + o] = __fsub_rn(__ldg(src + (size_t)l * kEcG + oc), __ldg(src + (size_t)(c + l) * kEcG + oc));
+        } else {
+#pragma unroll 8
+            for (int l = l0; l < c; l += 2) s_w[l * kEcProjW + o] = __ldg(src + (size_t)l * kEcG + oc);
+        }
+        if (l0 == 0) {
+            const float *bsrc = part == 1 ? pj.b0 : part == 2 ? pj.b1 : part == 3 ? pj.b2 : nullptr;
+            s_b[o] = bsrc ? __ldg(bsrc + oc) : 0.f;
+        }
+    }
+    __syncthreads();
+    {   // thread -> (row = tid / 8 of the CTA's 32 queries, 12 of the 96 columns)
+        const int rq = tid >> 3, cg = tid & 7;
+        const int j = blockIdx.x * (kFkWarps * kFkQueriesPerWarp) + rq;
+        if (j < m) {
+            const float *f = qry + (size_t)j * ldq;
+            float acc[12];
+#pragma unroll
+            for (int o = 0; o < 12; ++o) acc[o] = s_b[cg * 12 + o];
+            const float4 *w4 = reinterpret_cast<const float4 *>(s_w) + cg * 3;
+            for (int l = 0; l < c; ++l) {
+                const float fv = __ldg(f + l);
+#pragma unroll
+                for (int q4 = 0; q4 < 3; ++q4) {
+                    const float4 w = w4[(size_t)l * (kEcProjW / 4) + q4];
+                    acc[4 * q4 + 0] = __fmaf_rn(fv, w.x, acc[4 * q4 + 0]);
+                    acc[4 * q4 + 1] = __fmaf_rn(fv, w.y, acc[4 * q4 + 1]);
+                    acc[4 * q4 + 2] = __fmaf_rn(fv, w.z, acc[4 * q4 + 2]);
+                    acc[4 * q4 + 3] = __fmaf_rn(fv, w.w, acc[4 * q4 + 3]);
+                }
+            }
+            float4 *o4 = reinterpret_cast<float4 *>(pj.proj + ((size_t)cloud * m + j) * kEcProjW + cg * 12);
+#pragma unroll
+            for (int q4 = 0; q4 < 3; ++q4) o4[q4] = make_float4(acc[4 * q4], acc[4 * q4 + 1], acc[4 * q4 + 2], acc[4 * q4 + 3]);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
 // EdgeConv dense block
-constexpr int kEcG = 24;          // growth rate of the live generator (DisPU/generator.py:36)
-constexpr int kEcProjW = 4 * kEcG;  // pn | pc | t1 | t2
 constexpr int kEcThreads = 256;
 constexpr int kEcProjRows = 64;
 
@@ -458,15 +516,26 @@ using namespace dispu;
 
 template <int P>
 static int launch_feature_knn(int b, int n, int m, int c, int k, int skip, const float *points, int ldp, const float *queries,
-                              int ldq, float *dist, int *idx, cudaStream_t stream) {
-    const size_t smem = ((size_t)c * (32 * P + 1) + 32 * P + (size_t)kFkWarps * kFkQueriesPerWarp * c) * sizeof(float);
+                              int ldq, float *dist, int *idx, cudaStream_t stream, const EcProjArgs &pj = EcProjArgs{}) {
+    size_t smem = ((size_t)c * (32 * P + 1) + 32 * P + (size_t)kFkWarps * kFkQueriesPerWarp * c) * sizeof(float);
+    const size_t smem_proj = ((size_t)c * kEcProjW + kEcProjW) * sizeof(float);
+    if (pj.proj && smem < smem_proj) smem = smem_proj;
     if (smem > 220 * 1024) return DISPU_EUNSUPPORTED;
     cudaError_t e = cudaFuncSetAttribute(feature_knn_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     count_launch();
     dim3 grid(ceil_div(m, kFkWarps * kFkQueriesPerWarp), b);
-    feature_knn_kernel<P><<<grid, kFkWarps * 32, smem, stream>>>(n, m, c, k, skip, points, ldp, queries, ldq, dist, idx);
+    feature_knn_kernel<P><<<grid, kFkWarps * 32, smem, stream>>>(n, m, c, k, skip, points, ldp, queries, ldq, dist, idx, pj);
     return finish_launch();
+}
+
+static int feature_knn_dispatch(int b, int n, int m, int c, int k, int skip, const float *points, int ldp, const float *queries,
+                                int ldq, float *dist, int *idx, cudaStream_t stream, const EcProjArgs &pj = EcProjArgs{}) {
+    // largest chunk (32*P candidates) that covers the cloud and whose transposed features fit in shared memory
+    auto fits = [&](int P) { return ((size_t)c * (32 * P + 1) + 32 * P + (size_t)kFkWarps * kFkQueriesPerWarp * c) * sizeof(float) <= 220 * 1024; };
+    if (n > 512 && fits(32)) return launch_feature_knn<32>(b, n, m, c, k, skip, points, ldp, queries, ldq, dist, idx, stream, pj);
+    if (n > 256 && fits(16)) return launch_feature_knn<16>(b, n, m, c, k, skip, points, ldp, queries, ldq, dist, idx, stream, pj);
+    return launch_feature_knn<8>(b, n, m, c, k, skip, points, ldp, queries, ldq, dist, idx, stream, pj);
 }
 
 extern "C" int dispu_feature_knn(int b, int n, int m, int c, int k, int skip, const float *points, int ldp,
@@ -477,11 +546,7 @@ extern "C" int dispu_feature_knn(int b, int n, int m, int c, int k, int skip, co
     DISPU_REQUIRE(k <= 32 && c <= 128, DISPU_EUNSUPPORTED);
     if (b == 0 || m == 0) return DISPU_OK;
     DISPU_REQUIRE(points && queries && idx, DISPU_ENULL);
-    // largest chunk (32*P candidates) that covers the cloud and whose transposed features fit in shared memory
-    auto fits = [&](int P) { return ((size_t)c * (32 * P + 1) + 32 * P + (size_t)kFkWarps * kFkQueriesPerWarp * c) * sizeof(float) <= 220 * 1024; };
-    if (n > 512 && fits(32)) return launch_feature_knn<32>(b, n, m, c, k, skip, points, ldp, queries, ldq, dist, idx, stream);
-    if (n > 256 && fits(16)) return launch_feature_knn<16>(b, n, m, c, k, skip, points, ldp, queries, ldq, dist, idx, stream);
-    return launch_feature_knn<8>(b, n, m, c, k, skip, points, ldp, queries, ldq, dist, idx, stream);
+    return feature_knn_dispatch(b, n, m, c, k, skip, points, ldp, queries, ldq, dist, idx, stream);
 }
 
 extern "C" size_t dispu_dense_conv_workspace_bytes(int b, int n) {
@@ -489,33 +554,59 @@ extern "C" size_t dispu_dense_conv_workspace_bytes(int b, int n) {
     return (size_t)b * n * kEcProjW * sizeof(float);
 }
 
-extern "C" int dispu_dense_conv(int b, int n, int c, int k, int growth, const float *feat, int ldf, const int *idx,
-                                const float *w0, const float *b0, const float *w1, const float *b1, const float *w2,
-                                const float *b2, float *out, int ldo, void *workspace, size_t workspace_bytes,
-                                dispu_stream_t stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
+static int dense_conv_impl(int b, int n, int c, int k, int growth, const float *feat, int ldf, const int *idx, int *idx_out,
+                           const float *w0, const float *b0, const float *w1, const float *b1, const float *w2, const float *b2,
+                           float *out, int ldo, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
     DISPU_REQUIRE(b >= 0 && n > 0 && c > 0 && k > 0 && growth > 0, DISPU_EINVAL);
     DISPU_REQUIRE(ldf >= c && ldo >= 3 * growth + c, DISPU_EINVAL);
     DISPU_REQUIRE(growth == kEcG && c % 4 == 0 && c <= 128 && ldf % 4 == 0 && ldo % 4 == 0, DISPU_EUNSUPPORTED);
     if (b == 0) return DISPU_OK;
-    DISPU_REQUIRE(feat && idx && w0 && w1 && w2 && out, DISPU_ENULL);
+    DISPU_REQUIRE(feat && (idx || idx_out) && w0 && w1 && w2 && out, DISPU_ENULL);
     DISPU_REQUIRE(ec_aligned16(feat) && ec_aligned16(out), DISPU_EUNSUPPORTED);
     DISPU_REQUIRE(workspace && workspace_bytes >= dispu_dense_conv_workspace_bytes(b, n) && ec_aligned16(workspace),
                   DISPU_EWORKSPACE);
     float *proj = reinterpret_cast<float *>(workspace);
     const long long rows = (long long)b * n;
-    const size_t smem = ((size_t)c * kEcProjW + kEcProjW + (size_t)kEcProjRows * (c + 1)) * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(edge_proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    count_launch(2);
-    edge_proj_kernel<<<(unsigned)ceil_div64(rows, kEcProjRows), kEcThreads, smem, stream>>>(rows, c, feat, ldf, w0, b0, w1, b1,
-                                                                                          w2, b2, proj);
+    if (idx_out) {
+        // neighbour search and projection in ONE kernel (get_edge_feature: k+1 nearest in feature space, self dropped)
+        DISPU_REQUIRE(k + 1 <= n && k + 1 <= 32, DISPU_EUNSUPPORTED);
+        EcProjArgs pj{w0, b0, w1, b1, w2, b2, proj};
+        const int rc = feature_knn_dispatch(b, n, n, c, k + 1, 1, feat, ldf, feat, ldf, nullptr, idx_out, stream, pj);
+        if (rc != DISPU_OK) return rc;
+        idx = idx_out;
+    } else {
+        const size_t smem = ((size_t)c * kEcProjW + kEcProjW + (size_t)kEcProjRows * (c + 1)) * sizeof(float);
+        cudaError_t e = cudaFuncSetAttribute(edge_proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        count_launch();
+        edge_proj_kernel<<<(unsigned)ceil_div64(rows, kEcProjRows), kEcThreads, smem, stream>>>(rows, c, feat, ldf, w0, b0, w1, b1,
+                                                                                              w2, b2, proj);
+    }
+    count_launch();
     const unsigned g2 = (unsigned)ceil_div64(rows, kEcThreads / kEcLanes);
     if (k <= 2 * kEcLanes)
         edge_mlp_max_kernel<true><<<g2, kEcThreads, 0, stream>>>(rows, n, c, k, proj, idx, w1, w2, feat, ldf, out, ldo);
     else
         edge_mlp_max_kernel<false><<<g2, kEcThreads, 0, stream>>>(rows, n, c, k, proj, idx, w1, w2, feat, ldf, out, ldo);
     return finish_launch();
+}
+
+extern "C" int dispu_dense_conv(int b, int n, int c, int k, int growth, const float *feat, int ldf, const int *idx,
+                                const float *w0, const float *b0, const float *w1, const float *b1, const float *w2,
+                                const float *b2, float *out, int ldo, void *workspace, size_t workspace_bytes,
+                                dispu_stream_t stream_) {
+    DISPU_REQUIRE(idx, DISPU_ENULL);
+    return dense_conv_impl(b, n, c, k, growth, feat, ldf, idx, nullptr, w0, b0, w1, b1, w2, b2, out, ldo, workspace, workspace_bytes,
+                           (cudaStream_t)stream_);
+}
+
+extern "C" int dispu_dense_conv_knn(int b, int n, int c, int k, int growth, const float *feat, int ldf, int *idx_out,
+                                    const float *w0, const float *b0, const float *w1, const float *b1, const float *w2,
+                                    const float *b2, float *out, int ldo, void *workspace, size_t workspace_bytes,
+                                    dispu_stream_t stream_) {
+    DISPU_REQUIRE(idx_out, DISPU_ENULL);
+    return dense_conv_impl(b, n, c, k, growth, feat, ldf, nullptr, idx_out, w0, b0, w1, b1, w2, b2, out, ldo, workspace,
+                           workspace_bytes, (cudaStream_t)stream_);
 }
 
 extern "C" int dispu_weightnet_aggregate(int b, int m, int nsample, int C, int T, const float *xyz, const int *idx,

@@ -64,8 +64,6 @@ def dense_conv(feature, weights, k=16, idx=None, out=None):
     (w0, b0), (w1, b1), (w2, b2) = weights
     b, n, c = feature.shape
     g = w0.shape[1]
-    if idx is None:
-        idx = get_edge_feature_idx(feature, k)
     fp, _, ldf = rows(feature, "feature")
     if out is None:
         out = torch.empty((b, n, 3 * g + c), dtype=torch.float32, device=feature.device)
@@ -74,8 +72,13 @@ def dense_conv(feature, weights, k=16, idx=None, out=None):
         raise ValueError("dense_conv: out must be (b,n,3g+c)")
     nbytes = int(lib().dispu_dense_conv_workspace_bytes(b, n))
     ws = tf_grouping._workspace(nbytes, feature.device)
-    call("dispu_dense_conv", b, n, c, idx.shape[2], g, fp, ldf, ptr(idx), ptr(w0), ptr(b0), ptr(w1), ptr(b1), ptr(w2),
-         ptr(b2), op, ldo, ptr(ws), ws.numel(), stream_ptr())
+    if idx is None:  # neighbour search fused with the projection (two launches for the whole block)
+        idx = torch.empty((b, n, k), dtype=torch.int32, device=feature.device)
+        call("dispu_dense_conv_knn", b, n, c, k, g, fp, ldf, ptr(idx), ptr(w0), ptr(b0), ptr(w1), ptr(b1), ptr(w2), ptr(b2),
+             op, ldo, ptr(ws), ws.numel(), stream_ptr())
+    else:
+        call("dispu_dense_conv", b, n, c, idx.shape[2], g, fp, ldf, ptr(idx), ptr(w0), ptr(b0), ptr(w1), ptr(b1), ptr(w2),
+             ptr(b2), op, ldo, ptr(ws), ws.numel(), stream_ptr())
     return out, idx
 
 

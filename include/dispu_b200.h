@@ -302,6 +302,12 @@ size_t dispu_dense_conv_workspace_bytes(int b, int n);
 int dispu_dense_conv(int b, int n, int c, int k, int growth, const float *feat, int ldf, const int *idx, const float *w0,
                      const float *b0, const float *w1, const float *b1, const float *w2, const float *b2, float *out,
                      int ldo, void *workspace, size_t workspace_bytes, dispu_stream_t stream);
+/* The same block INCLUDING get_edge_feature's neighbour search (k+1 nearest in feature space, self dropped): the kNN
+ * kernel also evaluates the centre-point projections of its own queries, so the block is two launches in total.
+ * idx_out (b,n,k) receives the neighbour indices the block used. */
+int dispu_dense_conv_knn(int b, int n, int c, int k, int growth, const float *feat, int ldf, int *idx_out, const float *w0,
+                         const float *b0, const float *w1, const float *b1, const float *w2, const float *b2, float *out,
+                         int ldo, void *workspace, size_t workspace_bytes, dispu_stream_t stream);
 
 /* Weight net + transposed product of PointShuffle2 (Common/ops.py:1062-1067, weight_net_hidden :181-191):
  *   wn[s][t]   = relu(((xyz[idx[i][s]] - xyz[i]) . Ww[:,t] + bw[t]) * bn_scale)
