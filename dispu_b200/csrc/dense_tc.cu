@@ -434,10 +434,8 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
         const int half = ew >> 2;  // which of the quarter's two warps
         uint32_t tcount = 0;
         const bool yvec = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(prm.Y) & 15u) == 0) && (prm.ldy % 4 == 0);
-        const float *__restrict__ R1 = prm.R1;
-        const float *__restrict__ R2 = prm.R2;
-        const bool r1vec = ((reinterpret_cast<uintptr_t>(R1) & 15u) == 0) && (prm.ldr1 % 4 == 0);
-        const bool r2vec = ((reinterpret_cast<uintptr_t>(R2) & 15u) == 0) && (prm.ldr2 % 4 == 0);
+        const bool r1vec = ((reinterpret_cast<uintptr_t>(prm.R1) & 15u) == 0) && (prm.ldr1 % 4 == 0) && (N % 4 == 0);
+        const bool r2vec = ((reinterpret_cast<uintptr_t>(prm.R2) & 15u) == 0) && (prm.ldr2 % 4 == 0) && (N % 4 == 0);
         float *stg = s_epi[ew];
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
             const int a = acc_bufs == 2 ? (tcount & 1) : 0;
@@ -450,6 +448,8 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)a * 128u;
             float *__restrict__ Y = prm.Y + (long long)(tile - mt * prm.n_blocks) * N;  // column block of this tile
             const float *sb = s_bias + (tile - mt * prm.n_blocks) * npad;
+            const float *__restrict__ R1 = prm.R1 ? prm.R1 + (long long)(tile - mt * prm.n_blocks) * N : nullptr;  // residuals
+            const float *__restrict__ R2 = prm.R2 ? prm.R2 + (long long)(tile - mt * prm.n_blocks) * N : nullptr;  // follow Y's block
             float rscale = 1.f;  // softmax operand mode: 1 / (sum of my row's exponentials), applied to the raw accumulator
             if (prm.stat_in) {
                 const float t = __fadd_rn(s_rsum[tcount & 1][q * 32 + lane][0], s_rsum[tcount & 1][q * 32 + lane][1]);

@@ -3,11 +3,15 @@ The weight is packed once (TF32 hi/lo planes, UMMA layout); see dispu_dense_tf32
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
 from . import _lib
 from ._t import call, ptr, req, rows, stream_ptr
+
+
+SPLIT_256 = os.environ.get("DISPU_SPLIT_256", "0") == "1"  # measured slower on B200 (A operand re-read, smaller MMAs); kept as a switch
 
 
 class PackedLinear:
@@ -27,17 +31,26 @@ class PackedLinear:
         if self.N > 256:
             raise ValueError("PackedLinear supports N <= 256")
         self.bias = None if bias is None else req(bias, torch.float32, 1, "bias")
-        nbytes = int(_lib.lib().dispu_dense_packed_bytes(self.K, self.N))
-        self.packed = torch.empty((nbytes,), dtype=torch.uint8, device=weight.device)
-        call("dispu_dense_pack", self.K, self.N, ptr(weight), ptr(self.packed), stream_ptr())
+        # Optional (DISPU_SPLIT_256=1): a 256-column layer as two 128-column blocks, so that two TMEM accumulators fit and
+        # the epilogue of one tile overlaps the MMAs of the next.  Off by default: the doubled A-operand traffic and the
+        # smaller MMAs cost more than the overlap gains on B200 (after_conv 0.30 ms vs 0.19 ms).
+        self.n_blocks = 2 if (self.N == 256 and SPLIT_256) else 1
+        nblk = self.N // self.n_blocks
+        nbytes = int(_lib.lib().dispu_dense_packed_bytes(self.K, nblk))
+        self.block_stride = (nbytes + 15) // 16 * 16
+        self.packed = torch.empty((self.n_blocks * self.block_stride,), dtype=torch.uint8, device=weight.device)
+        # block j = columns [j*nblk, (j+1)*nblk): source element (k, n) at weight[k*N + j*nblk + n]
+        call("dispu_dense_pack_strided", self.K, nblk, ptr(weight), self.N, 1, self.n_blocks, nblk, ptr(self.packed),
+             self.block_stride, stream_ptr())
 
     def __call__(self, x, relu=False, out=None, gather=None, residuals=(), weightnet=None):
         if x.shape[-1] != self.K:
             raise ValueError(f"PackedLinear expects last dim {self.K}, got {tuple(x.shape)}")
         a = _lib.DenseArgs()
         xp, xm, ldx = rows(x, "x")
-        a.K, a.N, a.X, a.ldx = self.K, self.N, xp, ldx
+        a.K, a.N, a.X, a.ldx = self.K, self.N // self.n_blocks, xp, ldx
         a.packed, a.bias, a.relu = ptr(self.packed), ptr(self.bias), 1 if relu else 0
+        a.n_blocks, a.packed_block_stride = self.n_blocks, self.block_stride
         if gather is not None:
             idx, Q, sign = gather
             idx = req(idx, torch.int32, 3, "idx")
