@@ -113,6 +113,11 @@ struct DenseParams {
     int dbg;  // development only (DISPU_DENSE_DBG): 1 = no A loads, 2 = no weight TMA, 4 = no MMA issue; results are garbage
 };
 
+// 64-bit / 64-bit division is a ~100-instruction routine on the GPU; row and tile counts almost always fit 31 bits
+__device__ __forceinline__ long long dn_div(long long a, long long b) {
+    return (((a | b) >> 31) == 0) ? (long long)((unsigned)a / (unsigned)b) : a / b;
+}
+
 // four consecutive floats k..k+3 of a row (zero beyond K).  kWide: the vector path asks L2 for the whole 256-byte
 // block — a streamed row's next K-chunk sits in the same block, so it is already L2-resident when the ring reaches it
 // (not used for gathered rows, whose table lives in L2 anyway).
@@ -234,15 +239,15 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
         bool rvalid = false;
         int idx_next = 0;
         auto fetch_idx = [&](int tile) -> int {  // gather index of my row in `tile` (0 when out of range)
-            const long long row = (long long)(tile / nb) * 128 + r;
+            const long long row = (long long)(nb == 1 ? tile : tile / nb) * 128 + r;
             return (kGather && tile < n_tiles && row < M) ? __ldg(gidx + row) : 0;
         };
         auto enter_tile = [&](int idx_cur) {  // row pointers of ld_tile; prefetches the index of the tile after it
-            const long long row = (long long)(ld_tile / nb) * 128 + r;
+            const long long row = (long long)(nb == 1 ? ld_tile : ld_tile / nb) * 128 + r;
             rvalid = ld_tile < n_tiles && row < M;
             const long long rowc = rvalid ? row : 0;
             if (kGather) {
-                const long long cloud = rowc / prm.g_rows_per_cloud;
+                const long long cloud = dn_div(rowc, prm.g_rows_per_cloud);
                 xr = X + (cloud * prm.g_n + idx_cur) * prm.ldx;
                 idx_next = fetch_idx(ld_tile + gridDim.x);
             } else {
@@ -260,13 +265,17 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
         auto prefetch_row_head = [&](const float *rowp, int from) {  // lines from..kPf-1 of a row, split between the two halves
             for (int cc = from + h; cc < nchunks && cc < kPf; cc += 2) prefetch_l2(rowp + cc * kDnKC);
         };
+        const float *q_row = prm.Q;  // centre-term row of the tile being consumed (one per tile: no division per chunk)
+        bool q_ok = false;
         auto load_q = [&](int tile_q, int c_q) {  // centre-term loads of chunk (tile_q, c_q)
-            const long long row = (long long)(tile_q / nb) * 128 + r;
-            const bool ok = kGather && prm.Q && tile_q < n_tiles && row < M;
-            const float *qrow = ok ? prm.Q + (row / prm.g_ns) * prm.ldq : prm.Q;
+            if (c_q == 0) {
+                const long long row = (long long)(nb == 1 ? tile_q : tile_q / nb) * 128 + r;
+                q_ok = kGather && prm.Q && tile_q < n_tiles && row < M;
+                q_row = q_ok ? prm.Q + dn_div(row, prm.g_ns) * prm.ldq : prm.Q;
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                qb[j] = ok ? dn_load4(qrow, c_q * kDnKC + h * 16 + j * 4, K, qvec) : make_float4(0.f, 0.f, 0.f, 0.f);
+                qb[j] = q_ok ? dn_load4(q_row, c_q * kDnKC + h * 16 + j * 4, K, qvec) : make_float4(0.f, 0.f, 0.f, 0.f);
         };
         auto load_chunk = [&](float4 (&xv)[4]) {  // raw loads of chunk (ld_tile, ld_c); advances the cursor
             const int k0 = ld_c * kDnKC + h * 16;
@@ -281,16 +290,18 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
                 ld_tile += gridDim.x;
                 enter_tile(idx_next);
                 if (rvalid && !kGather) {  // (a gather source is a small table that lives in L2 anyway)
-                    const long long nrow = (long long)((ld_tile + (int)gridDim.x) / nb) * 128 + r;
-                    if (ld_tile + (int)gridDim.x < n_tiles && nrow < M) prefetch_row_head(X + nrow * prm.ldx, 0);
+                    const int nt = ld_tile + (int)gridDim.x;
+                    const long long nrow = (long long)(nb == 1 ? nt : nt / nb) * 128 + r;
+                    if (nt < n_tiles && nrow < M) prefetch_row_head(X + nrow * prm.ldx, 0);
                 }
             }
         };
         enter_tile(fetch_idx(ld_tile));
         if (!kGather) {  // the rest of my first row and my row of this CTA's second tile
             if (rvalid) prefetch_row_head(xr, kDepth);
-            const long long nrow = (long long)((ld_tile + (int)gridDim.x) / nb) * 128 + r;
-            if (ld_tile + (int)gridDim.x < n_tiles && nrow < M) prefetch_row_head(X + nrow * prm.ldx, 0);
+            const int nt = ld_tile + (int)gridDim.x;
+            const long long nrow = (long long)(nb == 1 ? nt : nt / nb) * 128 + r;
+            if (nt < n_tiles && nrow < M) prefetch_row_head(X + nrow * prm.ldx, 0);
         }
 #pragma unroll
         for (int d = 0; d < kDepth; ++d)
@@ -309,12 +320,12 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
                     const int s = it % n_stages;
                     const uint32_t ph = (it / n_stages) & 1;
                     if (!kResident && c == 0) {
-                        const int mt = tile / nb;
+                        const int mt = nb == 1 ? tile : tile / nb;
                         packed_t = packed + (long long)(tile - mt * nb) * prm.packed_block_stride;
-                        if (prm.rows_per_batch > 0) packed_t += ((long long)mt * 128 / prm.rows_per_batch) * prm.packed_batch_stride;
+                        if (prm.rows_per_batch > 0) packed_t += dn_div((long long)mt * 128, prm.rows_per_batch) * prm.packed_batch_stride;
                     }
                     if (prm.stat_in && c == 0) {  // row maximum (times log2 e) of my row of the tile consumed next
-                        const long long row = (long long)(tile / nb) * 128 + r;
+                        const long long row = (long long)(nb == 1 ? tile : tile / nb) * 128 + r;
                         float mx = 0.f;
                         sm_ok = row < M;
                         if (sm_ok) {
@@ -442,7 +453,7 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
             const uint32_t aph = acc_bufs == 2 ? ((tcount >> 1) & 1) : (tcount & 1);
             mbar_wait(&s_tfull[a], aph);
             tc_fence_after_sync();
-            const int mt = tile / prm.n_blocks;
+            const int mt = prm.n_blocks == 1 ? tile : tile / prm.n_blocks;
             const long long row0 = (long long)mt * 128 + q * 32;  // first row of this warp's quarter
             const long long row = row0 + lane;
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)a * 128u;
@@ -464,8 +475,8 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
                 float *wn = s_wn[kEpi == 1 ? q : 0];
                 {
                     const long long rowc = row < M ? row : 0;
-                    const long long cloud = rowc / prm.g_rows_per_cloud;
-                    const float *ctr = prm.wn_xyz + (rowc / 16) * 3;
+                    const long long cloud = dn_div(rowc, prm.g_rows_per_cloud);
+                    const float *ctr = prm.wn_xyz + (rowc >> 4) * 3;
                     const float *nbp = prm.wn_xyz + (cloud * prm.g_n + __ldg(prm.gidx + rowc)) * 3;
                     const float gx = __fsub_rn(__ldg(nbp), __ldg(ctr)), gy = __fsub_rn(__ldg(nbp + 1), __ldg(ctr + 1)),
                                 gz = __fsub_rn(__ldg(nbp + 2), __ldg(ctr + 2));
@@ -519,7 +530,7 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
                         asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[i][0]), "=f"(acc[i][1]) : "l"(acc2[i][0]));
                         asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[i][2]), "=f"(acc[i][3]) : "l"(acc2[i][1]));
                     }
-                    const long long pt = row0 / 16 + p;
+                    const long long pt = (row0 >> 4) + p;
                     const int ch = c0 + 4 * chq;
                     if (row0 + p * 16 < M) {
                         float *o = prm.Y + pt * prm.ldy + (long long)ch * 16 + 4 * tq;
