@@ -65,6 +65,7 @@ SIGNATURES = {
     "dispu_dense_pack": ([_i, _i, _p, _p, _p], _i),
     "dispu_dense_tf32x3": ([C.c_longlong, _i, _i, _p, _p, _p, _i, _p, _p], _i),
     "dispu_dense_tf32x3_ex": ([C.POINTER(DenseArgs), _p], _i),
+    "dispu_dense_args_size": ([], _sz),
     "dispu_dense_pack_strided": ([_i, _i, _p, _ll, _ll, _i, _ll, _p, _ll, _p], _i),
     "dispu_feature_knn": ([_i, _i, _i, _i, _i, _i, _p, _i, _p, _i, _p, _p, _p], _i),
     "dispu_dense_conv_workspace_bytes": ([_i, _i], _sz),
@@ -98,6 +99,8 @@ def lib():
             fn.restype = res
         if l.dispu_abi_version() != 1:
             raise RuntimeError("libdispu_b200.so ABI version mismatch")
+        if l.dispu_dense_args_size() != C.sizeof(DenseArgs):
+            raise RuntimeError("dispu_dense_args layout mismatch between include/dispu_b200.h and dispu_b200/_lib.py")
         _lib = l
     return _lib
 

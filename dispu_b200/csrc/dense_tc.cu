@@ -634,6 +634,8 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
 
 using namespace dispu;
 
+extern "C" size_t dispu_dense_args_size(void) { return sizeof(dispu_dense_args); }
+
 extern "C" size_t dispu_dense_packed_bytes(int K, int N) {
     if (K <= 0 || N <= 0 || N > 256) return 0;
     return (size_t)dn_chunks(K) * dn_chunk_bytes(N);

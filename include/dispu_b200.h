@@ -275,6 +275,8 @@ typedef struct dispu_dense_args {
     int n_stat;
 } dispu_dense_args;
 int dispu_dense_tf32x3_ex(const dispu_dense_args *args, dispu_stream_t stream);
+/* sizeof(dispu_dense_args) as this library was compiled: lets a foreign-language binding verify its struct layout. */
+size_t dispu_dense_args_size(void);
 /* Pack W[k][n] = src[k*stride_k + n*stride_n] for `batch` operands (source advances by w_batch_stride floats,
  * destination by packed_batch_stride bytes, a multiple of 16 and >= dispu_dense_packed_bytes(K,N)). */
 int dispu_dense_pack_strided(int K, int N, const float *W, long long stride_k, long long stride_n, int batch,

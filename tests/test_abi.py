@@ -41,6 +41,28 @@ def test_binding_covers_header(so):
     assert l.dispu_chamfer_workspace_bytes(32, 1024, 1024) == 8 * 32 * 2 * 4 + 8 * 32
 
 
+def test_dense_args_layout_and_validation(so):
+    """The ctypes mirror of dispu_dense_args has the compiled struct's size; bad arguments are rejected before any CUDA call."""
+    import ctypes as C
+    from dispu_b200 import _lib
+    l = _lib.lib()
+    assert l.dispu_dense_args_size() == C.sizeof(_lib.DenseArgs)
+    a = _lib.DenseArgs()
+    assert l.dispu_dense_tf32x3_ex(None, None) == _lib.ENULL
+    a.M, a.K, a.N = 128, 32, 300
+    assert l.dispu_dense_tf32x3_ex(C.byref(a), None) == _lib.EUNSUPPORTED  # N > 256 per column block
+    a.N = 64
+    assert l.dispu_dense_tf32x3_ex(C.byref(a), None) == _lib.ENULL         # X / packed / Y missing
+    a.M = 0
+    assert l.dispu_dense_tf32x3_ex(C.byref(a), None) == 0                  # empty problem: nothing to do
+    assert l.dispu_dense_packed_bytes(100, 64) == 4 * 2 * 64 * 32 * 4      # 4 K-chunks x [hi|lo] x 64 rows x 32 k
+    assert l.dispu_feature_knn(1, 8, 8, 4, 9, 0, None, 4, None, 4, None, None, None) == _lib.EINVAL   # k > n
+    assert l.dispu_feature_knn(1, 64, 8, 4, 33, 0, None, 4, None, 4, None, None, None) == _lib.EUNSUPPORTED
+    assert l.dispu_dense_conv(1, 8, 6, 4, 24, None, 6, None, None, None, None, None, None, None, None, 80, None, 0, None) == _lib.ENULL
+    assert l.dispu_knn_large(1, 100, 4, 2000, None, None, None, None, None, 0, None) == _lib.EINVAL
+    assert l.dispu_knn_large_workspace_bytes(2, 100, 4) == 2 * 4 * 100 * 4
+
+
 def test_reference_launcher_symbols_exported(so):
     """Mangled names of the launchers the reference wrappers call (tf_sampling.cpp:65,94,125,150;
     tf_grouping.cpp:67,112,146,177; tf_nndistance.cpp:168,208)."""
