@@ -5,8 +5,8 @@
 //    D = (r_q - 2 q.p) + r_p, ascending, ties to the lower index (tf.nn.top_k).  The reference materialises the
 //    (b,n,n) matrix, runs a full top_k and builds (b,n,k,2) gather_nd pairs; here a warp owns two queries, the
 //    cloud's features sit transposed in shared memory (conflict-free column reads), distances stay in
-//    registers and the k winners are extracted by k rounds of warp arg-min (redux.sync on an order-preserving
-//    key, then on the index).  Arithmetic is pinned (sequential fmaf over the channels), so results are reproducible bit for bit.
+//    registers and the k winners are selected by a lane-minima threshold + ballot compaction + rank counting (k rounds
+//    of warp arg-min — redux.sync on an order-preserving key, then on the index — when exact ties overflow that path).  Arithmetic is pinned (sequential fmaf over the channels), so results are reproducible bit for bit.
 //  * dispu_dense_conv — dense_conv (Common/ops.py:1897-1915) over get_edge_feature (:1856-1877): the three 1x1
 //    convs on concat[central, neighbour-central | y | central] and the max over the k neighbours in ONE pass.
 //    Everything that depends only on the centre point is hoisted to a per-point product (exact reassociation):
@@ -41,6 +41,22 @@ __device__ __forceinline__ unsigned ord_key(float f) {
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
+// ascending bitonic sort of one value per lane (15 shuffle steps)
+__device__ __forceinline__ float fk_warp_sort32(float v, int lane) {
+#pragma unroll
+    for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+#pragma unroll
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            const float o = __shfl_xor_sync(kFull, v, j);
+            const bool up = (lane & k2) == 0, lower = (lane & j) == 0;
+            v = (lower == up) ? fminf(v, o) : fmaxf(v, o);
+        }
+    }
+    return v;
+}
+
+constexpr int kFkCap = 96;  // survivors of the threshold selection a warp can rank in shared memory
+
 // P = candidates per lane per chunk (chunk = 32*P points staged transposed in shared memory).
 template <int P>
 __global__ void __launch_bounds__(kFkWarps * 32)
@@ -54,6 +70,10 @@ feature_knn_kernel(int n, int m, int c, int k, int skip, const float *__restrict
     float *s_ft = fk_smem;                           // [c][kStride]
     float *s_r = s_ft + (size_t)c * kStride;         // [kChunk]
     float *s_q = s_r + kChunk;                       // [warps][kFkQueriesPerWarp][c]
+    float *s_sd = s_q + (size_t)kFkWarps * kFkQueriesPerWarp * c;                 // [warps][kFkCap] survivor distances
+    int *s_si = reinterpret_cast<int *>(s_sd + kFkWarps * kFkCap);                // [warps][kFkCap] survivor indices
+    float *s_od = reinterpret_cast<float *>(s_si + kFkWarps * kFkCap);            // [warps][32] ranked output
+    int *s_oi = reinterpret_cast<int *>(s_od + kFkWarps * 32);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cloud = blockIdx.y;
     const float *pts = points + (size_t)cloud * n * ldp;
@@ -125,14 +145,69 @@ feature_knn_kernel(int n, int m, int c, int k, int skip, const float *__restrict
 #pragma unroll
                 for (int w = 0; w < kQ; ++w) d[w][t] = p < tn ? __fadd_rn(__fmaf_rn(-2.f, d[w][t], rq[w]), rp) : inf;
             }
-            // k rounds of warp arg-min; the kQ queries' rounds are independent chains issued back to back
             float cd[kQ], nd[kQ];
             int ci[kQ], ni[kQ];
 #pragma unroll
             for (int w = 0; w < kQ; ++w) { cd[w] = bd[u0 + w]; ci[w] = bi[u0 + w]; nd[w] = inf; ni[w] = 0x7fffffff; }
-            for (int r = 0; r < k; ++r) {
+            // ---- selection, fast path: threshold by LANE MINIMA.  The k-th smallest of the 32 per-lane minima bounds the
+            // k-th smallest value from above (k different lanes hold something <= it); everything <= that bound (about
+            // k + a few elements) is compacted into shared memory by ballot and ordered by rank counting on (d, idx) —
+            // ties to the lower index.  A query whose survivors overflow the buffer (masses of equal distances) takes the
+            // round-by-round extraction below instead.
+            unsigned slow = 0;  // bit w: query w needs the fallback
+            float *sd = s_sd + warp * kFkCap;
+            int *si = s_si + warp * kFkCap;
+            const unsigned lt_mask = (1u << lane) - 1u;
+#pragma unroll
+            for (int w = 0; w < kQ; ++w) {
+                float lmin = cd[w];
+#pragma unroll
+                for (int t = 0; t < P; ++t) lmin = fminf(lmin, d[w][t]);
+                const float bound = __shfl_sync(kFull, fk_warp_sort32(lmin, lane), k - 1);
+                int S = 0;
+                {
+                    const bool keep = cd[w] <= bound && cd[w] < inf;
+                    const unsigned mask = __ballot_sync(kFull, keep);
+                    if (keep) { const int pos = __popc(mask & lt_mask); sd[pos] = cd[w]; si[pos] = ci[w]; }
+                    S = __popc(mask);
+                }
+#pragma unroll
+                for (int t = 0; t < P; ++t) {
+                    const bool keep = d[w][t] <= bound && d[w][t] < inf;
+                    const unsigned mask = __ballot_sync(kFull, keep);
+                    if (mask) {
+                        const int pos = S + __popc(mask & lt_mask);
+                        if (keep && pos < kFkCap) { sd[pos] = d[w][t]; si[pos] = t0 + t * 32 + lane; }
+                        S += __popc(mask);
+                    }
+                }
+                __syncwarp();
+                if (S > kFkCap || S < k) {  // (S < k only with NaN/inf distances)
+                    slow |= 1u << w;
+                } else {
+                    for (int e0 = 0; e0 < S; e0 += 32) {
+                        const int e = e0 + lane;
+                        const float de = e < S ? sd[e] : inf;
+                        const int ie = e < S ? si[e] : 0x7fffffff;
+                        int rank = 0;
+                        for (int f = 0; f < S; ++f) {
+                            const float df = sd[f];
+                            const int jf = si[f];
+                            rank += (df < de) || (df == de && jf < ie);
+                        }
+                        if (e < S && rank < 32) { s_od[warp * 32 + rank] = de; s_oi[warp * 32 + rank] = ie; }
+                    }
+                    __syncwarp();
+                    nd[w] = lane < k ? s_od[warp * 32 + lane] : inf;
+                    ni[w] = lane < k ? s_oi[warp * 32 + lane] : 0x7fffffff;
+                }
+                __syncwarp();
+            }
+            // ---- fallback: k rounds of warp arg-min
+            for (int r = 0; r < (slow ? k : 0); ++r) {
 #pragma unroll
                 for (int w = 0; w < kQ; ++w) {
+                    if (!(slow & (1u << w))) continue;
                     // lane-local minimum; strict '<' keeps the carried entry (lower index) and the lower slot on ties
                     float lm = cd[w];
                     int lt = -1;
@@ -517,7 +592,7 @@ using namespace dispu;
 template <int P>
 static int launch_feature_knn(int b, int n, int m, int c, int k, int skip, const float *points, int ldp, const float *queries,
                               int ldq, float *dist, int *idx, cudaStream_t stream, const EcProjArgs &pj = EcProjArgs{}) {
-    size_t smem = ((size_t)c * (32 * P + 1) + 32 * P + (size_t)kFkWarps * kFkQueriesPerWarp * c) * sizeof(float);
+    size_t smem = ((size_t)c * (32 * P + 1) + 32 * P + (size_t)kFkWarps * kFkQueriesPerWarp * c + 2 * kFkWarps * (kFkCap + 32)) * sizeof(float);
     const size_t smem_proj = ((size_t)c * kEcProjW + kEcProjW) * sizeof(float);
     if (pj.proj && smem < smem_proj) smem = smem_proj;
     if (smem > 220 * 1024) return DISPU_EUNSUPPORTED;
@@ -532,7 +607,9 @@ static int launch_feature_knn(int b, int n, int m, int c, int k, int skip, const
 static int feature_knn_dispatch(int b, int n, int m, int c, int k, int skip, const float *points, int ldp, const float *queries,
                                 int ldq, float *dist, int *idx, cudaStream_t stream, const EcProjArgs &pj = EcProjArgs{}) {
     // largest chunk (32*P candidates) that covers the cloud and whose transposed features fit in shared memory
-    auto fits = [&](int P) { return ((size_t)c * (32 * P + 1) + 32 * P + (size_t)kFkWarps * kFkQueriesPerWarp * c) * sizeof(float) <= 220 * 1024; };
+    auto fits = [&](int P) {
+        return ((size_t)c * (32 * P + 1) + 32 * P + (size_t)kFkWarps * kFkQueriesPerWarp * c + 2 * kFkWarps * (kFkCap + 32)) * sizeof(float) <= 220 * 1024;
+    };
     if (n > 512 && fits(32)) return launch_feature_knn<32>(b, n, m, c, k, skip, points, ldp, queries, ldq, dist, idx, stream, pj);
     if (n > 256 && fits(16)) return launch_feature_knn<16>(b, n, m, c, k, skip, points, ldp, queries, ldq, dist, idx, stream, pj);
     return launch_feature_knn<8>(b, n, m, c, k, skip, points, ldp, queries, ldq, dist, idx, stream, pj);
