@@ -39,6 +39,7 @@ sys.path.insert(0, ROOT)
 B_PER_GPU = 32
 N_IN = 256
 UP = 4
+RESULT_OUT = sys.stdout  # main() replaces it with a private copy of the real stdout
 METRIC = "input_points_per_sec_4x_upsample_fwd_chamfer"
 UNIT = "points/s"
 
@@ -209,7 +210,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=RESULT_OUT, flush=True)
 
 
 def run_product(args, rank, world, local_rank):
@@ -357,7 +358,7 @@ def run_product(args, rank, world, local_rank):
             "cpu_baseline": cpu_base,
             "loss": {"cd_coarse_sum": loss[0], "cd_fine_sum": loss[1], "hd_coarse": loss[2], "hd_fine": loss[3]},
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=RESULT_OUT, flush=True)
 
 
 def measured_peaks():
@@ -492,6 +493,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line.  Libraries that print to fd 1 (NCCL's version banner under NCCL_DEBUG=VERSION
+    # does) are sent to stderr: keep a private copy of the real stdout for the result line, point fd 1 at stderr.
+    global RESULT_OUT
+    sys.stdout.flush()
+    RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
