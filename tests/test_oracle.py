@@ -245,3 +245,19 @@ def test_weightnet_aggregate_oracle_vs_numpy():
     wn = np.maximum((gx.astype(np.float64) @ Ww + bw) * 0.9995, 0)
     want = np.einsum("bmsc,bmst->bmct", G.astype(np.float64), wn).reshape(b, m, -1)
     np.testing.assert_allclose(H, want, rtol=1e-5, atol=1e-5)
+
+
+def test_f_rows_golden_fixture():
+    """The oracle's §8(f) restatements against the committed golden vectors (tests/golden/f_rows.npz, generated by
+    make_golden_f.py from independent numpy float64 restatements of the cited TensorFlow expressions)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "f_rows.npz"))
+    d, i = O.feature_knn(17, g["knn_feat"], g["knn_feat"])
+    assert np.array_equal(i, g["knn_i"])
+    np.testing.assert_allclose(d, g["knn_d"], atol=3e-5)
+    out = O.dense_conv(g["knn_feat"], g["dc_idx"], g["dc_w0"], g["dc_b0"], g["dc_w1"], g["dc_b1"], g["dc_w2"], g["dc_b2"])
+    np.testing.assert_allclose(out, g["dc_out"], rtol=1e-5, atol=1e-5)
+    H = O.weightnet_aggregate(g["wn_xyz"], g["wn_idx"], g["wn_G"], g["wn_Ww"], g["wn_bw"], 1.0 / np.sqrt(1.0 + 1e-3))
+    np.testing.assert_allclose(H, g["wn_out"], rtol=1e-5, atol=2e-5)
+    t = O.uniform_loss_term(g["un_pcd"], g["un_idx"], float(g["un_expect"]))
+    assert abs(float(t) - float(g["un_term"])) <= 1e-5 * max(1.0, abs(float(g["un_term"])))
