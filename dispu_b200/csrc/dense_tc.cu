@@ -6,16 +6,21 @@
 // contraction per point; tf_util.conv2d, Common/tf_util.py:120-185), with bias and ReLU fused in the epilogue
 // instead of separate bias_add / relu passes.
 //
-// Warp-specialised persistent kernel, one CTA per SM, 13 warps:
-//   warps 0-7   producers: two threads per row stream the X tile in 32-column chunks, split into TF32 hi/lo and
-//               write both planes in the K-major UMMA layout.  Small weights (K*N_pad*8 B + two stages fit) stay
-//               RESIDENT in shared memory for the CTA's lifetime; otherwise the producers also copy the matching
-//               pre-packed weight chunk (already split + laid out by dispu_dense_pack) into the stage;
-//   warps 8-11  epilogue: accumulator row r -> registers (tcgen05.ld), + bias, ReLU, 16-byte stores;
-//   warp  12    one thread issues 4 K-steps x 3 tcgen05.mma per chunk (A and B from shared memory, M=128,
-//               N=N_pad) and releases the stage with tcgen05.commit.
-// Up to four smem stages (full/empty mbarriers) and two TMEM accumulators (full/empty mbarriers) keep loads,
-// MMAs and the epilogue of consecutive tiles overlapped.
+// Warp-specialised persistent kernel, one CTA per SM, 17 warps (TS form: the A operand lives in tensor memory):
+//   warps 0-7   producers: thread (row, half of the 32-column K-chunk) keeps two chunks of raw global loads in flight
+//               in registers (plus prefetch.global.L2 further ahead), applies the optional gather front-end
+//               (relu(X[idx] + sign*Q)) or softmax transform at consume time, splits into TF32 hi/lo and writes both
+//               planes straight into the TMEM A ring (4 slots x 64 columns) with tcgen05.st;
+//   one of them also issues the TMA bulk copy (cp.async.bulk + mbarrier transaction bytes) of the pre-packed weight
+//               chunk when the weight does not stay resident in shared memory;
+//   warps 8-15  epilogue, two per TMEM lane quarter on alternating 16-column blocks: tcgen05.ld -> bias / ReLU /
+//               row scale -> shared-memory staging -> 8 rows x 64 B per store instruction (+ residuals), or the
+//               weight-net contraction (kEpi == 1);
+//   warp  16    one thread issues 4 K-steps x 3 tcgen05.mma per chunk (A from TMEM, B from shared memory, M=128,
+//               N=N_pad) and releases ring slots with tcgen05.commit.
+// full/empty mbarriers on the ring slots and on the TMEM accumulators (two of <= 128 columns, or one of 256) keep loads,
+// MMAs and the epilogue of consecutive tiles overlapped.  Development probes: DISPU_DENSE_DBG masks pipeline components,
+// DISPU_DENSE_TRACE records clock64 traces of the three roles (tools/dense_dbg.py, tools/dense_trace.py).
 #include <stdlib.h>
 
 #include "common.cuh"
