@@ -187,3 +187,23 @@ class BlockedLinear:
         a.n_blocks, a.packed_block_stride = self.nb, self.stride
         call("dispu_dense_tf32x3_ex", C.byref(a), stream_ptr())
         return out
+
+
+def attention_fused_experimental(kvq, m_block=128):
+    """EXPERIMENTAL (csrc/attention_tc.cu: compiled, not yet validated on hardware; nothing calls it by default).
+    kvq (b,m,256) = [key 64 | value 64 | query 64 pre-scaled by 1/sqrt(64) | pad]: softmax(q.k^T).v -> (b,m,64) in ONE
+    kernel, the (b,m,m) score tensor is never written.  m % 128 == 0."""
+    import ctypes as C2
+    if kvq.dim() != 3 or kvq.shape[2] != 256 or not kvq.is_contiguous() or kvq.shape[1] % 128:
+        raise ValueError("attention_fused_experimental expects a contiguous (b, m, 256) tensor with m % 128 == 0")
+    b, m, _ = kvq.shape
+    nb = m // m_block
+    kop = BatchedOperand(b * nb, 64, 128, kvq.device).pack(kvq, 0, 1, 256, m_block * 256)      # N = keys, K = channels
+    vop = BatchedOperand(b * nb, 128, 64, kvq.device).pack(kvq, 64, 256, 1, m_block * 256)     # N = channels, K = keys
+    out = torch.empty((b, m, 64), dtype=torch.float32, device=kvq.device)
+    fn = _lib.lib().dispu_attention_tf32x3_experimental
+    fn.argtypes = [C2.c_int, C2.c_int, C2.c_void_p, C2.c_longlong, C2.c_void_p, C2.c_void_p, C2.c_void_p, C2.c_longlong, C2.c_void_p]
+    fn.restype = C2.c_int
+    _lib.check("dispu_attention_tf32x3_experimental",
+               fn(b, m, kvq.data_ptr() + 4 * 128, 256, ptr(kop.packed), ptr(vop.packed), ptr(out), 64, stream_ptr()))
+    return out

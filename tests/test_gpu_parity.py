@@ -850,3 +850,18 @@ def test_dense_ex_fused_softmax(rng):
     np.testing.assert_allclose(got, want, rtol=2e-5, atol=2e-5)
     # the partial maxima merge to the exact row maximum
     np.testing.assert_allclose(stats.cpu().numpy().max(-1), S.max(-1), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.skip(reason="csrc/attention_tc.cu was written after the round-1 GPU budget was spent: validate it first thing in round 2")
+def test_attention_fused_experimental(rng):
+    """softmax(q.k^T).v in one tcgen05 kernel (no (b,m,m) score tensor) vs a float64 softmax."""
+    from dispu_b200.dense import attention_fused_experimental
+    b, m = 2, 512
+    kvq = np.zeros((b, m, 256), np.float32)
+    kvq[..., :128] = rng.standard_normal((b, m, 128))
+    kvq[..., 128:192] = rng.standard_normal((b, m, 64)) * 0.7
+    got = attention_fused_experimental(T(kvq)).cpu().numpy()
+    S = np.einsum("bik,bjk->bij", kvq[..., 128:192].astype(np.float64), kvq[..., :64].astype(np.float64))
+    P = np.exp(S - S.max(-1, keepdims=True))
+    P /= P.sum(-1, keepdims=True)
+    np.testing.assert_allclose(got, P @ kvq[..., 64:128].astype(np.float64), rtol=2e-5, atol=2e-5)
