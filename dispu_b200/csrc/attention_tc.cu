@@ -18,6 +18,9 @@
 // pass 2 recomputes S, turns it into P chunk by chunk and accumulates O.
 // Roles: warps 0-3 softmax / epilogue (thread = query row = TMEM lane), warp 4 lane 0 issues every MMA, warp 5 lane 0
 // issues the TMA bulk copies.  All hand-offs are mbarriers; MMA completion is signalled with tcgen05.commit.
+// The barrier protocol (not the arithmetic) is model-checked on the host by tools/attention_protocol_sim.py: random
+// interleavings of the six roles with the hardware's phase/parity semantics, no deadlock, no read-before-produce or
+// overwrite-before-consume on K/V buffers, S, the P ring, Q and O (o_empty is implied by q_full and kept as a guard).
 #include "common.cuh"
 #include "tc_common.cuh"
 
