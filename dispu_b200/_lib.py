@@ -73,6 +73,7 @@ SIGNATURES = {
     "dispu_dense_conv_knn": ([_i, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _sz, _p], _i),
     "dispu_weightnet_aggregate": ([_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, C.c_float, _p, _p], _i),
     "dispu_sa_mlp": ([_i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _p], _i),
+    "dispu_sa_mlp_ex": ([_i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _i, _p], _i),
 }
 
 _lib = None

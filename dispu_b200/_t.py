@@ -8,7 +8,15 @@ from . import _lib
 
 
 def stream_ptr() -> int:
+    """The current stream of the CURRENT device.  req()/rows() reject tensors that live on any other device, so a
+    kernel is never enqueued on one GPU's stream with another GPU's pointers."""
     return torch.cuda.current_stream().cuda_stream
+
+
+def _same_device(t, name):
+    if t.device.index is not None and t.device.index != torch.cuda.current_device():
+        raise RuntimeError(f"{name}: tensor lives on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+                           "call torch.cuda.set_device() / use `with torch.cuda.device(t.device)` around dispu_b200 ops")
 
 
 def req(t, dtype, ndim, name):
@@ -17,6 +25,7 @@ def req(t, dtype, ndim, name):
         raise TypeError(f"{name}: expected a torch.Tensor on a CUDA device, got {type(t).__name__}")
     if not t.is_cuda:
         raise RuntimeError(f"{name}: dispu_b200 ops are GPU-only (no CPU fallback); got a {t.device} tensor")
+    _same_device(t, name)
     if t.dtype != dtype:
         raise ValueError(f"{name}: expected dtype {dtype}, got {t.dtype}")
     if t.dim() != ndim:
@@ -63,6 +72,7 @@ def rows(t, name="tensor"):
     uniformly strided — a contiguous tensor or a column slice of one (x[..., a:b])."""
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise RuntimeError(f"{name}: dispu_b200 ops are GPU-only (no CPU fallback)")
+    _same_device(t, name)
     if t.dtype != torch.float32:
         raise ValueError(f"{name}: expected float32, got {t.dtype}")
     if t.dim() < 1 or (t.shape[-1] > 1 and t.stride(-1) != 1):

@@ -130,9 +130,15 @@ attention_tf32x3_kernel(int b, int m, const float *__restrict__ q, long long ldq
                             const uint64_t dbh = make_smem_desc(chunk, lbo_k, 128u);
                             const uint64_t dbl = make_smem_desc(chunk + plane_k, lbo_k, 128u);
                             const uint32_t a_hi = tmem_base + kAtColQ + (uint32_t)ks * 8u, a_lo = a_hi + 64u;
-                            mma_tf32_ts(tmem_base + kAtColS, a_lo, dbh, idesc_s, ks != 0);
-                            mma_tf32_ts(tmem_base + kAtColS, a_hi, dbl, idesc_s, 1);
-                            mma_tf32_ts(tmem_base + kAtColS, a_hi, dbh, idesc_s, 1);
+                            if (pass == 0) {
+                                // pass 1 only needs a row shift close to the maximum (softmax is shift-invariant as long as
+                                // numerator and denominator use the same shift): one TF32 product instead of three
+                                mma_tf32_ts(tmem_base + kAtColS, a_hi, dbh, idesc_s, ks != 0);
+                            } else {
+                                mma_tf32_ts(tmem_base + kAtColS, a_lo, dbh, idesc_s, ks != 0);
+                                mma_tf32_ts(tmem_base + kAtColS, a_hi, dbl, idesc_s, 1);
+                                mma_tf32_ts(tmem_base + kAtColS, a_hi, dbh, idesc_s, 1);
+                            }
                         }
                         mma_commit(&k_empty[buf]);
                         mma_commit(&s_full);

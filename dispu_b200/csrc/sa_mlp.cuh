@@ -12,6 +12,10 @@ struct MlpParams {
     int widths[kMlpMaxLayers + 1];
     const float *w[kMlpMaxLayers];
     const float *bias[kMlpMaxLayers];
+    // inference batch norm folded to a per-channel affine applied after the bias, before the ReLU
+    // (tf_util.conv2d bn=True, Common/tf_util.py:178-181): y = relu((x.W + b) * bn_scale + bn_shift); NULL = no BN
+    const float *bn_scale[kMlpMaxLayers];
+    const float *bn_shift[kMlpMaxLayers];
 };
 
 // Launches the tensor-core kernel when the shape is one it is built for; *handled tells.

@@ -189,13 +189,13 @@ class BlockedLinear:
         return out
 
 
-def attention_fused_experimental(kvq, m_block=128):
+def attention_fused(kvq, m_block=128):
     """EXPERIMENTAL (csrc/attention_tc.cu: compiled, not yet validated on hardware; nothing calls it by default).
     kvq (b,m,256) = [key 64 | value 64 | query 64 pre-scaled by 1/sqrt(64) | pad]: softmax(q.k^T).v -> (b,m,64) in ONE
     kernel, the (b,m,m) score tensor is never written.  m % 128 == 0."""
     import ctypes as C2
     if kvq.dim() != 3 or kvq.shape[2] != 256 or not kvq.is_contiguous() or kvq.shape[1] % 128:
-        raise ValueError("attention_fused_experimental expects a contiguous (b, m, 256) tensor with m % 128 == 0")
+        raise ValueError("attention_fused expects a contiguous (b, m, 256) tensor with m % 128 == 0")
     b, m, _ = kvq.shape
     nb = m // m_block
     kop = BatchedOperand(b * nb, 64, 128, kvq.device).pack(kvq, 0, 1, 256, m_block * 256)      # N = keys, K = channels

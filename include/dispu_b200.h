@@ -209,6 +209,27 @@ int dispu_sa_mlp(int b, int n, int m, int nsample, int c_pts, int layout, const 
                  const float *const *weights_host_array, const float *const *biases_host_array, float *out,
                  int precision, dispu_stream_t stream);
 
+/* The same with the remaining options of pointnet_sa_module (Common/pointnet_util.py:91-149):
+ *   use_xyz 0: channels = points only (:54-55; widths[0] = c_pts, c_pts > 0);
+ *   pooling (:122-141): MAX; AVG = sum/nsample; WEIGHTED_AVG = sum_s x_s * w_s / sum_s w_s with
+ *   w_s = exp(-5 |xyz_s - centre|); MIN = max(-x) (the reference pools -1*x and does not negate back);
+ *   MAX_AND_AVG = [max | avg], out is (b,m,2*widths[n_layers]);
+ *   bn_scale[l] / bn_shift[l]: DEVICE (widths[l+1]) or NULL — inference batch norm of tf_util.conv2d(bn=True)
+ *   (Common/tf_util.py:178-181) folded to y = relu((x.W + b) * scale + shift), scale = gamma / sqrt(var + 1e-3),
+ *   shift = beta - mean * scale; the arrays themselves are HOST arrays (may be NULL = no BN anywhere).
+ * The tensor-core precisions support the hot-path form only (MAX, use_xyz, no BN): anything else with
+ * precision != DISPU_MLP_FP32 returns DISPU_EUNSUPPORTED. */
+#define DISPU_POOL_MAX 0
+#define DISPU_POOL_AVG 1
+#define DISPU_POOL_WEIGHTED_AVG 2
+#define DISPU_POOL_MIN 3
+#define DISPU_POOL_MAX_AND_AVG 4
+int dispu_sa_mlp_ex(int b, int n, int m, int nsample, int c_pts, int layout, int use_xyz, int pooling, const float *xyz,
+                    const float *points, const float *new_xyz, const int *idx, int n_layers, const int *widths_host,
+                    const float *const *weights_host_array, const float *const *biases_host_array,
+                    const float *const *bn_scale_host_array, const float *const *bn_shift_host_array, float *out,
+                    int precision, dispu_stream_t stream);
+
 /* Dense layer on tcgen05 with FP32-level accuracy (3xTF32, FP32 accumulate in TMEM), bias + ReLU fused:
  *     Y[M,N] = act(X[M,K] . W[K,N] + bias),  N <= 256, any K.
  * The unit the live generator's grouped MLPs reduce to after hoisting their first layer (Common/ops.py:1055-1072:

@@ -260,6 +260,70 @@ def sample_and_group(npoint, radius, nsample, xyz, points, knn_mode=False, use_x
     return new_xyz, new_points, idx, grouped_xyz
 
 
+def sample_and_group_all(xyz, points, use_xyz=True):
+    """pointnet_util.py:62-88 -> (new_xyz zeros (b,1,3), new_points (b,1,n,3+c), idx (b,1,n), grouped_xyz)."""
+    xyz = _f(xyz)
+    b, n, _ = xyz.shape
+    new_xyz = np.zeros((b, 1, 3), np.float32)
+    idx = np.tile(np.arange(n, dtype=np.int32).reshape(1, 1, n), (b, 1, 1))
+    grouped_xyz = xyz.reshape(b, 1, n, 3)
+    if points is not None:
+        new_points = (np.concatenate([xyz, _f(points)], 2) if use_xyz else _f(points))[:, None]
+    else:
+        new_points = grouped_xyz
+    return new_xyz, new_points, idx, grouped_xyz
+
+
+def conv2d_1x1(x, w, b=None, bn=None, relu=True):
+    """tf_util.conv2d with a [1,1] kernel (Common/tf_util.py:120-185): x.W + bias, optional inference batch norm
+    (tf.nn.batch_normalization with the moving statistics, epsilon 1e-3, :527), ReLU.  float64 accumulate, so the
+    result is the exact value the fp32 implementations are compared against."""
+    y = x.astype(np.float64) @ w.astype(np.float64)
+    if b is not None:
+        y = y + b.astype(np.float64)
+    if bn is not None:
+        gamma, beta, mean, var = (np.asarray(t, np.float64) for t in bn)
+        y = (y - mean) / np.sqrt(var + 1e-3) * gamma + beta
+    return np.maximum(y, 0.0) if relu else y
+
+
+def sa_module(xyz, points, new_xyz, idx, layers, pooling="max", use_xyz=True, layout=0, mlp2=None):
+    """pointnet_sa_module's body after sampling/grouping (pointnet_util.py:117-149) and the _msg channel order (:179),
+    literally: grouped tensor -> conv2d per layer -> pooling variant -> mlp2.  layers: list of (w, b[, bn]).
+    Returns float64 (b,m,C)."""
+    xyz, new_xyz = _f(xyz), _f(new_xyz)
+    gx = group_point(xyz, idx) - new_xyz[:, :, None, :]
+    if points is not None:
+        gp = group_point(_f(points), idx)
+        if use_xyz:
+            x = np.concatenate([gx, gp], -1) if layout == 0 else np.concatenate([gp, gx], -1)
+        else:
+            x = gp
+    else:
+        x = gx
+    x = x.astype(np.float64)
+    for layer in layers:
+        x = conv2d_1x1(x, layer[0], layer[1], layer[2] if len(layer) > 2 else None)
+    ns = x.shape[2]
+    if pooling == "avg":
+        x = x.sum(2, keepdims=True) / ns
+    elif pooling == "weighted_avg":  # :124-131
+        d = np.sqrt((gx.astype(np.float64) ** 2).sum(-1, keepdims=True))
+        e = np.exp(-d * 5)
+        x = (x * (e / e.sum(2, keepdims=True))).sum(2, keepdims=True)
+    elif pooling == "max":
+        x = x.max(2, keepdims=True)
+    elif pooling == "min":  # :135-137: max_pool2d(-1 * new_points): the result is NOT negated back
+        x = (-x).max(2, keepdims=True)
+    elif pooling == "max_and_avg":  # :138-141 (the reference's variable names are swapped; the concat is [max | avg])
+        x = np.concatenate([x.max(2, keepdims=True), x.sum(2, keepdims=True) / ns], -1)
+    else:
+        raise ValueError(pooling)
+    for layer in (mlp2 or []):
+        x = conv2d_1x1(x, layer[0], layer[1], layer[2] if len(layer) > 2 else None)
+    return x[:, :, 0]
+
+
 def three_nn_weights(dist):
     """pointnet_util.py:205-208."""
     d = np.maximum(_f(dist), np.float32(1e-10))

@@ -338,6 +338,159 @@ def test_pointnet_sa_module_end_to_end(rng):
     assert np.array_equal(grouped.cpu().numpy(), o_new_points)
 
 
+def _mk_layers(rng, widths, bn=False):
+    out = []
+    for i in range(len(widths) - 1):
+        w = (rng.standard_normal((widths[i], widths[i + 1])) / np.sqrt(widths[i])).astype(np.float32)
+        bb = (rng.standard_normal((widths[i + 1],)) * 0.1).astype(np.float32)
+        layer = (w, bb)
+        if bn:
+            c = widths[i + 1]
+            layer = (w, bb, ((1 + 0.2 * rng.standard_normal(c)).astype(np.float32), (0.1 * rng.standard_normal(c)).astype(np.float32),
+                             (0.1 * rng.standard_normal(c)).astype(np.float32), rng.uniform(0.5, 1.5, c).astype(np.float32)))
+        out.append(layer)
+    return out
+
+
+def _TL(layers):
+    return [tuple(None if t is None else (tuple(T(u) for u in t) if isinstance(t, tuple) else T(t)) for t in layer) for layer in layers]
+
+
+@pytest.mark.parametrize("pooling", ["max", "avg", "weighted_avg", "min", "max_and_avg"])
+@pytest.mark.parametrize("ns,use_xyz,bn", [(32, True, False), (16, False, True), (200, True, True)])
+def test_sa_module_pooling_variants_bn_use_xyz(rng, pooling, ns, use_xyz, bn):
+    """pointnet_sa_module's pooling variants (Common/pointnet_util.py:122-141), use_xyz=False (:54-55) and inference
+    batch norm (tf_util.conv2d bn=True) inside the fused kernel vs the literal float64 restatement; ns=200 exercises
+    the chunked (ns > 128) accumulation of every variant."""
+    b, n, m, c_pts = 2, 500, 40, 6
+    xyz = unit_ball(rng, b, n)
+    pts = rng.standard_normal((b, n, c_pts)).astype(np.float32)
+    new_xyz = O.gather_point(xyz, O.farthest_point_sample(m, xyz))
+    idx, _ = O.query_ball_point(0.45, ns, xyz, new_xyz)
+    layers = _mk_layers(rng, [(3 if use_xyz else 0) + c_pts, 16, 24], bn=bn)
+    want = O.sa_module(xyz, pts, new_xyz, idx, layers, pooling=pooling, use_xyz=use_xyz)
+    got = PU.grouped_mlp_max(T(xyz), T(pts), T(new_xyz), T(idx), _TL(layers), pooling=pooling, use_xyz=use_xyz).cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5)
+
+
+def test_sa_module_mlp2_and_group_all(rng):
+    """mlp2 (pointnet_util.py:142-147) on the tcgen05 dense layer and group_all (sample_and_group_all, :62-88: one
+    group of all n points around the origin) through pointnet_sa_module."""
+    b, n, c_pts = 3, 384, 5
+    xyz = unit_ball(rng, b, n)
+    pts = rng.standard_normal((b, n, c_pts)).astype(np.float32)
+    mlp, mlp2 = _mk_layers(rng, [3 + c_pts, 32, 64]), _mk_layers(rng, [64, 48, 16], bn=True)
+    new_xyz, new_points, idx = PU.pointnet_sa_module(T(xyz), T(pts), None, None, None, _TL(mlp), mlp2=_TL(mlp2), group_all=True)
+    o_new_xyz, _, o_idx, _ = O.sample_and_group_all(xyz, pts)
+    assert np.array_equal(new_xyz.cpu().numpy(), o_new_xyz) and np.array_equal(idx.cpu().numpy(), o_idx)
+    want = O.sa_module(xyz, pts, o_new_xyz, o_idx, mlp, mlp2=mlp2)
+    assert new_points.shape == (b, 1, 16)
+    np.testing.assert_allclose(new_points.cpu().numpy(), want, rtol=2e-5, atol=2e-5)
+    # sampled groups + mlp2
+    new_xyz, new_points, idx = PU.pointnet_sa_module(T(xyz), T(pts), 32, 0.4, 16, _TL(mlp), mlp2=_TL(mlp2), pooling="avg")
+    o_new_xyz, _, o_idx, _ = O.sample_and_group(32, 0.4, 16, xyz, pts)
+    assert np.array_equal(idx.cpu().numpy(), o_idx)
+    np.testing.assert_allclose(new_points.cpu().numpy(), O.sa_module(xyz, pts, o_new_xyz, o_idx, mlp, pooling="avg", mlp2=mlp2),
+                               rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("precision", [PU.MLP_FP32, PU.MLP_TF32X3])
+def test_pointnet_sa_module_msg(rng, precision):
+    """pointnet_sa_module_msg (pointnet_util.py:152-189): one FPS, three radii, channel order [points | xyz-centre] (:179),
+    per-scale max, concat."""
+    b, n, npoint, c_pts = 2, 1024, 128, 16
+    xyz = unit_ball(rng, b, n)
+    pts = rng.standard_normal((b, n, c_pts)).astype(np.float32)
+    radii, nss = [0.1, 0.2, 0.4], [16, 32, 64]
+    mlps = [_mk_layers(rng, [c_pts + 3, 32, 32, 64]), _mk_layers(rng, [c_pts + 3, 64, 64, 128]), _mk_layers(rng, [c_pts + 3, 64, 96, 128])]
+    new_xyz, new_points = PU.pointnet_sa_module_msg(T(xyz), T(pts), npoint, radii, nss, [_TL(m_) for m_ in mlps], precision=precision)
+    o_new_xyz = O.gather_point(xyz, O.farthest_point_sample(npoint, xyz))
+    assert np.array_equal(new_xyz.cpu().numpy(), o_new_xyz)
+    want = np.concatenate([O.sa_module(xyz, pts, o_new_xyz, O.query_ball_point(r, ns, xyz, o_new_xyz)[0], m_, layout=1)
+                           for r, ns, m_ in zip(radii, nss, mlps)], -1)
+    assert new_points.shape == (b, npoint, 64 + 128 + 128)
+    np.testing.assert_allclose(new_points.cpu().numpy(), want, rtol=1e-5, atol=2e-5)
+
+
+def test_pointnet_fp_module_with_mlp(rng):
+    """pointnet_fp_module (pointnet_util.py:192-222) incl. the concat with points1 and the 1x1-conv mlp (with BN)."""
+    b, n, m, c1, c2 = 2, 512, 128, 32, 64
+    x1, x2 = unit_ball(rng, b, n), unit_ball(rng, b, m)
+    p1 = rng.standard_normal((b, n, c1)).astype(np.float32)
+    p2 = rng.standard_normal((b, m, c2)).astype(np.float32)
+    mlp = _mk_layers(rng, [c1 + c2, 128, 64], bn=True)
+    got = PU.pointnet_fp_module(T(x1), T(x2), T(p1), T(p2), _TL(mlp)).cpu().numpy()
+    d, i = O.three_nn(x1, x2)
+    x = np.concatenate([O.three_interpolate(p2, i, O.three_nn_weights(d)), p1], -1)
+    for layer in mlp:
+        x = O.conv2d_1x1(x, *layer)
+    np.testing.assert_allclose(got, x, rtol=2e-5, atol=2e-5)
+
+
+def test_losses_radius_tensor_and_gradients(rng):
+    """chamfer / hausdorff_loss with the per-cloud radius TENSOR the trainer passes (DisPU/model.py:75-79), and the
+    differentiable paths: d(loss)/d(pred) through NnDistanceGrad / GroupPointGrad equals torch autograd on a plain
+    cdist / gather formulation of the same losses (Common/loss_utils.py:45-84, :271-298)."""
+    b, n, m = 4, 256, 300
+    pred, gt = unit_ball(rng, b, n), unit_ball(rng, b, m)
+    radius = rng.uniform(0.5, 2.0, (b,)).astype(np.float32)
+    oc = O.chamfer(pred, gt, radius)
+    cd = LU.chamfer(T(pred), T(gt), radius=T(radius))
+    hd = LU.hausdorff_loss(T(pred), T(gt), radius=T(radius))
+    assert float(cd) == pytest.approx(oc["cd"], rel=1e-5) and float(hd) == pytest.approx(oc["hd"], rel=1e-5)
+    assert float(LU.chamfer(T(pred), T(gt))) == pytest.approx(O.chamfer(pred, gt)["cd"], rel=1e-5)
+
+    def torch_losses(p, g, r):
+        d = torch.cdist(g.double(), p.double()) ** 2  # (b, m, n): gt first, like nn_distance(gt, pred)
+        fwd, bwd = d.min(2)[0], d.min(1)[0]
+        return ((fwd.mean(1) + bwd.mean(1)) / r).mean(), ((fwd.max(1)[0] + bwd.max(1)[0]) / r).max()
+
+    p1 = T(pred).requires_grad_(True)
+    cd1, hd1 = LU.chamfer(p1, T(gt), radius=T(radius)), LU.hausdorff_loss(p1, T(gt), radius=T(radius))
+    (1000.0 * cd1 + 100.0 * hd1).backward()
+    p2 = T(pred).double().requires_grad_(True)
+    cd2, hd2 = torch_losses(p2, T(gt), T(radius).double())
+    (1000.0 * cd2 + 100.0 * hd2).backward()
+    assert float(cd1) == pytest.approx(float(cd2), rel=1e-5) and float(hd1) == pytest.approx(float(hd2), rel=1e-5)
+    np.testing.assert_allclose(p1.grad.cpu().numpy(), p2.grad.cpu().numpy(), rtol=1e-4, atol=1e-6)
+    assert float(p1.grad.abs().sum()) > 0
+    # repulsion (ball r=0.07, ns=20 on a dense cloud so the hinge is active) and uniform losses
+    dense = (unit_ball(rng, 2, 1024) * 0.3).astype(np.float32)
+    q1 = T(dense).requires_grad_(True)
+    rep = LU.get_repulsion_loss(q1)
+    assert float(rep) == pytest.approx(float(LU.get_repulsion_loss(T(dense))), rel=1e-5)
+    rep.backward()
+    q2 = T(dense).double().requires_grad_(True)
+    idx, _ = O.query_ball_point(0.07, 20, dense, dense)
+    g = q2[torch.arange(2, device=dev).view(2, 1, 1), T(idx).long()] - q2.unsqueeze(2)
+    val = torch.topk(-(g ** 2).sum(-1), 5)[0][:, :, 1:]
+    torch.clamp(0.001 + val, min=0).mean().backward()
+    assert float(q1.grad.abs().sum()) > 0
+    np.testing.assert_allclose(q1.grad.cpu().numpy(), q2.grad.cpu().numpy(), rtol=1e-4, atol=1e-7)
+    u1 = T(dense).requires_grad_(True)
+    uni = LU.get_uniform_loss(u1)
+    assert float(uni) == pytest.approx(float(LU.get_uniform_loss(T(dense))), rel=1e-4)
+    uni.backward()
+    assert torch.isfinite(u1.grad).all() and float(u1.grad.abs().sum()) > 0
+    # the fused SA module falls back to the differentiable op sequence when gradients are requested
+    xyz = unit_ball(rng, 2, 256)
+    layers = _mk_layers(rng, [3, 16, 32])
+    tl = [(T(w).requires_grad_(True), T(bb)) for w, bb in layers]
+    _, feat, _ = PU.pointnet_sa_module(T(xyz), None, 32, 0.4, 16, tl)
+    _, feat0, _ = PU.pointnet_sa_module(T(xyz), None, 32, 0.4, 16, _TL(layers))
+    np.testing.assert_allclose(feat.detach().cpu().numpy(), feat0.cpu().numpy(), rtol=1e-5, atol=1e-5)
+    feat.sum().backward()
+    assert float(tl[0][0].grad.abs().sum()) > 0
+
+
+def test_tensor_on_other_device_is_rejected():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    x = torch.zeros((1, 16, 3), device="cuda:1")
+    with pytest.raises(RuntimeError):
+        S.farthest_point_sample(4, x)
+
+
 def test_pointnet_fp_module(rng):
     b, n, m, c = 2, 512, 128, 64
     x1, x2 = unit_ball(rng, b, n), unit_ball(rng, b, m)
@@ -852,15 +1005,15 @@ def test_dense_ex_fused_softmax(rng):
     np.testing.assert_allclose(stats.cpu().numpy().max(-1), S.max(-1), rtol=1e-5, atol=1e-5)
 
 
-@pytest.mark.skip(reason="csrc/attention_tc.cu was written after the round-1 GPU budget was spent: validate it first thing in round 2")
-def test_attention_fused_experimental(rng):
-    """softmax(q.k^T).v in one tcgen05 kernel (no (b,m,m) score tensor) vs a float64 softmax."""
-    from dispu_b200.dense import attention_fused_experimental
-    b, m = 2, 512
+@pytest.mark.parametrize("b,m,scale", [(2, 512, 0.7), (3, 1024, 0.7), (1, 4096, 0.4), (2, 128, 2.0)])
+def test_attention_fused(rng, b, m, scale):
+    """softmax(q.k^T).v in one tcgen05 kernel (no (b,m,m) score tensor) vs a float64 softmax
+    (PointNonLocalCell, Common/ops.py:326-339)."""
+    from dispu_b200.dense import attention_fused
     kvq = np.zeros((b, m, 256), np.float32)
     kvq[..., :128] = rng.standard_normal((b, m, 128))
-    kvq[..., 128:192] = rng.standard_normal((b, m, 64)) * 0.7
-    got = attention_fused_experimental(T(kvq)).cpu().numpy()
+    kvq[..., 128:192] = rng.standard_normal((b, m, 64)) * scale
+    got = attention_fused(T(kvq)).cpu().numpy()
     S = np.einsum("bik,bjk->bij", kvq[..., 128:192].astype(np.float64), kvq[..., :64].astype(np.float64))
     P = np.exp(S - S.max(-1, keepdims=True))
     P /= P.sum(-1, keepdims=True)

@@ -179,6 +179,34 @@ def test_sa_mlp_against_numpy(rng):
     np.testing.assert_allclose(O.sa_mlp(xyz, pts, new_xyz, idx, ws, bs, 0), x.max(2), rtol=1e-4, atol=1e-5)
 
 
+def test_sa_module_numpy_restatement_matches_c_oracle(rng):
+    """The float64 numpy restatement of pointnet_sa_module's body (pooling variants, mlp2, BN: oracle.sa_module) agrees with
+    the C oracle's orc_sa_mlp on the form both cover (max pooling, [xyz | points] and the _msg channel order), and its
+    variants satisfy the identities the reference's definitions imply (pointnet_util.py:122-141)."""
+    b, n, m, ns, c = 2, 200, 16, 8, 5
+    xyz = unit_ball(rng, b, n)
+    pts = rng.standard_normal((b, n, c)).astype(np.float32)
+    new_xyz = O.gather_point(xyz, O.farthest_point_sample(m, xyz))
+    idx, _ = O.query_ball_point(0.5, ns, xyz, new_xyz)
+    ws = [(rng.standard_normal((3 + c, 16)) / 3).astype(np.float32), (rng.standard_normal((16, 12)) / 4).astype(np.float32)]
+    bs = [rng.standard_normal(16).astype(np.float32) * 0.1, None]
+    layers = list(zip(ws, bs))
+    for layout in (0, 1):
+        np.testing.assert_allclose(O.sa_module(xyz, pts, new_xyz, idx, layers, layout=layout),
+                                   O.sa_mlp(xyz, pts, new_xyz, idx, ws, bs, layout), rtol=1e-5, atol=1e-5)
+    mx = O.sa_module(xyz, pts, new_xyz, idx, layers, pooling="max")
+    av = O.sa_module(xyz, pts, new_xyz, idx, layers, pooling="avg")
+    both = O.sa_module(xyz, pts, new_xyz, idx, layers, pooling="max_and_avg")
+    np.testing.assert_array_equal(both, np.concatenate([mx, av], -1))
+    mn = O.sa_module(xyz, pts, new_xyz, idx, layers, pooling="min")
+    assert (mn <= 0).all() and (-mn <= av + 1e-12).all() and (av <= mx + 1e-12).all()  # post-ReLU: 0 <= min <= avg <= max
+    wa = O.sa_module(xyz, pts, new_xyz, idx, layers, pooling="weighted_avg")
+    assert (wa <= mx + 1e-12).all() and (wa >= -mn - 1e-12).all()
+    # identity BN statistics leave the layer unchanged up to the epsilon
+    ident = (np.ones(16, np.float32), np.zeros(16, np.float32), np.zeros(16, np.float32), np.ones(16, np.float32) - 1e-3)
+    np.testing.assert_allclose(O.sa_module(xyz, pts, new_xyz, idx, [(ws[0], bs[0], ident), (ws[1], bs[1])]), mx, rtol=1e-6, atol=1e-7)  # float32(1 - 1e-3) + 1e-3 is 1 to ~2e-8
+
+
 def test_selection_sort_known_answer():
     """tf_ops/grouping/selection_sort.cpp:65-94: k=3 of a 2x2x4 descending ramp -> idx 3 2 1 ..."""
     dist = np.arange(16, 0, -1, dtype=np.float32).reshape(2, 2, 4)

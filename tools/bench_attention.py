@@ -1,0 +1,63 @@
+"""Development probe: non-local attention softmax(q.k^T).v at the c2 / c4 shapes — the two batched dense products with
+the folded softmax (round-1 product path) vs the single tcgen05 kernel (csrc/attention_tc.cu).  CUDA events, L2 flushed."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from dispu_b200.dense import BatchedOperand, attention_fused  # noqa: E402
+
+dev = "cuda"
+flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts))
+
+
+def two_products(kvq):
+    b, m, _ = kvq.shape
+    nb = m // 256
+    q = kvq[..., 128:192]
+    kop = BatchedOperand(b * nb, 64, 256, dev).pack(kvq, 0, 1, 256, 256 * 256)
+    stats = torch.empty((b, m, 2 * nb), dtype=torch.float32, device=dev)
+    scores = kop.matmul(q, n_blocks=nb, stats_out=stats)
+    vop = BatchedOperand(b, m, 64, dev).pack(kvq, 64, 256, 1, m * 256)
+    return vop.matmul(scores, softmax_stats=stats)
+
+
+def main():
+    rows = []
+    for b, m in [(32, 1024), (32, 4096), (8, 1024)]:
+        kvq = torch.randn((b, m, 256), device=dev)
+        kvq[..., 128:192] *= 0.5
+        a = two_products(kvq)
+        f = attention_fused(kvq)
+        err = float((a - f).abs().max())
+        r = {"b": b, "m": m, "two_products_ms": timeit(lambda: two_products(kvq)), "fused_ms": timeit(lambda: attention_fused(kvq)),
+             "max_abs_diff": err, "alg_TFLOPs_fused": None}
+        r["alg_TFLOPs_fused"] = 4.0 * b * m * m * 64 / r["fused_ms"] / 1e9
+        rows.append(r)
+        print(json.dumps(r), flush=True)
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(rows, open("gpurun_out/bench_attention.json", "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
