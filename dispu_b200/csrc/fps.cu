@@ -286,13 +286,38 @@ static int launch_onchip(int b, int n, int m, const float *inp, int *out, cudaSt
     return finish_launch();
 }
 
-constexpr int kFpsOnchipCapacity = 16 * 1024 * 8;
+
+// Largest cluster the 1024-thread kernel can be launched with on THIS device / partition (16 needs the non-portable
+// cluster size; a MIG slice or a future part may only give 8).  Queried once; decides the on-chip capacity the
+// wrappers see, so "no temp needed" is never promised for a cloud that would have to fall back to the global kernel.
+static int fps_max_cluster() {
+    static const int cached = [] {
+        auto kern = fps_onchip_kernel<1024, 8, 16>;
+        const size_t smem = sizeof(float4) * 1024 * 8;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+            cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return 8;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(16);
+        cfg.blockDim = dim3(1024);
+        cfg.dynamicSmemBytes = smem;
+        int c = 0;
+        if (cudaOccupancyMaxPotentialClusterSize(&c, kern, &cfg) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return 8;
+        }
+        return c >= 16 ? 16 : 8;
+    }();
+    return cached;
+}
 
 }  // namespace dispu
 
 using namespace dispu;
 
-extern "C" int dispu_fps_onchip_capacity(void) { return kFpsOnchipCapacity; }
+extern "C" int dispu_fps_onchip_capacity(void) { return fps_max_cluster() * 1024 * 8; }
 
 extern "C" int dispu_fps(int b, int n, int m, const float *inp, float *temp, int *out, dispu_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -311,17 +336,18 @@ extern "C" int dispu_fps(int b, int n, int m, const float *inp, float *temp, int
     // one cluster per cloud: the fewest CTAs that hold the cloud (<= 8 points per thread), then more
     // CTAs with fewer points each while that still leaves the GPU under-filled (small batches: the
     // per-step scan shrinks with P, the exchange cost barely grows with C).
-    if (n <= kFpsOnchipCapacity) {
+    const int max_c = fps_max_cluster();
+    if (n <= max_c * 8192) {
         int C = 2;
         while (C * 8192 < n) C *= 2;
         int P = ceil_div(n, C * 1024);
-        while (C < 16 && P > 1 && (long long)b * C * 2 <= kNumSMs) {
+        while (C < max_c && P > 1 && (long long)b * C * 2 <= kNumSMs) {
             C *= 2;
             P = ceil_div(n, C * 1024);
         }
         if (const char *force = getenv("DISPU_FPS_FORCE_C")) {  // tuning hook (tools/), not a product knob
             const int fc = atoi(force);
-            if ((fc == 2 || fc == 4 || fc == 8 || fc == 16) && (long long)fc * 8192 >= n) {
+            if ((fc == 2 || fc == 4 || fc == 8 || fc == 16) && fc <= max_c && (long long)fc * 8192 >= n) {
                 C = fc;
                 P = ceil_div(n, C * 1024);
             }
@@ -335,13 +361,7 @@ extern "C" int dispu_fps(int b, int n, int m, const float *inp, float *temp, int
         DISPU_FPS_CASE(8, 1) DISPU_FPS_CASE(8, 2) DISPU_FPS_CASE(8, 4) DISPU_FPS_CASE(8, 8)
         DISPU_FPS_CASE(16, 1) DISPU_FPS_CASE(16, 2) DISPU_FPS_CASE(16, 4) DISPU_FPS_CASE(16, 8)
 #undef DISPU_FPS_CASE
-        if (rc == DISPU_OK) return rc;
-        if (C == 16) {  // 16-CTA clusters unavailable on this part/partition: retry with 8 if it fits
-            (void)cudaGetLastError();
-            if (n <= 8 * 8192) return launch_onchip<1024, 8, 8>(b, n, m, inp, out, stream);
-        } else {
-            return rc;
-        }
+        return rc;
     }
     DISPU_REQUIRE(temp != nullptr, DISPU_EWORKSPACE);
     count_launch();

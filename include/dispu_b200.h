@@ -49,7 +49,9 @@ uint64_t dispu_launch_count(void);
  * tf_sampling_g.cu:203) and its kernel (tf_sampling_g.cu:105-170).  inp (b,n,3) -> out (b,m),
  * out[:,0]=0, bit-exact tie order of the reference.  `temp` is the
  * reference's (32,n) float scratch (tf_sampling.cpp:115); it is only touched when n exceeds
- * what fits on chip (n > dispu_fps_onchip_capacity()) and may be NULL otherwise. */
+ * what fits on chip (n > dispu_fps_onchip_capacity()) and may be NULL otherwise.  The capacity is
+ * 131072 points where 16-CTA (non-portable) clusters can be launched and 65536 where only the portable
+ * 8-CTA clusters can (queried once per process with cudaOccupancyMaxPotentialClusterSize). */
 int dispu_fps(int b, int n, int m, const float *inp, float *temp, int *out, dispu_stream_t stream);
 int dispu_fps_onchip_capacity(void);
 

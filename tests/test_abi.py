@@ -36,7 +36,7 @@ def test_binding_covers_header(so):
     assert sorted(_lib.SIGNATURES) == declared_symbols()
     l = _lib.lib()
     assert l.dispu_abi_version() == 1
-    assert l.dispu_fps_onchip_capacity() == 131072
+    assert l.dispu_fps_onchip_capacity() in (65536, 131072)  # 131072 where 16-CTA clusters launch (B200); 65536 otherwise / without a device
     assert b"invalid" in l.dispu_error_string(-1)
     assert l.dispu_chamfer_workspace_bytes(32, 1024, 1024) == 8 * 32 * 2 * 4 + 8 * 32
 

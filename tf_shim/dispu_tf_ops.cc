@@ -51,7 +51,7 @@ REGISTER_OP("ProbSample").Input("inp: float32").Input("inpr: float32").Output("o
 REGISTER_OP("FarthestPointSample").Attr("npoint: int").Input("inp: float32").Output("out: int32")
     .SetShapeFn([](InferenceContext *c) {
       ShapeHandle s; TF_RETURN_IF_ERROR(c->WithRank(c->input(0), 3, &s));
-      int npoint; TF_RETURN_IF_ERROR(c->GetAttr("npoint", &npoint));
+      int npoint = 0; TF_RETURN_IF_ERROR(c->GetAttr("npoint", &npoint));
       c->set_output(0, c->MakeShape({c->Dim(s, 0), npoint})); return Status::OK(); });
 REGISTER_OP("GatherPoint").Input("inp: float32").Input("idx: int32").Output("out: float32")
     .SetShapeFn([](InferenceContext *c) {
@@ -149,7 +149,7 @@ REGISTER_OP("QueryBallPoint").Attr("nsample: int").Input("xyz1: float32").Input(
     .Input("radius: float32").Output("idx: int32").Output("pts_cnt: int32")
     .SetShapeFn([](InferenceContext *c) {
       ShapeHandle q; TF_RETURN_IF_ERROR(c->WithRank(c->input(1), 3, &q));
-      int nsample; TF_RETURN_IF_ERROR(c->GetAttr("nsample", &nsample));
+      int nsample = 0; TF_RETURN_IF_ERROR(c->GetAttr("nsample", &nsample));
       c->set_output(0, c->MakeShape({c->Dim(q, 0), c->Dim(q, 1), nsample}));
       c->set_output(1, c->MakeShape({c->Dim(q, 0), c->Dim(q, 1)})); return Status::OK(); });
 REGISTER_OP("SelectionSort").Attr("k: int").Input("dist: float32").Output("outi: int32").Output("out: float32")
