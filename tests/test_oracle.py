@@ -92,6 +92,55 @@ def test_golden_gpu_query_ball_and_nn(gc, gg, tag):
     assert np.array_equal(d2, gg[f"{tag}_nn_d2"]) and np.array_equal(i2, gg[f"{tag}_nn_i2"])
 
 
+# ---- real clouds shipped with the reference (data/test/*.xyz, output/*_X4.xyz): goldens from the reference host code ----
+@pytest.fixture(scope="module")
+def real():
+    return np.load(os.path.join(GOLD, "real_clouds.npz"))
+
+
+def knn_dist(a, idx):
+    g = np.take_along_axis(a[:, None], idx[..., None].astype(np.int64), 2)
+    d = a[:, :, None, :] - g
+    return ((d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]).astype(np.float32)
+
+
+@pytest.mark.parametrize("name", ["Icosahedron", "fandisk"])
+def test_real_clouds_oracle_vs_reference_host_code(real, name):
+    """Icosahedron.xyz has exact distance ties (symmetry) — the tie-break stressor SURVEY.md §8c names."""
+    x, y = real[name], real[name + "_X4"]
+    d1, i1, d2, i2 = O.nn_distance(x, y, mode=O.CPU)
+    assert np.array_equal(d1, real[name + "_nn_d1"]) and np.array_equal(i1, real[name + "_nn_i1"])
+    assert np.array_equal(d2, real[name + "_nn_d2"]) and np.array_equal(i2, real[name + "_nn_i2"])
+    d, i = O.three_nn(y, x)
+    assert np.array_equal(d, real[name + "_3nn_d"]) and np.array_equal(i, real[name + "_3nn_i"])
+    idx, _ = O.query_ball_point(0.2, 32, x, x[:, ::8].copy(), mode=O.CPU, fill_empty=False)
+    assert np.array_equal(idx, real[name + "_qbp_r0.2_ns32"])
+    # nanoflann orders exactly equal distances by tree traversal: distances must agree everywhere, indices wherever
+    # a neighbour's distance is distinct from its rank neighbours'
+    d, i = O.knn(16, x, x)
+    gi = real[name + "_knn16"]
+    assert np.array_equal(d, knn_dist(x, gi))
+    uniq = np.ones_like(d, bool)
+    uniq[..., 1:] &= d[..., 1:] != d[..., :-1]
+    uniq[..., :-1] &= d[..., :-1] != d[..., 1:]
+    uniq[..., -1] = False  # the last slot may tie with the first neighbour left out
+    assert np.array_equal(i[uniq], gi[uniq]) and uniq.mean() > 0.5
+
+
+@pytest.mark.parametrize("name", ["Icosahedron", "fandisk"])
+def test_real_clouds_evaluate_metrics_golden(real, name):
+    """evaluate.py:34-39,153-165 (CD / HD of the reference's own 4x output against its input cloud) through the oracle."""
+    def norm(pc):
+        c = pc.mean(axis=1, keepdims=True, dtype=np.float32)
+        pc = (pc - c).astype(np.float32)
+        return (pc / np.sqrt((pc * pc).sum(-1, keepdims=True, dtype=np.float32)).max(axis=1, keepdims=True)).astype(np.float32)
+    p, g = norm(real[name + "_X4"]), norm(real[name])
+    d_f, _, d_b, _ = O.nn_distance(p, g, mode=O.CPU)
+    assert float(d_f.astype(np.float64).mean() + d_b.astype(np.float64).mean()) == pytest.approx(float(real[name + "_eval_cd"]), rel=1e-12)
+    assert float(d_f.max() + d_b.max()) == pytest.approx(float(real[name + "_eval_hd"]), rel=1e-7)
+    assert 0 < float(real[name + "_eval_cd"]) < 1e-2  # a 4x upsampling of the same surface sits close to it
+
+
 # ---- live reference host loops (present where oracle/build_ref.sh ran) -----------------------
 needs_ref = pytest.mark.skipif(not (R.available("cpu") and R.available("knn")), reason="oracle/_ref not built")
 
