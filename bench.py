@@ -238,25 +238,28 @@ def run_product(args, rank, world, local_rank):
     gen = Generator(device=dev)
     out_c = torch.zeros((4,), dtype=torch.float32, device=dev)
     out_f = torch.zeros((4,), dtype=torch.float32, device=dev)
-    partial = torch.zeros((4,), dtype=torch.float32, device=dev)  # [sum cd_coarse, sum cd_fine, hd_coarse, hd_fine]
+    # [sum cd_coarse, sum cd_fine | hd_coarse, hd_fine]: the fused Chamfer kernels deposit their partials here themselves
+    # (dispu_chamfer_ex), the first two floats are what the ONE collective of the path sums over the ranks
+    partial = torch.zeros((4,), dtype=torch.float32, device=dev)
     h_loss = torch.zeros((4,), dtype=torch.float32).pin_memory()
     flush = torch.empty((192 * 1024 * 1024 // 4,), dtype=torch.float32, device=dev)  # > 126 MB L2
-
-    def step_body():
-        with torch.no_grad():
-            coarse, fine = gen(d_inp)
-            loss_utils.chamfer_hausdorff(coarse, d_gt, out=out_c)
-            loss_utils.chamfer_hausdorff(fine, d_gt, out=out_f)
-            partial[0] = out_c[2]
-            partial[1] = out_f[2]
-            partial[2] = out_c[1]
-            partial[3] = out_f[1]
+    in_graph_collective = world > 1 and not args.eager_collective
 
     def allreduce():
         if world > 1:
-            # ONE collective on the path: sum of the per-rank Chamfer partials;
+            # ONE collective on the path: sum of the per-rank Chamfer partials, enqueued on the step's
+            # stream — inside the captured CUDA graph, so a replay contains the ncclAllReduce kernel and no host work;
             # (Hausdorff is only logged by the trainer — max over ranks is taken on the host from the same 4 floats)
             dist.all_reduce(partial[:2], op=dist.ReduceOp.SUM)
+
+    def step_body():
+        with torch.no_grad():
+            # the coarse cloud's loss runs on a side stream as soon as the coarse cloud exists (overlaps PointShuffle2)
+            coarse, fine = gen(d_inp, on_coarse=lambda c: loss_utils.chamfer_hausdorff(
+                c, d_gt, out=out_c, sum_out=partial[0:1], max_out=partial[2:3]))
+            loss_utils.chamfer_hausdorff(fine, d_gt, out=out_f, sum_out=partial[1:2], max_out=partial[3:4])
+            if in_graph_collective:
+                allreduce()
 
     stream = torch.cuda.Stream(device=dev)
     with torch.cuda.stream(stream):
@@ -282,7 +285,8 @@ def run_product(args, rank, world, local_rank):
                 graph.replay()
             else:
                 step_body()
-            allreduce()
+            if not in_graph_collective:
+                allreduce()
 
         def barrier():
             torch.cuda.synchronize(dev)
@@ -348,7 +352,10 @@ def run_product(args, rank, world, local_rank):
                        "batch_per_gpu": B, "n_in": N_IN, "up_ratio": UP, "cuda_graph": graph is not None,
                        "l2": "flushed between timed steps (192 MiB memset outside the event pairs)",
                        "weights": "Xavier-uniform seed 7, zero bias (random init; no checkpoint offline)",
-                       "sharding": f"batch-sharded x{world}, one all-reduce of 2 Chamfer partial sums" if world > 1 else "single GPU"},
+                       "sharding": (f"batch-sharded x{world}, one all-reduce of 2 Chamfer partial sums "
+                                    f"({'captured in the CUDA graph' if (in_graph_collective and graph is not None) else 'eager, after the replay'})")
+                       if world > 1 else "single GPU",
+                       "streams": "kNN of the coarse cloud and the coarse Chamfer on side streams (graph fork/join)" if gen.use_streams else "single stream"},
             "e2e": {"value": pts / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": int(h_inp.numel() * 4 + h_gt.numel() * 4), "d2h_bytes_per_step": 16},
             "gpu_launches": int(launches_per_step * args.steps),
@@ -380,6 +387,7 @@ def dominant_kernel_roofline(gen, d_inp, d_gt, stream, flush, reps=10):
     hbm, bf16_peak, which = measured_peaks()
     out_c = torch.zeros((4,), dtype=torch.float32, device=d_inp.device)
     recs = []
+    use_streams, gen.use_streams = gen.use_streams, False  # one stream: the event pairs must bracket one kernel each
     with torch.no_grad():
         for rep in range(reps + 2):
             flush.zero_()
@@ -395,6 +403,7 @@ def dominant_kernel_roofline(gen, d_inp, d_gt, stream, flush, reps=10):
             stream.synchronize()
             if prof:
                 recs.append([(k, a.elapsed_time(b)) for k, a, b in prof])
+    gen.use_streams = use_streams
     per_key = {}
     for step in recs:
         for k, ms in step:
@@ -487,6 +496,7 @@ def main():
     ap.add_argument("--impl", default="dispu", choices=["dispu", "reference"])
     ap.add_argument("--ref-sample", type=int, default=8, help="patches per CPU step (bounded sample of the batch)")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--eager-collective", action="store_true", help="issue the all-reduce from the host after the graph replay (round-1 form)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     args = ap.parse_args()
 

@@ -24,6 +24,7 @@ class DenseArgs(C.Structure):
         ("rows_per_batch", _ll), ("packed_batch_stride", _ll), ("n_blocks", _i), ("packed_block_stride", _ll),
         ("wn_xyz", _p), ("wn_w", _p), ("wn_b", _p), ("wn_scale", C.c_float),
         ("stat_out", _p), ("stat_in", _p), ("n_stat", _i),
+        ("Y2", _p), ("ldy2", _ll), ("y2_block", _i),
     ]
 
 
@@ -57,6 +58,7 @@ SIGNATURES = {
     "dispu_nn_distance_grad": ([_i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p], _i),
     "dispu_chamfer_workspace_bytes": ([_i, _i, _i], _sz),
     "dispu_chamfer": ([_i, _i, _p, _i, _p, _p, _p, _p, _p, _sz, _p], _i),
+    "dispu_chamfer_ex": ([_i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _p], _i),
     "dispu_repulsion_workspace_bytes": ([_i, _i], _sz),
     "dispu_repulsion_loss": ([_i, _i, _i, C.c_float, _p, _p, _p, _p, _sz, _p], _i),
     "dispu_uniform_workspace_bytes": ([_i, _i, _i], _sz),

@@ -11,8 +11,10 @@
 // where s_max is the largest float whose rounded square root is still below r (found once per
 // thread by stepping ulps around r*r).  NaN distances are hits in both forms.
 #include <float.h>
+#include <stdlib.h>
 
 #include "common.cuh"
+#include "tile_stage.cuh"
 
 namespace dispu {
 
@@ -30,12 +32,17 @@ __device__ __forceinline__ float ball_s_max(float r, bool &any) {
     return c;
 }
 
+// kTma: tiles land as raw AoS bytes by cp.async.bulk + mbarrier (tile_stage.cuh), double-buffered when the cloud spans
+// several tiles, and the scan reads them in place (lane k touches floats 3k..3k+2: stride 3 is conflict-free), so no
+// thread issues a staging load or store at all.  Otherwise: per-thread __ldg staging into x | y | z arrays.
+template <bool kTma>
 __global__ void __launch_bounds__(kBqThreads)
 ball_query_kernel(int n, int m, const float *__restrict__ radius, int ns, const float *__restrict__ xyz1,
                   const float *__restrict__ xyz2, int *__restrict__ idx, int *__restrict__ pts_cnt, int qpc,
                   int tile) {
-    extern __shared__ float s_pts[];  // x[tile] | y[tile] | z[tile]
+    extern __shared__ __align__(16) float s_pts[];  // x[tile] | y[tile] | z[tile]   or (kTma)   raw tile 0 [| raw tile 1]
     __shared__ int s_cnt[kBqMaxQpc], s_first[kBqMaxQpc];
+    __shared__ __align__(8) uint64_t s_bar[2];
     float *sx = s_pts, *sy = s_pts + tile, *sz = s_pts + 2 * tile;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -54,14 +61,41 @@ ball_query_kernel(int n, int m, const float *__restrict__ radius, int ns, const 
         s_cnt[q] = 0;
         s_first[q] = 0;
     }
-
-    for (int t0 = 0; t0 < n; t0 += tile) {
-        const int tn = min(tile, n - t0);
-        for (int e = tid; e < tn * 3; e += kBqThreads) {
-            const int k = e / 3, c = e - k * 3;
-            s_pts[c * tile + k] = __ldg(pts + (size_t)t0 * 3 + e);
+    const int ntiles = ceil_div(n, tile);
+    if (kTma) {
+        if (tid == 0) {
+            ts::mbar_init(&s_bar[0], 1);
+            ts::mbar_init(&s_bar[1], 1);
+            ts::fence_mbar_init();
+            ts::issue_tile(s_pts, pts, min(tile, n), &s_bar[0]);
         }
         __syncthreads();
+    }
+    int pending = -1;  // kTma: tile whose copy is in flight and has not been waited for
+
+    for (int i = 0; i < ntiles; ++i) {
+        const int t0 = i * tile;
+        const int tn = min(tile, n - t0);
+        const float *raw = s_pts;
+        if (kTma) {
+            // landing buffer (i+1)&1 was last scanned in iteration i-1, which every thread left through the
+            // __syncthreads_and below: refill it while this tile is scanned
+            if (i + 1 < ntiles) {
+                if (tid == 0)
+                    ts::issue_tile(s_pts + ((i + 1) & 1) * tile * 3, pts + (size_t)(t0 + tile) * 3, min(tile, n - t0 - tile), &s_bar[(i + 1) & 1]);
+                pending = i + 1;
+            } else {
+                pending = -1;
+            }
+            ts::mbar_wait(&s_bar[i & 1], (uint32_t)((i >> 1) & 1));
+            raw = s_pts + (i & 1) * tile * 3;
+        } else {
+            for (int e = tid; e < tn * 3; e += kBqThreads) {
+                const int k = e / 3, c = e - k * 3;
+                s_pts[c * tile + k] = __ldg(pts + (size_t)t0 * 3 + e);
+            }
+            __syncthreads();
+        }
         bool all_done = true;
         for (int q = warp; q < nq; q += kBqWarps) {
             int cnt = s_cnt[q];
@@ -73,7 +107,8 @@ ball_query_kernel(int n, int m, const float *__restrict__ radius, int ns, const 
                 const int k = k0 + lane;
                 bool hit = false;
                 if (k < tn) {
-                    const float s = d2_ref_gpu(__fsub_rn(qx, sx[k]), __fsub_rn(qy, sy[k]), __fsub_rn(qz, sz[k]));
+                    const float px = kTma ? raw[3 * k] : sx[k], py = kTma ? raw[3 * k + 1] : sy[k], pz = kTma ? raw[3 * k + 2] : sz[k];
+                    const float s = d2_ref_gpu(__fsub_rn(qx, px), __fsub_rn(qy, py), __fsub_rn(qz, pz));
                     hit = any && !(s > smax);
                 }
                 const unsigned mask = __ballot_sync(kFull, hit);
@@ -91,7 +126,10 @@ ball_query_kernel(int n, int m, const float *__restrict__ radius, int ns, const 
             all_done = all_done && (cnt >= ns);
         }
         if (__syncthreads_and(all_done)) break;
+        pending = -1;  // the next iteration waits for it
     }
+    // never leave with a bulk copy still writing into this CTA's shared memory (early exit above)
+    if (kTma && pending >= 0) ts::mbar_wait(&s_bar[pending & 1], (uint32_t)((pending >> 1) & 1));
     __syncthreads();
     for (int q = warp; q < nq; q += kBqWarps) {
         const int cnt = min(s_cnt[q], ns);
@@ -119,16 +157,25 @@ extern "C" int dispu_query_ball_point(int b, int n, int m, const float *radius, 
     qpw = qpw < 1 ? 1 : (qpw > 8 ? 8 : qpw);
     const int qpc = qpw * kBqWarps;
     const int tile = n < kBqTile ? ((n + 31) & ~31) : kBqTile;
-    const size_t smem = sizeof(float) * 3 * (size_t)tile;
+    static const bool no_tma = getenv("DISPU_NO_TMA") != nullptr;  // development switch (A/B timing)
+    const bool tma = !no_tma && ts::tma_ok(xyz1, n);
+    const size_t smem = sizeof(float) * 3 * (size_t)tile * (tma && n > tile ? 2 : 1);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(ball_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)(sizeof(float) * 3 * kBqTile));
+        cudaError_t e = cudaFuncSetAttribute(ball_query_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(sizeof(float) * 3 * kBqTile * 2));
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(ball_query_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(sizeof(float) * 3 * kBqTile));
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
     count_launch();
-    ball_query_kernel<<<dim3(ceil_div(m, qpc), b), kBqThreads, smem, stream>>>(n, m, radius, nsample, xyz1, xyz2, idx,
-                                                                              pts_cnt, qpc, tile);
+    if (tma)
+        ball_query_kernel<true><<<dim3(ceil_div(m, qpc), b), kBqThreads, smem, stream>>>(n, m, radius, nsample, xyz1, xyz2,
+                                                                                        idx, pts_cnt, qpc, tile);
+    else
+        ball_query_kernel<false><<<dim3(ceil_div(m, qpc), b), kBqThreads, smem, stream>>>(n, m, radius, nsample, xyz1, xyz2,
+                                                                                         idx, pts_cnt, qpc, tile);
     return finish_launch();
 }

@@ -113,6 +113,11 @@ struct DenseParams {
     float *stat_out;
     const float *stat_in;
     int n_stat;
+    // split output: column blocks j >= y2_block are written to Y2 (row stride ldy2) at columns (j - y2_block)*N —
+    // layers that share their input but feed different consumers keep separate (compact) output tensors
+    float *Y2;
+    long long ldy2;
+    int y2_block;
     int n_tiles, n_stages;
     long long *dbg_buf;  // development only: clock64 samples of CTA 0 (3 roles x 64 iterations x 8 slots)
     int dbg;  // development only (DISPU_DENSE_DBG): 1 = no A loads, 2 = no weight TMA, 4 = no MMA issue; results are garbage
@@ -462,7 +467,10 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
             const long long row0 = (long long)mt * 128 + q * 32;  // first row of this warp's quarter
             const long long row = row0 + lane;
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)a * 128u;
-            float *__restrict__ Y = prm.Y + (long long)(tile - mt * prm.n_blocks) * N;  // column block of this tile
+            const int blk = tile - mt * prm.n_blocks;  // column block of this tile
+            const bool to_y2 = prm.Y2 != nullptr && blk >= prm.y2_block;
+            float *__restrict__ Y = to_y2 ? prm.Y2 + (long long)(blk - prm.y2_block) * N : prm.Y + (long long)blk * N;
+            const long long ldy_t = to_y2 ? prm.ldy2 : prm.ldy;
             const float *sb = s_bias + (tile - mt * prm.n_blocks) * npad;
             const float *__restrict__ R1 = prm.R1 ? prm.R1 + (long long)(tile - mt * prm.n_blocks) * N : nullptr;  // residuals
             const float *__restrict__ R2 = prm.R2 ? prm.R2 + (long long)(tile - mt * prm.n_blocks) * N : nullptr;  // follow Y's block
@@ -589,7 +597,7 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
                                 float4 o = *reinterpret_cast<const float4 *>(stg + rr * kDnEpiStride + cq * 4);
                                 if (R1) { o.x = __fadd_rn(o.x, r1v[pass].x); o.y = __fadd_rn(o.y, r1v[pass].y); o.z = __fadd_rn(o.z, r1v[pass].z); o.w = __fadd_rn(o.w, r1v[pass].w); }
                                 if (R2) { o.x = __fadd_rn(o.x, r2v[pass].x); o.y = __fadd_rn(o.y, r2v[pass].y); o.z = __fadd_rn(o.z, r2v[pass].z); o.w = __fadd_rn(o.w, r2v[pass].w); }
-                                if (!(prm.dbg & 32)) *reinterpret_cast<float4 *>(Y + grow * prm.ldy + col) = o;
+                                if (!(prm.dbg & 32)) *reinterpret_cast<float4 *>(Y + grow * ldy_t + col) = o;
                             }
                         }
                     }
@@ -603,7 +611,7 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
                     prm.stat_out[(row * prm.n_blocks + (tile - mt * prm.n_blocks)) * 2 + half] = run_m;
             } else {
                 // narrow / unaligned outputs (e.g. the 3-channel coordinate layers): one row per thread, scalar stores
-                float *yr = Y + row * prm.ldy;
+                float *yr = Y + row * ldy_t;
                 const float *r1 = R1 ? R1 + row * prm.ldr1 : nullptr;
                 const float *r2 = R2 ? R2 + row * prm.ldr2 : nullptr;
                 for (int c0 = half * 16; c0 < npad; c0 += 32) {
@@ -691,13 +699,21 @@ extern "C" int dispu_dense_tf32x3_ex(const dispu_dense_args *a, dispu_stream_t s
     }
     const int n_blocks = a->n_blocks > 0 ? a->n_blocks : 1;
     const bool wnet = a->wn_xyz != nullptr;
-    if (n_blocks > 1) DISPU_REQUIRE(a->packed_block_stride % 16 == 0 && ldy >= (long long)n_blocks * N, DISPU_EINVAL);
+    if (n_blocks > 1)
+        DISPU_REQUIRE(a->packed_block_stride % 16 == 0 && ldy >= (long long)(a->Y2 ? a->y2_block : n_blocks) * N, DISPU_EINVAL);
     if (a->bias) DISPU_REQUIRE((long long)n_blocks * dn_npad(N) <= 1024, DISPU_EUNSUPPORTED);
     if (wnet) {
         DISPU_REQUIRE(a->gather_idx && a->wn_w, DISPU_ENULL);
         DISPU_REQUIRE(a->gather_ns == 16 && N % 32 == 0 && M % 128 == 0 && n_blocks == 1, DISPU_EUNSUPPORTED);
         DISPU_REQUIRE((a->ldy > 0 ? a->ldy : (long long)N * 16) >= (long long)N * 16 && (a->ldy % 4) == 0 &&
                           (reinterpret_cast<uintptr_t>(a->Y) & 15u) == 0, DISPU_EINVAL);
+    }
+    if (a->Y2) {
+        DISPU_REQUIRE(n_blocks > 1 && a->y2_block > 0 && a->y2_block < n_blocks && !wnet && !a->stat_out && !a->R1 && !a->R2, DISPU_EINVAL);
+        const long long ldy2 = a->ldy2 > 0 ? a->ldy2 : (long long)(n_blocks - a->y2_block) * N;
+        DISPU_REQUIRE(ldy2 >= (long long)(n_blocks - a->y2_block) * N, DISPU_EINVAL);
+        DISPU_REQUIRE(N % 4 == 0 && ldy % 4 == 0 && ldy2 % 4 == 0 &&
+                          ((reinterpret_cast<uintptr_t>(a->Y) | reinterpret_cast<uintptr_t>(a->Y2)) & 15u) == 0, DISPU_EUNSUPPORTED);
     }
     if (a->stat_out) DISPU_REQUIRE(!wnet && N % 4 == 0 && ldy % 4 == 0 && (reinterpret_cast<uintptr_t>(a->Y) & 15u) == 0, DISPU_EUNSUPPORTED);
     if (a->stat_in) DISPU_REQUIRE(!a->gather_idx && a->n_stat > 0 && K % 32 == 0, DISPU_EUNSUPPORTED);
@@ -739,6 +755,8 @@ extern "C" int dispu_dense_tf32x3_ex(const dispu_dense_args *a, dispu_stream_t s
     p.stat_out = reinterpret_cast<float *>(a->stat_out);
     p.stat_in = reinterpret_cast<const float *>(a->stat_in);
     p.n_stat = a->n_stat;
+    p.Y2 = a->Y2; p.y2_block = a->y2_block;
+    p.ldy2 = a->ldy2 > 0 ? a->ldy2 : (long long)(n_blocks - a->y2_block) * N;
     if (wnet) p.ldy = a->ldy > 0 ? a->ldy : (long long)N * 16;
     p.n_tiles = n_tiles; p.n_stages = stages;
     {

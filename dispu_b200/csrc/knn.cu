@@ -15,18 +15,23 @@
 // (statically indexed, strict '<' insertion so equal distances keep the lower index first — the
 // order of tf.nn.top_k and of the reference's cascades).  Distances use the unfused host-loop
 // contraction (d2_ref_cpu) so they are bit-identical to nanoflann's / threenn_cpu's floats.
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "tile_stage.cuh"
 
 namespace dispu {
 
 constexpr int kKnnThreads = 128;
 constexpr int kKnnTile = 2048;  // float4 points per tile (32 KB)
 
-template <int KT>
+template <int KT, bool kTma>
 __global__ void __launch_bounds__(kKnnThreads)
 knn_kernel(int n, int m, int k, const float *__restrict__ data, const float *__restrict__ query,
            float *__restrict__ dist, int *__restrict__ idx) {
     __shared__ float4 s_tile[kKnnTile];
+    extern __shared__ __align__(16) float s_raw[];  // kTma: one or two 24 KB landing buffers (cp.async.bulk)
+    __shared__ __align__(8) uint64_t s_bar[2];
     const int cloud = blockIdx.y;
     const int j = blockIdx.x * kKnnThreads + threadIdx.x;
     const float *pts = data + (size_t)cloud * n * 3;
@@ -43,14 +48,11 @@ knn_kernel(int n, int m, int k, const float *__restrict__ data, const float *__r
         bd[i] = __int_as_float(0x7f800000);  // +inf
         bi[i] = 0;
     }
-    for (int t0 = 0; t0 < n; t0 += kKnnTile) {
-        const int tn = min(kKnnTile, n - t0);
-        __syncthreads();
-        for (int e = threadIdx.x; e < tn; e += kKnnThreads) {
-            const float *p = pts + (size_t)(t0 + e) * 3;
-            s_tile[e] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
-        }
-        __syncthreads();
+    const int ntiles = ceil_div(n, kKnnTile);
+    ts::stage_begin<kTma>(s_raw, s_bar, pts, n, kKnnTile);
+    for (int ti = 0; ti < ntiles; ++ti) {
+        const int t0 = ti * kKnnTile;
+        const int tn = ts::stage_tile<kTma>(s_tile, s_raw, s_bar, pts, n, kKnnTile, ti, ntiles);
         if (active) {
             for (int e = 0; e < tn; ++e) {
                 const float4 p = s_tile[e];
@@ -137,10 +139,13 @@ __device__ __noinline__ void knn_insertion_scan(int n, int k, const float *__res
     }
 }
 
+template <bool kTma>
 __global__ void __launch_bounds__(kKsWarps * 32)
 knn_select_kernel(int n, int m, int k, const float *__restrict__ data, const float *__restrict__ query,
                   float *__restrict__ dist, int *__restrict__ idx) {
     __shared__ float4 s_tile[kKsChunk];
+    extern __shared__ __align__(16) float s_raw[];  // kTma: one or two 12 KB landing buffers (cp.async.bulk)
+    __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ float s_bd[kKsWarps][kKsCap];
     __shared__ int s_bi[kKsWarps][kKsCap];
     __shared__ float s_od[kKsWarps][32];
@@ -165,14 +170,11 @@ knn_select_kernel(int n, int m, int k, const float *__restrict__ data, const flo
         const float *q = query + ((size_t)cloud * m + j) * 3;
         qx[u] = __ldg(q); qy[u] = __ldg(q + 1); qz[u] = __ldg(q + 2);
     }
-    for (int t0 = 0; t0 < n; t0 += kKsChunk) {
-        const int tn = min(kKsChunk, n - t0);
-        __syncthreads();
-        for (int e = threadIdx.x; e < tn; e += kKsWarps * 32) {
-            const float *p = pts + (size_t)(t0 + e) * 3;
-            s_tile[e] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
-        }
-        __syncthreads();
+    const int ntiles = ceil_div(n, kKsChunk);
+    ts::stage_begin<kTma>(s_raw, s_bar, pts, n, kKsChunk);
+    for (int ti = 0; ti < ntiles; ++ti) {
+        const int t0 = ti * kKsChunk;
+        const int tn = ts::stage_tile<kTma>(s_tile, s_raw, s_bar, pts, n, kKsChunk, ti, ntiles);
         if (q0 >= m) continue;
 #pragma unroll 1
         for (int u = 0; u < kKsQueriesPerWarp; ++u) {
@@ -361,11 +363,28 @@ knn_warp_kernel(int n, int m, int k, const float *__restrict__ data, const float
 
 // The KT-slot list holds the KT smallest; the first k of them are the k smallest, so running
 // with KT >= k is exact.
+// dynamic shared memory of a kTma launch: two landing buffers when the cloud spans several tiles, else one
+static size_t landing_bytes(int n, int tile_pts) { return (size_t)(n > tile_pts ? 2 : 1) * tile_pts * 12; }
+
+static bool knn_use_tma(const float *data, int n) {
+    static const bool no_tma = getenv("DISPU_NO_TMA") != nullptr;  // development switch (A/B timing)
+    return !no_tma && ts::tma_ok(data, n);
+}
+
 template <int KT>
 static int launch_knn(int b, int n, int m, int k, const float *data, const float *query, float *dist, int *idx,
                       cudaStream_t stream) {
-    count_launch();
-    knn_kernel<KT><<<dim3(ceil_div(m, kKnnThreads), b), kKnnThreads, 0, stream>>>(n, m, k, data, query, dist, idx);
+    const dim3 grid(ceil_div(m, kKnnThreads), b);
+    if (knn_use_tma(data, n)) {
+        const size_t smem = landing_bytes(n, kKnnTile);
+        const cudaError_t e = cudaFuncSetAttribute(knn_kernel<KT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kKnnTile * 12);
+        if (e != cudaSuccess) return (int)e;
+        count_launch();
+        knn_kernel<KT, true><<<grid, kKnnThreads, smem, stream>>>(n, m, k, data, query, dist, idx);
+    } else {
+        count_launch();
+        knn_kernel<KT, false><<<grid, kKnnThreads, 0, stream>>>(n, m, k, data, query, dist, idx);
+    }
     return finish_launch();
 }
 
@@ -373,10 +392,13 @@ static int launch_knn(int b, int n, int m, int k, const float *data, const float
 // The reference compares in double against 1e40; for float inputs that is the float order with a
 // +inf start (a finite float is always < 1e40, inf/NaN never are), and float(1e40) = +inf is what
 // it stores when fewer than three known points exist.
+template <bool kTma>
 __global__ void __launch_bounds__(kKnnThreads)
 three_nn_kernel(int n, int m, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
                 float *__restrict__ dist, int *__restrict__ idx) {
     __shared__ float4 s_tile[kKnnTile];
+    extern __shared__ __align__(16) float s_raw[];  // kTma: one or two 24 KB landing buffers (cp.async.bulk)
+    __shared__ __align__(8) uint64_t s_bar[2];
     const int cloud = blockIdx.y;
     const int j = blockIdx.x * kKnnThreads + threadIdx.x;
     const float *known = xyz2 + (size_t)cloud * m * 3;
@@ -389,14 +411,11 @@ three_nn_kernel(int n, int m, const float *__restrict__ xyz1, const float *__res
     const float inf = __int_as_float(0x7f800000);
     float b1 = inf, b2 = inf, b3 = inf;
     int i1 = 0, i2 = 0, i3 = 0;
-    for (int t0 = 0; t0 < m; t0 += kKnnTile) {
-        const int tn = min(kKnnTile, m - t0);
-        __syncthreads();
-        for (int e = threadIdx.x; e < tn; e += kKnnThreads) {
-            const float *p = known + (size_t)(t0 + e) * 3;
-            s_tile[e] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
-        }
-        __syncthreads();
+    const int ntiles = ceil_div(m, kKnnTile);
+    ts::stage_begin<kTma>(s_raw, s_bar, known, m, kKnnTile);
+    for (int ti = 0; ti < ntiles; ++ti) {
+        const int t0 = ti * kKnnTile;
+        const int tn = ts::stage_tile<kTma>(s_tile, s_raw, s_bar, known, m, kKnnTile, ti, ntiles);
         if (active) {
             for (int e = 0; e < tn; ++e) {
                 const float4 p = s_tile[e];
@@ -433,9 +452,16 @@ extern "C" int dispu_knn(int b, int n, int m, int k, const float *xyz1, const fl
     DISPU_REQUIRE(xyz1 && xyz2 && idx, DISPU_ENULL);
     DISPU_REQUIRE(b <= 65535, DISPU_EUNSUPPORTED);
     if (k <= 32) {
-        count_launch();
-        knn_select_kernel<<<dim3(ceil_div(m, kKsWarps * kKsQueriesPerWarp), b), kKsWarps * 32, 0, stream>>>(n, m, k, xyz1, xyz2,
-                                                                                                  dist, idx);
+        const dim3 grid(ceil_div(m, kKsWarps * kKsQueriesPerWarp), b);
+        if (knn_use_tma(xyz1, n)) {
+            const cudaError_t e = cudaFuncSetAttribute(knn_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kKsChunk * 12);
+            if (e != cudaSuccess) return (int)e;
+            count_launch();
+            knn_select_kernel<true><<<grid, kKsWarps * 32, landing_bytes(n, kKsChunk), stream>>>(n, m, k, xyz1, xyz2, dist, idx);
+        } else {
+            count_launch();
+            knn_select_kernel<false><<<grid, kKsWarps * 32, 0, stream>>>(n, m, k, xyz1, xyz2, dist, idx);
+        }
         return finish_launch();
     }
     if (k <= 4) return launch_knn<4>(b, n, m, k, xyz1, xyz2, dist, idx, stream);
@@ -454,6 +480,11 @@ extern "C" int dispu_three_nn(int b, int n, int m, const float *xyz1, const floa
     DISPU_REQUIRE(xyz1 && xyz2 && dist && idx, DISPU_ENULL);
     DISPU_REQUIRE(b <= 65535, DISPU_EUNSUPPORTED);
     count_launch();
-    three_nn_kernel<<<dim3(ceil_div(n, kKnnThreads), b), kKnnThreads, 0, stream>>>(n, m, xyz1, xyz2, dist, idx);
+    if (knn_use_tma(xyz2, m)) {
+        const cudaError_t e = cudaFuncSetAttribute(three_nn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kKnnTile * 12);
+        if (e != cudaSuccess) return (int)e;
+        three_nn_kernel<true><<<dim3(ceil_div(n, kKnnThreads), b), kKnnThreads, landing_bytes(m, kKnnTile), stream>>>(n, m, xyz1, xyz2, dist, idx);
+    } else
+        three_nn_kernel<false><<<dim3(ceil_div(n, kKnnThreads), b), kKnnThreads, 0, stream>>>(n, m, xyz1, xyz2, dist, idx);
     return finish_launch();
 }

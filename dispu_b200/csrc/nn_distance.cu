@@ -16,7 +16,10 @@
 // minima to (sum, max) in a fixed order and stores one partial; a second tiny kernel reduces the
 // partials in a fixed order -> per-cloud cd/hd and the batch mean / max / sum.  No float atomics,
 // so results are run-to-run deterministic.
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "tile_stage.cuh"
 
 namespace dispu {
 
@@ -24,22 +27,31 @@ constexpr int kNnThreads = 256;
 constexpr int kNnTile = 1024;  // float4 candidates per tile (16 KB)
 
 // One thread = one query of direction `dir` (0: xyz1 -> xyz2, 1: xyz2 -> xyz1).
-template <bool kReduce>
+// kTma: candidate tiles land as raw AoS bytes by cp.async.bulk + mbarrier, double-buffered (tile_stage.cuh), and are
+// widened to the float4 tile the inner loop broadcasts; otherwise per-thread __ldg staging.
+template <bool kTma>
 __global__ void __launch_bounds__(kNnThreads)
 nn_distance_kernel(int n, int m, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
                    float *__restrict__ dist1, int *__restrict__ idx1, float *__restrict__ dist2,
-                   int *__restrict__ idx2, float2 *__restrict__ partials, int chunks) {
+                   int *__restrict__ idx2) {
     __shared__ float4 s_tile[kNnTile];
-    __shared__ float s_red[2][kNnThreads / 32];
+    __shared__ __align__(16) float s_raw[kTma ? 2 * kNnTile * 3 : 4];
+    __shared__ __align__(8) uint64_t s_bar[2];
     const int cloud = blockIdx.y, dir = blockIdx.z;
     const int nq = dir == 0 ? n : m, nc = dir == 0 ? m : n;
-    if ((int)blockIdx.x * kNnThreads >= nq) {  // this direction has fewer query chunks
-        if (kReduce && threadIdx.x == 0 && (int)blockIdx.x < chunks)
-            partials[((size_t)cloud * 2 + dir) * chunks + blockIdx.x] = make_float2(0.f, -1.f);
-        return;
-    }
+    if ((int)blockIdx.x * kNnThreads >= nq) return;  // this direction has fewer query chunks
     const float *qs = (dir == 0 ? xyz1 : xyz2) + (size_t)cloud * nq * 3;
     const float *cs = (dir == 0 ? xyz2 : xyz1) + (size_t)cloud * nc * 3;
+    const int ntiles = ceil_div(nc, kNnTile);
+    if (kTma) {
+        if (threadIdx.x == 0) {
+            ts::mbar_init(&s_bar[0], 1);
+            ts::mbar_init(&s_bar[1], 1);
+            ts::fence_mbar_init();
+            ts::issue_tile(s_raw, cs, min(kNnTile, nc), &s_bar[0]);
+        }
+        __syncthreads();
+    }
     const int j = blockIdx.x * kNnThreads + threadIdx.x;
     const bool active = j < nq;
     float qx = 0.f, qy = 0.f, qz = 0.f;
@@ -48,12 +60,22 @@ nn_distance_kernel(int n, int m, const float *__restrict__ xyz1, const float *__
     }
     float best = __int_as_float(0x7f800000);
     int bi = 0;
-    for (int t0 = 0; t0 < nc; t0 += kNnTile) {
+    for (int i = 0; i < ntiles; ++i) {
+        const int t0 = i * kNnTile;
         const int tn = min(kNnTile, nc - t0);
-        __syncthreads();
-        for (int e = threadIdx.x; e < tn; e += kNnThreads) {
-            const float *p = cs + (size_t)(t0 + e) * 3;
-            s_tile[e] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
+        if (i > 0) __syncthreads();
+        if (kTma) {
+            if (threadIdx.x == 0 && i + 1 < ntiles)
+                ts::issue_tile(s_raw + ((i + 1) & 1) * kNnTile * 3, cs + (size_t)(t0 + kNnTile) * 3, min(kNnTile, nc - t0 - kNnTile),
+                               &s_bar[(i + 1) & 1]);
+            ts::mbar_wait(&s_bar[i & 1], (uint32_t)((i >> 1) & 1));
+            const float *raw = s_raw + (i & 1) * kNnTile * 3;
+            for (int e = threadIdx.x; e < tn; e += kNnThreads) s_tile[e] = make_float4(raw[e * 3], raw[e * 3 + 1], raw[e * 3 + 2], 0.f);
+        } else {
+            for (int e = threadIdx.x; e < tn; e += kNnThreads) {
+                const float *p = cs + (size_t)(t0 + e) * 3;
+                s_tile[e] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
+            }
         }
         __syncthreads();
         if (t0 == 0) {  // k==0 initialises unconditionally (tf_nndistance_g.cu:29), even for NaN/inf
@@ -71,32 +93,9 @@ nn_distance_kernel(int n, int m, const float *__restrict__ xyz1, const float *__
             }
         }
     }
-    if (!kReduce) {
-        if (active) {
-            (dir == 0 ? dist1 : dist2)[(size_t)cloud * nq + j] = best;
-            (dir == 0 ? idx1 : idx2)[(size_t)cloud * nq + j] = bi;
-        }
-    } else {
-        // fixed-order block reduction: lanes by xor-shuffle, then warps 0..7 in order
-        float s = active ? best : 0.f;
-        float mx = active ? best : -1.f;  // distances are >= 0
-        s = warp_sum(s);
-        mx = warp_max(mx);
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        if (lane == 0) {
-            s_red[0][warp] = s;
-            s_red[1][warp] = mx;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            float ts = 0.f, tm = -1.f;
-#pragma unroll
-            for (int w = 0; w < kNnThreads / 32; ++w) {
-                ts += s_red[0][w];
-                tm = fmaxf(tm, s_red[1][w]);
-            }
-            partials[((size_t)cloud * 2 + dir) * chunks + blockIdx.x] = make_float2(ts, tm);
-        }
+    if (active) {
+        (dir == 0 ? dist1 : dist2)[(size_t)cloud * nq + j] = best;
+        (dir == 0 ? idx1 : idx2)[(size_t)cloud * nq + j] = bi;
     }
 }
 
@@ -128,21 +127,44 @@ __device__ __forceinline__ nn_f32x2 nn_fma2(nn_f32x2 a, nn_f32x2 b, nn_f32x2 c) 
     return r;
 }
 
-__global__ void __launch_bounds__(kNnThreads)
+// Shape of the launch: kNmThreads queries per CTA against ALL candidates of the other cloud.  Small CTAs on purpose:
+// at the c2 shape (32 clouds x 2 directions x 1024 queries) 128-thread CTAs give 512 CTAs = 3.5 per SM, all resident
+// at once, instead of 256 CTAs of 256 threads in 1.7 waves (the round-1 form, warps active 20 %).
+// kTma: candidate tiles arrive by cp.async.bulk into a raw AoS landing buffer (double-buffered: the copy of tile i+1
+// flies while tile i is searched), completion on an mbarrier (tile_stage.cuh); the CTA then transposes the tile to
+// the x / y / z arrays the packed inner loop reads.  Otherwise the threads stage with __ldg.
+constexpr int kNmThreads = 128;
+
+template <bool kTma>
+__global__ void __launch_bounds__(kNmThreads)
 nn_min_reduce_kernel(int n, int m, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
                      float2 *__restrict__ partials, int chunks) {
-    __shared__ __align__(16) float s_x[kNnTile + 2], s_y[kNnTile + 2], s_z[kNnTile + 2];
-    __shared__ float s_red[2][kNnThreads / 32];
+    extern __shared__ __align__(16) float s_dyn[];  // x | y | z (kNnTile + 2 each, padded to 16 B) [| raw 0 | raw 1]
+    constexpr int kArr = (kNnTile + 2 + 3) & ~3;
+    float *s_x = s_dyn, *s_y = s_dyn + kArr, *s_z = s_dyn + 2 * kArr;
+    float *s_raw = s_dyn + 3 * kArr;
+    __shared__ float s_red[2][kNmThreads / 32];
+    __shared__ __align__(8) uint64_t s_bar[2];
     const int cloud = blockIdx.y, dir = blockIdx.z;
     const int nq = dir == 0 ? n : m, nc = dir == 0 ? m : n;
-    if ((int)blockIdx.x * kNnThreads >= nq) {  // this direction has fewer query chunks
+    if ((int)blockIdx.x * kNmThreads >= nq) {  // this direction has fewer query chunks
         if (threadIdx.x == 0 && (int)blockIdx.x < chunks)
             partials[((size_t)cloud * 2 + dir) * chunks + blockIdx.x] = make_float2(0.f, -1.f);
         return;
     }
     const float *qs = (dir == 0 ? xyz1 : xyz2) + (size_t)cloud * nq * 3;
     const float *cs = (dir == 0 ? xyz2 : xyz1) + (size_t)cloud * nc * 3;
-    const int j = blockIdx.x * kNnThreads + threadIdx.x;
+    const int ntiles = ceil_div(nc, kNnTile);
+    if (kTma) {
+        if (threadIdx.x == 0) {
+            ts::mbar_init(&s_bar[0], 1);
+            ts::mbar_init(&s_bar[1], 1);
+            ts::fence_mbar_init();
+            ts::issue_tile(s_raw, cs, min(kNnTile, nc), &s_bar[0]);
+        }
+        __syncthreads();
+    }
+    const int j = blockIdx.x * kNmThreads + threadIdx.x;
     const bool active = j < nq;
     float qx = 0.f, qy = 0.f, qz = 0.f;
     if (active) {
@@ -152,13 +174,27 @@ nn_min_reduce_kernel(int n, int m, const float *__restrict__ xyz1, const float *
     // candidate 0 apart (tf_nndistance_g.cu:29 initialises with it unconditionally)
     const float d0 = d2_ref_gpu(__fsub_rn(__ldg(cs), qx), __fsub_rn(__ldg(cs + 1), qy), __fsub_rn(__ldg(cs + 2), qz));
     float best = __int_as_float(0x7f800000);
-    for (int t0 = 0; t0 < nc; t0 += kNnTile) {
+    for (int i = 0; i < ntiles; ++i) {
+        const int t0 = i * kNnTile;
         const int tn = min(kNnTile, nc - t0);
         const int tn2 = (tn + 1) & ~1;  // odd tail: the last candidate is staged twice (the minimum is unchanged)
-        __syncthreads();
-        for (int e = threadIdx.x; e < tn2; e += kNnThreads) {
-            const float *p = cs + (size_t)(t0 + min(e, tn - 1)) * 3;
-            s_x[e] = __ldg(p); s_y[e] = __ldg(p + 1); s_z[e] = __ldg(p + 2);
+        if (i > 0) __syncthreads();     // everyone has finished searching the previous tile's x / y / z
+        if (kTma) {
+            // the other landing buffer was transposed in iteration i-1, before the barrier above: refill it now
+            if (threadIdx.x == 0 && i + 1 < ntiles)
+                ts::issue_tile(s_raw + ((i + 1) & 1) * kNnTile * 3, cs + (size_t)(t0 + kNnTile) * 3, min(kNnTile, nc - t0 - kNnTile),
+                               &s_bar[(i + 1) & 1]);
+            ts::mbar_wait(&s_bar[i & 1], (uint32_t)((i >> 1) & 1));
+            const float *raw = s_raw + (i & 1) * kNnTile * 3;
+            for (int e = threadIdx.x; e < tn2; e += kNmThreads) {  // stride-3 reads: conflict-free (3 is odd)
+                const float *p = raw + min(e, tn - 1) * 3;
+                s_x[e] = p[0]; s_y[e] = p[1]; s_z[e] = p[2];
+            }
+        } else {
+            for (int e = threadIdx.x; e < tn2; e += kNmThreads) {
+                const float *p = cs + (size_t)(t0 + min(e, tn - 1)) * 3;
+                s_x[e] = __ldg(p); s_y[e] = __ldg(p + 1); s_z[e] = __ldg(p + 2);
+            }
         }
         __syncthreads();
         const nn_f32x2 *x2 = reinterpret_cast<const nn_f32x2 *>(s_x), *y2 = reinterpret_cast<const nn_f32x2 *>(s_y),
@@ -185,13 +221,13 @@ nn_min_reduce_kernel(int n, int m, const float *__restrict__ xyz1, const float *
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        float ts = 0.f, tm = -1.f;
+        float ts_ = 0.f, tm = -1.f;
 #pragma unroll
-        for (int w = 0; w < kNnThreads / 32; ++w) {
-            ts += s_red[0][w];
+        for (int w = 0; w < kNmThreads / 32; ++w) {
+            ts_ += s_red[0][w];
             tm = fmaxf(tm, s_red[1][w]);
         }
-        partials[((size_t)cloud * 2 + dir) * chunks + blockIdx.x] = make_float2(ts, tm);
+        partials[((size_t)cloud * 2 + dir) * chunks + blockIdx.x] = make_float2(ts_, tm);
     }
 }
 
@@ -199,7 +235,7 @@ nn_min_reduce_kernel(int n, int m, const float *__restrict__ xyz1, const float *
 __global__ void __launch_bounds__(256)
 chamfer_finalize_kernel(int b, int n_gt, int n_pred, int chunks, const float2 *__restrict__ partials,
                         const float *__restrict__ radius, float *__restrict__ out, float *__restrict__ per_cloud,
-                        float *__restrict__ scratch /* (b,2) */) {
+                        float *__restrict__ scratch /* (b,2) */, float *__restrict__ sum_out, float *__restrict__ max_out) {
     for (int i = threadIdx.x; i < b; i += blockDim.x) {
         float sf = 0.f, sb = 0.f, mf = -1.f, mb = -1.f;
         for (int c = 0; c < chunks; ++c) {
@@ -230,6 +266,8 @@ chamfer_finalize_kernel(int b, int n_gt, int n_pred, int chunks, const float2 *_
         out[1] = mx;
         out[2] = sum;
         out[3] = (float)b;
+        if (sum_out) *sum_out = sum;  // this rank's partial of the batch mean (the operand of the multi-GPU all-reduce)
+        if (max_out) *max_out = mx;
     }
 }
 
@@ -256,7 +294,7 @@ nn_distance_grad_kernel(int n, int m, const float *__restrict__ xyz1, const floa
     }
 }
 
-static inline int nn_chunks(int n, int m) { return ceil_div(n > m ? n : m, kNnThreads); }
+static inline int nn_chunks(int n, int m) { return ceil_div(n > m ? n : m, kNmThreads); }
 
 }  // namespace dispu
 
@@ -269,9 +307,13 @@ extern "C" int dispu_nn_distance(int b, int n, const float *xyz1, int m, const f
     if (b == 0) return DISPU_OK;
     DISPU_REQUIRE(xyz1 && xyz2 && dist1 && idx1 && dist2 && idx2, DISPU_ENULL);
     DISPU_REQUIRE(b <= 65535, DISPU_EUNSUPPORTED);
+    static const bool no_tma = getenv("DISPU_NO_TMA") != nullptr;  // development switch (A/B timing)
+    const dim3 grid(ceil_div(n > m ? n : m, kNnThreads), b, 2);
     count_launch();
-    nn_distance_kernel<false><<<dim3(nn_chunks(n, m), b, 2), kNnThreads, 0, stream>>>(n, m, xyz1, xyz2, dist1, idx1,
-                                                                                     dist2, idx2, nullptr, 0);
+    if (!no_tma && ts::tma_ok(xyz1, n) && ts::tma_ok(xyz2, m))
+        nn_distance_kernel<true><<<grid, kNnThreads, 0, stream>>>(n, m, xyz1, xyz2, dist1, idx1, dist2, idx2);
+    else
+        nn_distance_kernel<false><<<grid, kNnThreads, 0, stream>>>(n, m, xyz1, xyz2, dist1, idx1, dist2, idx2);
     return finish_launch();
 }
 
@@ -298,9 +340,9 @@ extern "C" size_t dispu_chamfer_workspace_bytes(int b, int n_gt, int n_pred) {
     return sizeof(float2) * (size_t)b * 2 * nn_chunks(n_gt, n_pred) + sizeof(float) * 2 * (size_t)b;
 }
 
-extern "C" int dispu_chamfer(int b, int n_gt, const float *gt, int n_pred, const float *pred, const float *radius,
-                             float *out, float *per_cloud, void *workspace, size_t workspace_bytes,
-                             dispu_stream_t stream_) {
+static int chamfer_impl(int b, int n_gt, const float *gt, int n_pred, const float *pred, const float *radius, float *out,
+                        float *per_cloud, float *sum_out, float *max_out, void *workspace, size_t workspace_bytes,
+                        dispu_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     DISPU_REQUIRE(b > 0 && n_gt > 0 && n_pred > 0, DISPU_EINVAL);
     DISPU_REQUIRE(gt && pred && out, DISPU_ENULL);
@@ -309,9 +351,31 @@ extern "C" int dispu_chamfer(int b, int n_gt, const float *gt, int n_pred, const
     const int chunks = nn_chunks(n_gt, n_pred);
     float2 *partials = reinterpret_cast<float2 *>(workspace);
     float *scratch = reinterpret_cast<float *>(partials + (size_t)b * 2 * chunks);
+    // both clouds are candidate sets (one per direction): bulk copies need both to qualify
+    static const bool no_tma = getenv("DISPU_NO_TMA") != nullptr;  // development switch (A/B timing)
+    const bool tma = !no_tma && ts::tma_ok(gt, n_gt) && ts::tma_ok(pred, n_pred);
+    constexpr int kArr = (kNnTile + 2 + 3) & ~3;
+    const int ntiles = ceil_div(n_gt > n_pred ? n_gt : n_pred, kNnTile);
+    const size_t smem = sizeof(float) * (3 * (size_t)kArr + (tma ? (ntiles > 1 ? 2 : 1) * (size_t)kNnTile * 3 : 0));
     count_launch(2);
     // nn_distance(gt, pred): dists_forward belongs to gt (loss_utils.py:51)
-    nn_min_reduce_kernel<<<dim3(chunks, b, 2), kNnThreads, 0, stream>>>(n_gt, n_pred, gt, pred, partials, chunks);
-    chamfer_finalize_kernel<<<1, 256, 0, stream>>>(b, n_gt, n_pred, chunks, partials, radius, out, per_cloud, scratch);
+    if (tma)
+        nn_min_reduce_kernel<true><<<dim3(chunks, b, 2), kNmThreads, smem, stream>>>(n_gt, n_pred, gt, pred, partials, chunks);
+    else
+        nn_min_reduce_kernel<false><<<dim3(chunks, b, 2), kNmThreads, smem, stream>>>(n_gt, n_pred, gt, pred, partials, chunks);
+    chamfer_finalize_kernel<<<1, 256, 0, stream>>>(b, n_gt, n_pred, chunks, partials, radius, out, per_cloud, scratch, sum_out,
+                                                   max_out);
     return finish_launch();
+}
+
+extern "C" int dispu_chamfer(int b, int n_gt, const float *gt, int n_pred, const float *pred, const float *radius,
+                             float *out, float *per_cloud, void *workspace, size_t workspace_bytes,
+                             dispu_stream_t stream) {
+    return chamfer_impl(b, n_gt, gt, n_pred, pred, radius, out, per_cloud, nullptr, nullptr, workspace, workspace_bytes, stream);
+}
+
+extern "C" int dispu_chamfer_ex(int b, int n_gt, const float *gt, int n_pred, const float *pred, const float *radius,
+                                float *out, float *per_cloud, float *sum_out, float *max_out, void *workspace,
+                                size_t workspace_bytes, dispu_stream_t stream) {
+    return chamfer_impl(b, n_gt, gt, n_pred, pred, radius, out, per_cloud, sum_out, max_out, workspace, workspace_bytes, stream);
 }

@@ -172,21 +172,33 @@ class BlockedLinear:
         if biases is not None and any(b is not None for b in biases):
             self.bias = torch.cat([torch.zeros((self.N,), device=stacked.device) if b is None else b.float() for b in biases]).contiguous()
 
-    def __call__(self, x, relu=False, out=None):
+    def __call__(self, x, relu=False, out=None, split=None, out2=None):
+        """split = j: blocks [0, j) go to `out` (..., j*N) and blocks [j, nb) to a second tensor `out2` (..., (nb-j)*N);
+        returns (out, out2) then."""
         if x.shape[-1] != self.K:
             raise ValueError(f"BlockedLinear expects last dim {self.K}")
         a = _lib.DenseArgs()
         xp, xm, ldx = rows(x, "x")
+        n1 = self.nb if split is None else split
+        if not (0 < n1 <= self.nb) or (split is not None and split == self.nb):
+            raise ValueError("BlockedLinear: split must be in 1..nb-1")
         if out is None:
-            out = torch.empty((*x.shape[:-1], self.nb * self.N), dtype=torch.float32, device=x.device)
+            out = torch.empty((*x.shape[:-1], n1 * self.N), dtype=torch.float32, device=x.device)
         yp, ym, ldy = rows(out, "out")
-        if ym != xm or out.shape[-1] != self.nb * self.N:
+        if ym != xm or out.shape[-1] != n1 * self.N:
             raise ValueError("BlockedLinear: out shape mismatch")
         a.M, a.K, a.N, a.X, a.ldx = xm, self.K, self.N, xp, ldx
         a.packed, a.bias, a.relu, a.Y, a.ldy = ptr(self.packed), ptr(self.bias), 1 if relu else 0, yp, ldy
         a.n_blocks, a.packed_block_stride = self.nb, self.stride
+        if split is not None:
+            if out2 is None:
+                out2 = torch.empty((*x.shape[:-1], (self.nb - n1) * self.N), dtype=torch.float32, device=x.device)
+            y2p, y2m, ldy2 = rows(out2, "out2")
+            if y2m != xm or out2.shape[-1] != (self.nb - n1) * self.N:
+                raise ValueError("BlockedLinear: out2 shape mismatch")
+            a.Y2, a.ldy2, a.y2_block = y2p, ldy2, n1
         call("dispu_dense_tf32x3_ex", C.byref(a), stream_ptr())
-        return out
+        return out if split is None else (out, out2)
 
 
 def attention_fused(kvq, m_block=128):

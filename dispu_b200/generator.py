@@ -72,7 +72,12 @@ class Generator:
         # (forward_fused); default = whenever the CUDA backend, hoisting and the tensor-core layers are all on
         self.fused = fused
         self.fuse_weightnet = os.environ.get("DISPU_FUSE_WEIGHTNET", "1") == "1"
+        self.attention = os.environ.get("DISPU_ATTENTION", "fused")  # "fused" (one kernel) | "two_products"
         self._bufs = {}
+        self._streams = {}
+        # independent branches (the 3-D kNN of the coarse cloud, the caller's coarse-loss hook) run on side streams so
+        # they overlap the non-local branch; inside a CUDA graph this becomes a fork/join.  DISPU_STREAMS=0: one stream.
+        self.use_streams = os.environ.get("DISPU_STREAMS", "1") == "1"
         self._dup_idx = {}
         self._packed = {}
         self.hoist = hoist  # use the fused / hoisted grouped-layer formulation when the backend offers it
@@ -289,8 +294,17 @@ class Generator:
             lin = self._packed[name] = PackedLinear(w, b)
         return lin(x, relu=act, **kw)
 
-    def forward_fused(self, inputs):
-        """Same function as forward() with every layer on this library's kernels: layers write into their slot of the
+    def _side(self, i, dev):
+        key = (i, str(dev))
+        st = self._streams.get(key)
+        if st is None:
+            st = self._streams[key] = torch.cuda.Stream(device=dev)
+        return st
+
+    def forward_fused(self, inputs, on_coarse=None):
+        """`on_coarse(coarse)`: optional callback run on a SIDE stream as soon as the coarse cloud exists (e.g. its
+        Chamfer loss), concurrently with PointShuffle2; it is joined before this function returns.
+        Same function as forward() with every layer on this library's kernels: layers write into their slot of the
         tensors the reference builds with tf.concat, grouped layers gather inside the operand load, the EdgeConv
         dense blocks and the feature-space kNN are single kernels, the non-local attention is two batched tcgen05
         products around a softmax."""
@@ -325,11 +339,31 @@ class Generator:
         coarse = self._fx(self._fx(self._fx(coarse_feat, "coarse_fc0"), "coarse_fc1"), "coarse_fc2", act=False)
         xf[..., 1:4].copy_(coarse)
         # ---- PointShuffle2 (ops.py:1012-1087)
-        idx = self.ops.knn3d(16, coarse, coarse)
+        main = torch.cuda.current_stream(dev)
+        forks = []
+        if self.use_streams:
+            s_knn = self._side(0, dev)
+            s_knn.wait_stream(main)
+            with torch.cuda.stream(s_knn):
+                idx = self.ops.knn3d(16, coarse, coarse)  # only conv1's gather and the skip branch need it
+            forks.append(s_knn)
+            if on_coarse is not None:
+                s_cb = self._side(1, dev)
+                s_cb.wait_stream(main)
+                with torch.cuda.stream(s_cb):
+                    on_coarse(coarse)
+                forks.append(s_cb)
+        else:
+            idx = self.ops.knn3d(16, coarse, coarse)
+            if on_coarse is not None:
+                on_coarse(coarse)
         # non-local cell (PointNonLocalCell ops.py:302-346): q.k^T and att.v as batched tcgen05 products
         # key|value and query share their input [0 | xyz | coarse_feat]: ONE launch, two 128-column blocks (the 4 xyz
         # columns get zero weights, the query is zero-padded to 128).  The hoisted conv0 product pm keeps its own dense
         # (b,m,128) tensor: conv1 gathers its rows 16x each and a compact table stays L2-resident.
+        # ... and the hoisted conv0 product pm = x_j(Wa+Wb) + f_j Wc + b shares that input too: it is a third column
+        # block of the same launch, written to its OWN compact (b,m,128) tensor (conv1 gathers its rows 16x each, and a
+        # compact table stays L2-resident)
         blk = self._packed.get("_f_kvq")
         if blk is None:
             from .dense import BlockedLinear
@@ -338,21 +372,28 @@ class Generator:
             z4 = torch.zeros((4, 128), device=dev)
             wq128 = torch.cat([wq, torch.zeros((wq.shape[0], 64), device=dev)], dim=1)
             bq128 = torch.cat([bq, torch.zeros((64,), device=dev)])
-            blk = self._packed["_f_kvq"] = BlockedLinear([torch.cat([z4, wkv]), torch.cat([z4, wq128])], [bkv, bq128])
-        kvq = blk(xf)                  # (b,m,256): key | value | query (pre-scaled by 1/sqrt(64)) | 0
+            wp, bp = P["_f_psp"]
+            blk = self._packed["_f_kvq"] = BlockedLinear([torch.cat([z4, wkv]), torch.cat([z4, wq128]), wp], [bkv, bq128, bp])
+        kvq, pm = blk(xf, split=2)     # kvq (b,m,256): key | value | query (pre-scaled by 1/sqrt(64)) | 0 ; pm (b,m,128)
         q = kvq[..., 128:192]
-        pm = self._fx(xf, "_f_psp", act=False)  # (b,m,128) = x_j(Wa+Wb) + f_j Wc + b
-        nb = m // 256
-        if m % 256:
-            raise ValueError("forward_fused: 4*n must be a multiple of 256")
-        kop = BatchedOperand(b * nb, 64, 256, dev).pack(kvq, 0, 1, 256, 256 * 256)
-        # scores (b,m,m) in one launch (column block j = keys [256j, 256j+256)); its epilogue also leaves per-row
-        # partial maxima; the second product applies exp(x - max) while loading its operand, sums it, and divides in its
-        # epilogue: no softmax pass, the normalised attention matrix is never written
-        stats = torch.empty((b, m, 2 * nb), dtype=torch.float32, device=dev)
-        scores = kop.matmul(q, n_blocks=nb, stats_out=stats)
-        vop = BatchedOperand(b, m, 64, dev).pack(kvq, 64, 256, 1, m * 256)
-        att_v = vop.matmul(scores, softmax_stats=stats)
+        if m % 128:
+            raise ValueError("forward_fused: 4*n must be a multiple of 128")
+        if self.attention == "fused":
+            # softmax(q.k^T).v as ONE tcgen05 kernel (csrc/attention_tc.cu): per 128-query tile two passes over the key
+            # blocks (row maximum, then exp -> P ring in tensor memory -> O += P.V); the (b,m,m) score tensor of
+            # Common/ops.py:330-336 is never written
+            from .dense import attention_fused
+            att_v = attention_fused(kvq)
+        else:
+            # two batched products with the softmax folded into them (round-1 form, kept for A/B: DISPU_ATTENTION=two_products)
+            nb = m // 256
+            if m % 256:
+                raise ValueError("forward_fused (two_products attention): 4*n must be a multiple of 256")
+            kop = BatchedOperand(b * nb, 64, 256, dev).pack(kvq, 0, 1, 256, 256 * 256)
+            stats = torch.empty((b, m, 2 * nb), dtype=torch.float32, device=dev)
+            scores = kop.matmul(q, n_blocks=nb, stats_out=stats)
+            vop = BatchedOperand(b, m, 64, dev).pack(kvq, 64, 256, 1, m * 256)
+            att_v = vop.matmul(scores, softmax_stats=stats)
         nonlocal_pt = self._fx(att_v, "nl_back")
         # local cell: conv0 hoisted to per-point products, gathered + ReLU'd inside conv1's operand load
         qm = self._fx(coarse, "_f_psq", act=False)   # (b,m,128) = x_i Wa
@@ -361,6 +402,8 @@ class Generator:
         # fused epilogue no longer competes with the MMAs for shared-memory bandwidth: 0.23 ms vs 0.21 + 0.12 ms unfused;
         # DISPU_FUSE_WEIGHTNET=0 selects the two-kernel form.)
         ww, bw = P["wconv0"]
+        if forks:
+            main.wait_stream(forks[0])  # idx
         if self.fuse_weightnet:
             H = self._fx(pm, "conv1", gather=(idx, qm, -1.0), weightnet=(coarse, ww, bw, 1.0 / math.sqrt(1.0 + BN_EPS)))
         else:
@@ -374,14 +417,18 @@ class Generator:
         fine_feat = self._fx(g, "aggregation")
         off = self._fx(self._fx(self._fx(fine_feat, "fine_fc0"), "fine_fc1"), "fine_fc2", act=False)
         fine = coarse + (torch.sigmoid(off) - 0.5)
+        for st in forks[1:]:
+            main.wait_stream(st)
         return coarse, fine
 
-    def forward(self, inputs):
+    def forward(self, inputs, on_coarse=None):
         fused = self.fused
         if fused is None:
             fused = self.tc and self.hoist and inputs.is_cuda and isinstance(self.ops, DispuOps)
         if fused:
-            return self.forward_fused(inputs)
+            return self.forward_fused(inputs, on_coarse=on_coarse)
+        if on_coarse is not None:
+            raise ValueError("on_coarse is a feature of the fused forward")
         feat = self.feature_extraction(inputs)
         coarse_feat = self.duplicate_up(feat)
         coarse = self.regressor(coarse_feat, "coarse")

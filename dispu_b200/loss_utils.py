@@ -21,9 +21,10 @@ def _workspace(nbytes, device):
     return ws
 
 
-def chamfer_hausdorff(pred, gt, radius=None, out=None, per_cloud=None):
+def chamfer_hausdorff(pred, gt, radius=None, out=None, per_cloud=None, sum_out=None, max_out=None):
     """One fused pass: returns a (4,) device tensor [cd_mean, hd_max, cd_sum, b] (see dispu_chamfer).
-    pred (b,n_pred,3), gt (b,n_gt,3), radius None | float | (b,) tensor."""
+    pred (b,n_pred,3), gt (b,n_gt,3), radius None | float | (b,) tensor.  sum_out / max_out: optional 1-element float32
+    views that also receive cd_sum / hd_max (e.g. slots of the buffer a single all-reduce sums, dispu_chamfer_ex)."""
     pred = req(pred, torch.float32, 3, "pred")
     gt = req(gt, torch.float32, 3, "gt")
     b, n_pred, c = pred.shape
@@ -38,8 +39,15 @@ def chamfer_hausdorff(pred, gt, radius=None, out=None, per_cloud=None):
         out = torch.empty((4,), dtype=torch.float32, device=pred.device)
     nbytes = int(_lib.lib().dispu_chamfer_workspace_bytes(b, n_gt, n_pred))
     ws = _workspace(nbytes, pred.device)
-    call("dispu_chamfer", b, n_gt, ptr(gt), n_pred, ptr(pred), ptr(radius), ptr(out), ptr(per_cloud), ptr(ws),
-         ws.numel(), stream_ptr())
+    if sum_out is None and max_out is None:
+        call("dispu_chamfer", b, n_gt, ptr(gt), n_pred, ptr(pred), ptr(radius), ptr(out), ptr(per_cloud), ptr(ws),
+             ws.numel(), stream_ptr())
+    else:
+        for t in (sum_out, max_out):
+            if t is not None and (t.dtype != torch.float32 or not t.is_cuda or t.numel() != 1):
+                raise ValueError("sum_out / max_out must be 1-element float32 CUDA tensors (views are fine)")
+        call("dispu_chamfer_ex", b, n_gt, ptr(gt), n_pred, ptr(pred), ptr(radius), ptr(out), ptr(per_cloud), ptr(sum_out),
+             ptr(max_out), ptr(ws), ws.numel(), stream_ptr())
     return out
 
 

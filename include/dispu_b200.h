@@ -169,6 +169,13 @@ int dispu_nn_distance_grad(int b, int n, const float *xyz1, int m, const float *
 size_t dispu_chamfer_workspace_bytes(int b, int n_gt, int n_pred);
 int dispu_chamfer(int b, int n_gt, const float *gt, int n_pred, const float *pred, const float *radius,
                   float *out, float *per_cloud, void *workspace, size_t workspace_bytes, dispu_stream_t stream);
+/* The same, additionally storing this call's batch SUM of per-cloud cd (= out[2], the per-rank partial that the
+ * multi-GPU all-reduce sums) to *sum_out and the batch max of hd (= out[1]) to *max_out — arbitrary
+ * device addresses (either may be NULL), so several losses can deposit their partials side by side in ONE buffer
+ * that a single collective reduces. */
+int dispu_chamfer_ex(int b, int n_gt, const float *gt, int n_pred, const float *pred, const float *radius, float *out,
+                     float *per_cloud, float *sum_out, float *max_out, void *workspace, size_t workspace_bytes,
+                     dispu_stream_t stream);
 
 /* Repulsion loss (Common/loss_utils.py:271-298, DisPU/model.py:83), fused after the ball query:
  * idx (b,n,nsample) = QueryBallPoint(radius, nsample, pred, pred); per point the five smallest squared
@@ -256,6 +263,8 @@ int dispu_dense_tf32x3(long long M, int K, int N, const float *X, const void *pa
  *   - column blocks (n_blocks > 1): Y[:, j*N:(j+1)*N] = act(X . W_j + bias[j*N:(j+1)*N]) with W_j at
  *     packed + j*packed_block_stride (after the batch offset): one launch for an output wider than 256 columns
  *     (q.k^T: 1024 keys = 4 blocks) or for several layers that share their input (n_blocks * N <= 1024 with a bias);
+ *     with Y2 != NULL the blocks j >= y2_block are written to a SECOND tensor Y2 (row stride ldy2, 0 = dense) at columns
+ *     (j - y2_block)*N, so layers that only share their input keep separate compact outputs (N % 4 == 0, 16-byte aligned);
  *   - softmax without a softmax pass (PointNonLocalCell, Common/ops.py:326-339: softmax(q.k^T) . v): the launch that
  *     writes the scores also writes, per row and per (column block, warp half), the maximum of the values it stored:
  *     stat_out is (M, 2*n_blocks) float; the launch that consumes the scores as its X operand gets stat_in = that
@@ -296,6 +305,9 @@ typedef struct dispu_dense_args {
     void *stat_out;                 /* softmax statistics written by the epilogue, see below */
     const void *stat_in;            /* softmax applied to the operand rows by the producers, see below */
     int n_stat;
+    float *Y2;                      /* split output: column blocks j >= y2_block go to Y2[:, (j-y2_block)*N ...], row stride ldy2 */
+    long long ldy2;
+    int y2_block;
 } dispu_dense_args;
 int dispu_dense_tf32x3_ex(const dispu_dense_args *args, dispu_stream_t stream);
 /* sizeof(dispu_dense_args) as this library was compiled: lets a foreign-language binding verify its struct layout. */

@@ -38,7 +38,7 @@ def test_binding_covers_header(so):
     assert l.dispu_abi_version() == 1
     assert l.dispu_fps_onchip_capacity() in (65536, 131072)  # 131072 where 16-CTA clusters launch (B200); 65536 otherwise / without a device
     assert b"invalid" in l.dispu_error_string(-1)
-    assert l.dispu_chamfer_workspace_bytes(32, 1024, 1024) == 8 * 32 * 2 * 4 + 8 * 32
+    assert l.dispu_chamfer_workspace_bytes(32, 1024, 1024) == 8 * 32 * 2 * 8 + 8 * 32  # float2 partial per (cloud, direction, 128-query chunk)
 
 
 def test_dense_args_layout_and_validation(so):

@@ -50,6 +50,13 @@ def main():
         a = two_products(kvq)
         f = attention_fused(kvq)
         err = float((a - f).abs().max())
+        # float64 check of both forms on a few rows of the last cloud (the (b,m,m) reference does not fit at m = 4096)
+        rows_ = torch.tensor([0, 1, m // 2, m - 1], device=dev)
+        k64, v64 = kvq[-1, :, :64].double(), kvq[-1, :, 64:128].double()
+        want = torch.softmax(kvq[-1, rows_, 128:192].double() @ k64.T, dim=-1) @ v64
+        err_f = float((f[-1, rows_].double() - want).abs().max())
+        err_a = float((a[-1, rows_].double() - want).abs().max())
+        print(json.dumps({"b": b, "m": m, "fused_vs_f64": err_f, "two_products_vs_f64": err_a}), flush=True)
         r = {"b": b, "m": m, "two_products_ms": timeit(lambda: two_products(kvq)), "fused_ms": timeit(lambda: attention_fused(kvq)),
              "max_abs_diff": err, "alg_TFLOPs_fused": None}
         r["alg_TFLOPs_fused"] = 4.0 * b * m * m * 64 / r["fused_ms"] / 1e9
