@@ -1,8 +1,13 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the Dis-PU hot path on B200 (contract: see DESIGN.md §Measurement).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config c2|c3|c4|c5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+--config selects the workload (default c2 = the configuration BASELINE.json's metric is quoted on; the others are the
+remaining GPU configs of BASELINE.json, same JSON schema): c3 = B=128 sample_and_group + grouped MLP on tcgen05 (two
+set-abstraction levels), c4 = two-stage 16x generator (256 -> 1024 -> 4096) + Chamfer, batch-sharded, c5 = FPS +
+ball-query sweep N in {1k,4k,16k,64k}, B=64 over all ranks.
 
 Workload (BASELINE.json configs[1], "c2"): B=32 patches of 256 points per GPU -> 4x upsampling generator
 forward (1024 points) + Chamfer/Hausdorff of coarse and fine against a 1024-point ground truth
@@ -163,49 +168,438 @@ def cpu_chamfer(pred, gt):
     return cd, hd
 
 
-def cpu_arm(steps, warmup, sample_b):
-    """Times the CPU path on `sample_b` clouds per step; returns (points/s, ms/step, cores, kind, sample)."""
+def _time_cpu(step, steps, warmup):
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    return (time.perf_counter() - t0) / steps
+
+
+def cpu_arm_generator(steps, warmup, sample_b, stages=1):
+    """c2 / c4 on the host: the torch restatement of the generator on CPU threads with the REFERENCE's own kNN
+    (nanoflann, OpenMP over the batch) and NnDistance host loop, on `sample_b` clouds per step."""
     import torch
     from oracle import ref as R
     from dispu_b200.generator import Generator
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     inp, gt = synth_batch(0)
-    inp, gt = inp[:sample_b], gt[:sample_b]
+    inp = inp[:sample_b]
+    gt = gt[:sample_b] if stages == 1 else synth_gt(4000, sample_b, N_IN * UP * UP)
     gen = Generator(device="cpu", ops=CpuRefOps())
     x = torch.from_numpy(inp)
 
     def step():
         with torch.no_grad():
             coarse, fine = gen(x)
-        c1 = cpu_chamfer(coarse.numpy(), gt)
-        c2 = cpu_chamfer(fine.numpy(), gt)
-        return c1, c2
+            if stages == 2:
+                _, fine = gen(fine.contiguous())
+        if stages == 1:
+            cpu_chamfer(coarse.numpy(), gt)
+        cpu_chamfer(fine.numpy(), gt)
 
-    for _ in range(warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    dt = time.perf_counter() - t0
+    dt = _time_cpu(step, steps, warmup)
     kind = "reference" if (R.available("knn") and R.available("cpu")) else "port"
     sample = (f"{sample_b} of {B_PER_GPU} patches per step x {steps} steps; reference nanoflann kNN (OpenMP, {cores} threads) "
               f"+ reference nnsearch NnDistance (1 thread, as the TF CPU op) from oracle/_ref; stock dense layers = torch CPU "
               f"({cores} threads) restatement of generator.py (TF is not installable here)")
-    return sample_b * N_IN * steps / dt, dt / steps * 1e3, cores, kind, sample
+    return sample_b * N_IN / dt, dt * 1e3, cores, kind, sample
+
+
+def synth_gt(seed, b, n):
+    rng = np.random.default_rng(seed)
+    gt = np.empty((b, n, 3), np.float32)
+    for i in range(b):
+        got = 0
+        while got < n:
+            c = rng.uniform(-1, 1, (3 * n, 3)).astype(np.float32)
+            c = c[(c.astype(np.float64) ** 2).sum(1) < 1.0]
+            k = min(len(c), n - got)
+            gt[i, got:got + k] = c[:k]
+            got += k
+    return gt
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), d.get("sm_max_mhz", 1965.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1590.0, 1965.0, "fallback (B200_PROFILING.md)"
+
+
+def fp32_peak_tflops(sm_mhz):
+    """148 SMs x 128 FP32 FMA lanes x 2 flop at the maximum SM clock (the bound of the distance-test kernels)."""
+    return 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+
+
+# ------------------------------------------------------------------------------------------------
+# Workloads: one class per BASELINE.json config.  A workload owns its pinned host inputs, the matching device buffers,
+# a graph-capturable step_body() and what it costs algorithmically.
+class Workload:
+    metric = METRIC
+    unit = UNIT
+    scaling = "weak"
+
+    def __init__(self, args, rank, world, dev):
+        self.args, self.rank, self.world, self.dev = args, rank, world, dev
+        self.host = []      # pinned host inputs, copied every end-to-end step
+        self.device = []    # their device copies
+        self.h_result = None  # pinned host result buffer, read every end-to-end step
+        self.d_result = None
+        self.units_per_step = 0   # metric units THIS rank processes per step
+        self.collective = None    # device tensor the ONE data-path collective sums (None: no collective)
+        self.gen = None
+
+    def pin(self, arr):
+        import torch
+        h = torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
+        d = torch.empty_like(h, device=self.dev)
+        d.copy_(h)
+        self.host.append(h)
+        self.device.append(d)
+        return d
+
+    def step_body(self):
+        raise NotImplementedError
+
+    def profile_body(self):
+        """The step on ONE stream (the per-call event pairs of the roofline leg must bracket one kernel each)."""
+        if self.gen is not None:
+            saved, self.gen.use_streams = self.gen.use_streams, False
+            try:
+                self.step_body_no_collective()
+            finally:
+                self.gen.use_streams = saved
+        else:
+            self.step_body_no_collective()
+
+    def step_body_no_collective(self):
+        self.step_body()
+
+    def alg(self, key):
+        """('flops' | 'bytes', amount per launch) of a profiled C-ABI call, or None."""
+        return None
+
+    def config(self):
+        return {}
+
+    def extra(self):
+        return {}
+
+    def cpu_arm(self, steps, warmup):
+        raise NotImplementedError
+
+
+def dense_flops(key):
+    f = key.split(" ")
+    M_, K_, N_ = int(f[1][1:]), int(f[2][1:]), int(f[3][1:])
+    fl = 2.0 * M_ * K_ * N_
+    for tok in f[4:]:
+        if tok.startswith("x") and tok.endswith("blocks"):
+            fl *= int(tok[1:-6])  # column blocks: N per block
+        if tok == "+weightnet":
+            fl += 2.0 * M_ * N_ * 16  # transposed product with the weight net in the epilogue
+    return fl
+
+
+class GeneratorWorkload(Workload):
+    """c2 (stages=1) and c4 (stages=2): generator forward + fused Chamfer/Hausdorff, batch-sharded, one all-reduce."""
+
+    def __init__(self, args, rank, world, dev, stages):
+        super().__init__(args, rank, world, dev)
+        import torch
+        from dispu_b200.generator import Generator
+        self.stages = stages
+        self.B = B_PER_GPU
+        inp_np, gt_np = synth_batch(rank)
+        if stages == 2:  # SURVEY.md §8d C4: gt (B,4096,3), seed 4000+rank
+            gt_np = synth_gt(4000 + rank, self.B, N_IN * UP * UP)
+        self.d_inp = self.pin(inp_np)
+        self.d_gt = self.pin(gt_np)
+        self.gen = Generator(device=dev)
+        self.out_c = torch.zeros((4,), dtype=torch.float32, device=dev)
+        self.out_f = torch.zeros((4,), dtype=torch.float32, device=dev)
+        # [sum cd_coarse, sum cd_fine | hd_coarse, hd_fine]: the fused Chamfer kernels deposit their partials here themselves
+        # (dispu_chamfer_ex); the first two floats are what the ONE collective of the path sums over the ranks
+        self.partial = torch.zeros((4,), dtype=torch.float32, device=dev)
+        self.d_result = self.partial
+        self.h_result = torch.zeros((4,), dtype=torch.float32).pin_memory()
+        self.collective = self.partial[:2]
+        self.units_per_step = self.B * N_IN
+        self.name = "c2" if stages == 1 else "c4"
+
+    def step_body_no_collective(self):
+        import torch
+        from dispu_b200 import loss_utils
+        p = self.partial
+        with torch.no_grad():
+            if self.stages == 1:
+                # the coarse cloud's loss is handed to the generator as a hook: with DISPU_STREAMS=1 it runs on a side stream
+                coarse, fine = self.gen(self.d_inp, on_coarse=lambda c: loss_utils.chamfer_hausdorff(
+                    c, self.d_gt, out=self.out_c, sum_out=p[0:1], max_out=p[2:3]))
+            else:  # DisPU/model.py:116-118: G(G(x).fine), shared weights; the loss is on the final 16x cloud
+                _, fine1 = self.gen(self.d_inp)
+                _, fine = self.gen(fine1)
+            loss_utils.chamfer_hausdorff(fine, self.d_gt, out=self.out_f, sum_out=p[1:2], max_out=p[3:4])
+
+    def step_body(self):
+        self.step_body_no_collective()
+
+    def alg(self, key):
+        nm = key.split(" ")[0]
+        if nm == "dispu_dense_tf32x3_ex":
+            return ("flops", dense_flops(key))
+        ints = [int(x) for x in key.split(" ")[1].split(",")] if " " in key and key.split(" ")[1][0].isdigit() else []
+        if nm == "dispu_attention_tf32x3":
+            b, m = ints[0], ints[1]
+            return ("flops", 4.0 * b * m * m * 64)
+        if nm == "dispu_knn":
+            b, n, m, k = ints[:4]
+            return ("bytes", b * (12 * n + 12 * m + 4 * m * k))
+        if nm in ("dispu_chamfer", "dispu_chamfer_ex"):
+            b, n, m = ints[0], ints[1], ints[2]
+            return ("bytes", b * (12 * n + 12 * m) + 16)
+        if nm == "dispu_group_max_ld":
+            b, n, c, m, ns = ints[:5]
+            return ("bytes", b * (4 * m * ns + 4 * n * c + 4 * m * c))
+        if nm in ("dispu_dense_conv", "dispu_dense_conv_knn"):
+            b, n, c, k = ints[0], ints[1], ints[2], ints[3]
+            return ("bytes", b * n * (4 * c + 4 * k + 4 * (72 + c)))
+        return None
+
+    def config(self):
+        w = ("c2: B=32/GPU, N=256->1024 (4x) generator forward + Chamfer/Hausdorff(coarse,fine)" if self.stages == 1 else
+             "c4: B=32/GPU (256 over 8 GPUs), two-stage 16x generator 256->1024->4096 (shared weights) + Chamfer/Hausdorff vs 4096-point gt")
+        return {"workload": w, "batch_per_gpu": self.B, "n_in": N_IN, "up_ratio": UP if self.stages == 1 else UP * UP,
+                "weights": "Xavier-uniform seed 7, zero bias (random init; no checkpoint offline)",
+                "attention": self.gen.attention,
+                "streams": "kNN of the coarse cloud and the coarse Chamfer on side streams (graph fork/join)" if self.gen.use_streams else "single stream"}
+
+    def extra(self):
+        loss = self.h_result.tolist()
+        return {"loss": {"cd_coarse_sum": loss[0], "cd_fine_sum": loss[1], "hd_coarse": loss[2], "hd_fine": loss[3]}}
+
+    def cpu_arm(self, steps, warmup):
+        return cpu_arm_generator(steps, warmup, sample_b=self.args.ref_sample if self.stages == 1 else max(1, self.args.ref_sample // 4),
+                                 stages=self.stages)
+
+
+class SetAbstractionWorkload(Workload):
+    """c3: B=128 clouds of 4096 points per GPU -> SA level 1 (npoint 1024, r 0.2, ns 32, mlp [32,32,64]) -> SA level 2
+    (npoint 512, r 0.4, ns 32, mlp [64,64,128] on 3+64 channels): FPS, gather, ball query and the fused group + MLP + max
+    on tcgen05 (3xTF32), the shapes of Common/ops.py:564-570.  No collective (independent clouds)."""
+    name = "c3"
+    metric = "input_points_per_sec_sample_and_group_grouped_mlp"
+
+    def __init__(self, args, rank, world, dev):
+        super().__init__(args, rank, world, dev)
+        import torch
+        self.B = 128
+        rng = np.random.default_rng(3000 + rank)
+        self.d_xyz = self.pin(synth_gt(3000 + rank, self.B, 4096))
+        g = torch.Generator().manual_seed(11)
+
+        def layers(widths):
+            return [((torch.randn((widths[i], widths[i + 1]), generator=g) / widths[i] ** 0.5).to(dev), torch.zeros(widths[i + 1], device=dev))
+                    for i in range(len(widths) - 1)]
+        self.l1, self.l2 = layers([3, 32, 32, 64]), layers([67, 64, 64, 128])
+        self.units_per_step = self.B * 4096
+        self.d_result = torch.zeros((self.B, 512, 128), dtype=torch.float32, device=dev)
+        self.h_result = torch.zeros((self.B, 512, 128), dtype=torch.float32).pin_memory()
+        del rng
+
+    def step_body(self):
+        import torch
+        import dispu_b200.pointnet_util as PU
+        with torch.no_grad():
+            xyz1, f1, _ = PU.pointnet_sa_module(self.d_xyz, None, 1024, 0.2, 32, self.l1, precision=PU.MLP_TF32X3)
+            _, f2, _ = PU.pointnet_sa_module(xyz1, f1, 512, 0.4, 32, self.l2, precision=PU.MLP_TF32X3)
+            self.d_result.copy_(f2)
+
+    def alg(self, key):
+        nm = key.split(" ")[0]
+        ints = [int(x) for x in key.split(" ")[1].split(",")] if " " in key else []
+        if nm == "dispu_sa_mlp":
+            b, n, m, ns, c_pts = ints[:5]
+            w = [3, 32, 32, 64] if c_pts == 0 else [67, 64, 64, 128]
+            return ("flops", 2.0 * b * m * ns * sum(w[i] * w[i + 1] for i in range(3)))
+        if nm == "dispu_fps":
+            b, n, m = ints[:3]
+            return ("bytes", b * (m - 1) * n * 16)
+        if nm in ("dispu_query_ball_point", "dispu_query_ball_point_ws"):
+            b, n, m = ints[:3]
+            return ("bytes", b * (12 * n + 12 * m + 4 * m * 32 + 4 * m))
+        if nm == "dispu_gather_point":
+            b, n, m = ints[:3]
+            return ("bytes", b * (4 * m + 24 * m))
+        return None
+
+    def config(self):
+        return {"workload": "c3: B=128/GPU, 4096 -> npoint 1024 (r 0.2, ns 32, mlp [32,32,64]) -> npoint 512 (r 0.4, ns 32, mlp [64,64,128]): "
+                            "FPS + gather + ball query + fused group/MLP/max on tcgen05 (3xTF32)",
+                "batch_per_gpu": self.B, "n_in": 4096, "weights": "N(0, 1/sqrt(C_in)) seed 11, zero bias"}
+
+    def cpu_arm(self, steps, warmup):
+        return self.cpu_arm_static(steps, warmup)
+
+    @staticmethod
+    def cpu_arm_static(steps, warmup):
+        """Reference host loops (query_ball_point_cpu + group_point_cpu from oracle/_ref) around the literal FPS restatement
+        (the reference has NO CPU FPS kernel) and torch-CPU matmuls for the 1x1 convs, on 2 clouds."""
+        import torch
+        from oracle import oracle as O
+        from oracle import ref as R
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        sb, B = 2, 128
+        xyz = synth_gt(3000, sb, 4096)
+        g = torch.Generator().manual_seed(11)
+
+        def mk(widths):
+            return [((torch.randn((widths[i], widths[i + 1]), generator=g) / widths[i] ** 0.5), torch.zeros(widths[i + 1])) for i in range(len(widths) - 1)]
+        l1, l2 = mk([3, 32, 32, 64]), mk([67, 64, 64, 128])
+        use_ref = R.available("cpu")
+
+        def sa(x, pts, npoint, r, ns, layers):
+            new_xyz = O.gather_point(x, O.farthest_point_sample(npoint, x))
+            idx = R.cpu_query_ball_point(r, ns, x, new_xyz) if use_ref else O.query_ball_point(r, ns, x, new_xyz, mode=O.CPU)[0]
+            idx = np.maximum(idx, 0)
+            g_ = (R.cpu_group_point(x, idx) if use_ref else O.group_point(x, idx)) - new_xyz[:, :, None, :]
+            if pts is not None:
+                g_ = np.concatenate([g_, R.cpu_group_point(pts, idx) if use_ref else O.group_point(pts, idx)], -1)
+            h = torch.from_numpy(g_)
+            for w, b in layers:
+                h = torch.relu(h @ w + b)
+            return new_xyz, h.max(dim=2)[0].numpy()
+
+        def step():
+            x1, f1 = sa(xyz, None, 1024, 0.2, 32, l1)
+            sa(x1, f1, 512, 0.4, 32, l2)
+
+        dt = _time_cpu(step, steps, warmup)
+        kind = "reference" if use_ref else "port"
+        sample = (f"{sb} of {B} clouds per step x {steps} steps; reference query_ball_point_cpu / group_point_cpu host loops (oracle/_ref), "
+                  f"literal single-thread FPS restatement (the reference has no CPU FPS), torch CPU ({cores} threads) 1x1 convs")
+        return sb * 4096 / dt, dt * 1e3, cores, kind, sample
+
+
+class SweepWorkload(Workload):
+    """c5: FPS + ball query, N in {1k,4k,16k,64k}, B=64 clouds over ALL ranks (strong scaling: 64 / world per rank),
+    FPS m=N/4, ball query of those centres into the N points, ns=32, r=(32/N)^(1/3).  No collective."""
+    name = "c5"
+    metric = "input_points_per_sec_fps_ball_query_sweep"
+    scaling = "strong"
+    SIZES = (1024, 4096, 16384, 65536)
+
+    def __init__(self, args, rank, world, dev):
+        super().__init__(args, rank, world, dev)
+        import torch
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from conftest import unit_ball
+        if 64 % world:
+            raise SystemExit("c5 shards 64 clouds: --gpus must divide 64")
+        self.B = 64 // world
+        self.x = []
+        for n in self.SIZES:
+            rng = np.random.default_rng(5000 + int(np.log2(n)) + 100 * rank)
+            self.x.append(self.pin(unit_ball(rng, self.B, n)))
+        self.units_per_step = self.B * sum(self.SIZES)
+        tot = sum(n // 4 for n in self.SIZES)
+        self.d_result = torch.zeros((self.B, 2 * tot), dtype=torch.int32, device=dev)  # [FPS idx | pts_cnt] of every size
+        self.h_result = torch.zeros((self.B, 2 * tot), dtype=torch.int32).pin_memory()
+
+    def step_body(self):
+        import torch
+        import dispu_b200.tf_grouping as G
+        import dispu_b200.tf_sampling as S
+        o = 0
+        with torch.no_grad():
+            for n, x in zip(self.SIZES, self.x):
+                m, r = n // 4, (32.0 / n) ** (1.0 / 3.0)
+                fidx = S.farthest_point_sample(m, x)
+                centres = S.gather_point(x, fidx)
+                _, cnt = G.query_ball_point(r, 32, x, centres)
+                self.d_result[:, o:o + m].copy_(fidx)
+                self.d_result[:, o + m:o + 2 * m].copy_(cnt)
+                o += 2 * m
+
+    def alg(self, key):
+        nm = key.split(" ")[0]
+        ints = [int(x) for x in key.split(" ")[1].split(",")] if " " in key else []
+        if nm == "dispu_fps":
+            b, n, m = ints[:3]
+            return ("bytes", b * (m - 1) * n * 16)
+        if nm in ("dispu_query_ball_point", "dispu_query_ball_point_ws"):
+            b, n, m = ints[:3]
+            return ("bytes", b * (12 * n + 12 * m + 4 * m * 32 + 4 * m))
+        if nm == "dispu_gather_point":
+            b, n, m = ints[:3]
+            return ("bytes", b * 28 * m)
+        return None
+
+    def config(self):
+        return {"workload": "c5: FPS (m=N/4) + ball query (ns=32, r=(32/N)^(1/3)) sweep, N in {1024,4096,16384,65536}, B=64 clouds over all ranks",
+                "batch_per_gpu": self.B, "sizes": list(self.SIZES)}
+
+    def cpu_arm(self, steps, warmup):
+        return self.cpu_arm_static(steps, warmup)
+
+    @staticmethod
+    def cpu_arm_static(steps, warmup):
+        from oracle import oracle as O
+        from oracle import ref as R
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from conftest import unit_ball
+        use_ref = R.available("cpu")
+        sb, sizes = 1, (1024, 4096)
+        xs = [unit_ball(np.random.default_rng(5000 + int(np.log2(n))), sb, n) for n in sizes]
+
+        def step():
+            for n, x in zip(sizes, xs):
+                m, r = n // 4, (32.0 / n) ** (1.0 / 3.0)
+                c = O.gather_point(x, O.farthest_point_sample(m, x))
+                R.cpu_query_ball_point(r, 32, x, c) if use_ref else O.query_ball_point(r, 32, x, c, mode=O.CPU)
+
+        dt = _time_cpu(step, steps, warmup)
+        sample = (f"{sb} cloud per size, sizes {list(sizes)} only (bounded sample) x {steps} steps; literal single-thread FPS restatement "
+                  f"(the reference has no CPU FPS kernel) + reference query_ball_point_cpu host loop (oracle/_ref), 1 thread")
+        return sb * sum(sizes) / dt, dt * 1e3, 1, ("reference" if use_ref else "port"), sample
+
+
+def make_workload(args, rank, world, dev):
+    if args.config == "c2":
+        return GeneratorWorkload(args, rank, world, dev, stages=1)
+    if args.config == "c4":
+        return GeneratorWorkload(args, rank, world, dev, stages=2)
+    if args.config == "c3":
+        return SetAbstractionWorkload(args, rank, world, dev)
+    return SweepWorkload(args, rank, world, dev)
 
 
 # ------------------------------------------------------------------------------------------------
 def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the selected workload on the host cores (rank 0 only)."""
     if rank != 0:
         return
-    val, ms, cores, kind, sample = cpu_arm(args.steps, args.warmup, sample_b=args.ref_sample)
+    if args.config in ("c2", "c4"):
+        stages = 1 if args.config == "c2" else 2
+        val, ms, cores, kind, sample = cpu_arm_generator(args.steps, args.warmup, stages=stages,
+                                                         sample_b=args.ref_sample if stages == 1 else max(1, args.ref_sample // 4))
+        metric = METRIC
+        workload = ("c2: B=32/GPU, N=256->1024 (4x) generator forward + Chamfer/Hausdorff(coarse,fine)" if stages == 1 else
+                    "c4: two-stage 16x generator 256->1024->4096 + Chamfer/Hausdorff vs 4096-point gt")
+    else:
+        cls = SetAbstractionWorkload if args.config == "c3" else SweepWorkload
+        val, ms, cores, kind, sample = cls.cpu_arm_static(args.steps, args.warmup)
+        metric, workload = cls.metric, (cls.__doc__ or args.config).split(":")[0]
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": metric, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "c2: B=32/GPU, N=256->1024 (4x) generator forward + Chamfer/Hausdorff(coarse,fine)",
-                   "sample": sample},
+        "config": {"workload": workload, "sample": sample},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -216,8 +610,7 @@ def run_reference(args, rank, world):
 def run_product(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from dispu_b200 import _lib, loss_utils
-    from dispu_b200.generator import Generator
+    from dispu_b200 import _lib
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — dispu_b200 has no CPU fallback (use --impl reference for the CPU arm)")
@@ -227,39 +620,21 @@ def run_product(args, rank, world, local_rank):
     torch.backends.cuda.matmul.allow_tf32 = False  # stock dense layers stay FP32 like the reference's
     torch.backends.cudnn.allow_tf32 = False
 
-    B = B_PER_GPU
-    inp_np, gt_np = synth_batch(rank)
-    h_inp = torch.from_numpy(inp_np).pin_memory()
-    h_gt = torch.from_numpy(gt_np).pin_memory()
-    d_inp = torch.empty_like(h_inp, device=dev)
-    d_gt = torch.empty_like(h_gt, device=dev)
-    d_inp.copy_(h_inp)
-    d_gt.copy_(h_gt)
-    gen = Generator(device=dev)
-    out_c = torch.zeros((4,), dtype=torch.float32, device=dev)
-    out_f = torch.zeros((4,), dtype=torch.float32, device=dev)
-    # [sum cd_coarse, sum cd_fine | hd_coarse, hd_fine]: the fused Chamfer kernels deposit their partials here themselves
-    # (dispu_chamfer_ex), the first two floats are what the ONE collective of the path sums over the ranks
-    partial = torch.zeros((4,), dtype=torch.float32, device=dev)
-    h_loss = torch.zeros((4,), dtype=torch.float32).pin_memory()
+    wl = make_workload(args, rank, world, dev)
     flush = torch.empty((192 * 1024 * 1024 // 4,), dtype=torch.float32, device=dev)  # > 126 MB L2
-    in_graph_collective = world > 1 and not args.eager_collective
+    has_coll = world > 1 and wl.collective is not None
+    in_graph_collective = has_coll and not args.eager_collective
 
     def allreduce():
-        if world > 1:
-            # ONE collective on the path: sum of the per-rank Chamfer partials, enqueued on the step's
-            # stream — inside the captured CUDA graph, so a replay contains the ncclAllReduce kernel and no host work;
-            # (Hausdorff is only logged by the trainer — max over ranks is taken on the host from the same 4 floats)
-            dist.all_reduce(partial[:2], op=dist.ReduceOp.SUM)
+        # ONE collective on the path: sum of the per-rank Chamfer partials, enqueued on the step's
+        # stream — inside the captured CUDA graph, so a replay contains the ncclAllReduce kernel and no host work;
+        # (Hausdorff is only logged by the trainer — max over ranks is taken on the host from the same 4 floats)
+        dist.all_reduce(wl.collective, op=dist.ReduceOp.SUM)
 
     def step_body():
-        with torch.no_grad():
-            # the coarse cloud's loss runs on a side stream as soon as the coarse cloud exists (overlaps PointShuffle2)
-            coarse, fine = gen(d_inp, on_coarse=lambda c: loss_utils.chamfer_hausdorff(
-                c, d_gt, out=out_c, sum_out=partial[0:1], max_out=partial[2:3]))
-            loss_utils.chamfer_hausdorff(fine, d_gt, out=out_f, sum_out=partial[1:2], max_out=partial[3:4])
-            if in_graph_collective:
-                allreduce()
+        wl.step_body()
+        if in_graph_collective:
+            allreduce()
 
     stream = torch.cuda.Stream(device=dev)
     with torch.cuda.stream(stream):
@@ -285,7 +660,7 @@ def run_product(args, rank, world, local_rank):
                 graph.replay()
             else:
                 step_body()
-            if not in_graph_collective:
+            if has_coll and not in_graph_collective:
                 allreduce()
 
         def barrier():
@@ -310,7 +685,7 @@ def run_product(args, rank, world, local_rank):
                 evs.append((e0, e1))
             barrier()
             dev_ms = sum(a.elapsed_time(b) for a, b in evs)
-            # ---------------- end-to-end (host buffers in, host scalars out, every step)
+            # ---------------- end-to-end (host buffers in, host result out, every step)
             barrier()
             evs = []
             for _ in range(args.steps):
@@ -318,12 +693,12 @@ def run_product(args, rank, world, local_rank):
                 e0 = torch.cuda.Event(enable_timing=True)
                 e1 = torch.cuda.Event(enable_timing=True)
                 e0.record(stream)
-                d_inp.copy_(h_inp, non_blocking=True)
-                d_gt.copy_(h_gt, non_blocking=True)
+                for h, d in zip(wl.host, wl.device):
+                    d.copy_(h, non_blocking=True)
                 step()
-                h_loss.copy_(partial, non_blocking=True)
+                wl.h_result.copy_(wl.d_result, non_blocking=True)
                 e1.record(stream)
-                e1.synchronize()  # the caller reads the loss every step
+                e1.synchronize()  # the caller reads the result every step
                 evs.append((e0, e1))
             barrier()
             e2e_ms = sum(a.elapsed_time(b) for a, b in evs)
@@ -336,74 +711,79 @@ def run_product(args, rank, world, local_rank):
         roof = None
         cpu_base = None
         if rank == 0:
-            roof = dominant_kernel_roofline(gen, d_inp, d_gt, stream, flush)
+            roof = dominant_kernel_roofline(wl, stream, flush)
 
     if rank == 0:
         if args.cpu_baseline:
-            v, ms, cores, kind, sample = cpu_arm(steps=1, warmup=1, sample_b=args.ref_sample)
+            v, ms, cores, kind, sample = wl.cpu_arm(steps=1, warmup=1)
             cpu_base = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
-        pts = B * N_IN * world * args.steps
-        loss = h_loss.tolist()
+        units = wl.units_per_step * world * args.steps
+        cfg = wl.config()
+        cfg.update({"cuda_graph": graph is not None,
+                    "l2": "flushed between timed steps (192 MiB memset outside the event pairs)",
+                    "sharding": ("single GPU" if world == 1 else
+                                 (f"batch-sharded x{world}, one all-reduce of 2 Chamfer partial sums "
+                                  f"({'captured in the CUDA graph' if (in_graph_collective and graph is not None) else 'eager, after the replay'})")
+                                 if wl.collective is not None else f"clouds sharded x{world}, no data-path collective")})
         line = {
-            "metric": METRIC, "value": pts / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "metric": wl.metric, "value": units / (dev_ms * 1e-3), "unit": wl.unit, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": wl.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "c2: B=32/GPU, N=256->1024 (4x) generator forward + Chamfer/Hausdorff(coarse,fine)",
-                       "batch_per_gpu": B, "n_in": N_IN, "up_ratio": UP, "cuda_graph": graph is not None,
-                       "l2": "flushed between timed steps (192 MiB memset outside the event pairs)",
-                       "weights": "Xavier-uniform seed 7, zero bias (random init; no checkpoint offline)",
-                       "sharding": (f"batch-sharded x{world}, one all-reduce of 2 Chamfer partial sums "
-                                    f"({'captured in the CUDA graph' if (in_graph_collective and graph is not None) else 'eager, after the replay'})")
-                       if world > 1 else "single GPU",
-                       "streams": "kNN of the coarse cloud and the coarse Chamfer on side streams (graph fork/join)" if gen.use_streams else "single stream"},
-            "e2e": {"value": pts / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
-                    "h2d_bytes_per_step": int(h_inp.numel() * 4 + h_gt.numel() * 4), "d2h_bytes_per_step": 16},
+            "config": cfg,
+            "e2e": {"value": units / (e2e_ms * 1e-3), "unit": wl.unit, "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": int(sum(h.numel() * h.element_size() for h in wl.host)),
+                    "d2h_bytes_per_step": int(wl.h_result.numel() * wl.h_result.element_size())},
             "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step),
             "clocks": clocks.summary(),
             "roofline": roof,
             "cpu_baseline": cpu_base,
-            "loss": {"cd_coarse_sum": loss[0], "cd_fine_sum": loss[1], "hd_coarse": loss[2], "hd_fine": loss[3]},
         }
+        line.update(wl.extra())
         print(json.dumps(line), file=RESULT_OUT, flush=True)
 
 
-def measured_peaks():
-    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(p):
-        d = json.load(open(p))
-        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+def kernel_traffic(family):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture, or None.  The file is
+    stamped with the SHA-256 of the kernel's source: a capture taken from different code is refused (None), so the number
+    cannot silently go stale (VERDICT r1 weak #10)."""
+    import hashlib
+    tp = os.path.join(ROOT, "profiles", "dense_traffic.json")
+    if not os.path.exists(tp):
+        return None, "no capture committed"
+    d = json.load(open(tp))
+    ent = d.get(family)
+    if not ent:
+        return None, "no capture for this kernel"
+    src = os.path.join(ROOT, "dispu_b200", "csrc", ent["source"])
+    sha = hashlib.sha256(open(src, "rb").read()).hexdigest()
+    if sha != ent.get("source_sha256"):
+        return None, f"profiles/dense_traffic.json was captured from a different {ent['source']} (stale): re-run tools/capture_traffic.sh"
+    return ent["dram_bytes_per_launch"], f"profiles/dense_traffic.json ({ent.get('how', 'ncu dram__bytes_read+write')})"
 
 
-def dominant_kernel_roofline(gen, d_inp, d_gt, stream, flush, reps=10):
+def dominant_kernel_roofline(wl, stream, flush, reps=10):
     """Per-kernel device time INSIDE the step: the step runs eagerly `reps` times with a CUDA-event pair around
     every C-ABI call of this library (dispu_b200._t._profile; a spin kernel at the head of each step keeps the
     launch queue full so the pairs bracket execution, not host launch latency; L2 flushed before each step).
     Reports the roofline of the kernel family with the largest share of the step:
-    achieved = ALGORITHMIC flops (2*M*K*N of each dense launch) or bytes / measured duration."""
+    achieved = ALGORITHMIC flops or bytes (Workload.alg; DESIGN.md §4) / measured duration."""
     import torch
-    from dispu_b200 import _t, loss_utils
-    hbm, bf16_peak, which = measured_peaks()
-    out_c = torch.zeros((4,), dtype=torch.float32, device=d_inp.device)
+    from dispu_b200 import _t
+    hbm, bf16_peak, sm_mhz, which = measured_peaks()
     recs = []
-    use_streams, gen.use_streams = gen.use_streams, False  # one stream: the event pairs must bracket one kernel each
-    with torch.no_grad():
-        for rep in range(reps + 2):
-            flush.zero_()
-            torch.cuda._sleep(24_000_000)  # ~12 ms of device spin: the whole step is enqueued behind it
-            _t._profile = [] if rep >= 2 else None
-            try:
-                coarse, fine = gen(d_inp)
-                loss_utils.chamfer_hausdorff(coarse, d_gt, out=out_c)
-                loss_utils.chamfer_hausdorff(fine, d_gt, out=out_c)
-                prof = _t._profile
-            finally:
-                _t._profile = None
-            stream.synchronize()
-            if prof:
-                recs.append([(k, a.elapsed_time(b)) for k, a, b in prof])
-    gen.use_streams = use_streams
+    for rep in range(reps + 2):
+        flush.zero_()
+        torch.cuda._sleep(24_000_000)  # ~12 ms of device spin: the whole step is enqueued behind it
+        _t._profile = [] if rep >= 2 else None
+        try:
+            wl.profile_body()
+            prof = _t._profile
+        finally:
+            _t._profile = None
+        stream.synchronize()
+        if prof:
+            recs.append([(k, a.elapsed_time(b)) for k, a, b in prof])
     per_key = {}
     for step in recs:
         for k, ms in step:
@@ -411,53 +791,43 @@ def dominant_kernel_roofline(gen, d_inp, d_gt, stream, flush, reps=10):
             e[0] += ms
             e[1] += 1
     n = len(recs)
-    b, m = d_inp.shape[0], d_inp.shape[1] * UP
-    n_in, kk = d_inp.shape[1], 16
-
-    def alg_bytes(key):
-        """SURVEY.md §8d / DESIGN.md §4 algorithmic bytes of one launch of the non-GEMM kernels at the step's shapes."""
-        nm = key.split(" ")[0]
-        if nm == "dispu_knn":
-            return b * (12 * m + 12 * m + 4 * m * kk)
-        if nm == "dispu_chamfer":
-            return b * (12 * m + 12 * m) + 16
-        if nm == "dispu_group_max_ld":
-            return b * (4 * m * kk + 4 * m * 132 + 4 * m * 132)
-        if nm == "dispu_weightnet_aggregate":
-            return b * m * (4 * kk * 128 + 4 * 2048 + 4 * kk + 12)
-        if nm == "dispu_feature_knn":
-            c = int(key.split(" ")[1].split(",")[3])
-            return b * n_in * (4 * c + 4 * kk)
-        if nm in ("dispu_dense_conv", "dispu_dense_conv_knn"):
-            c = int(key.split(" ")[1].split(",")[2])
-            return b * n_in * (4 * c + 4 * kk + 4 * (72 + c))
-        return None
-
+    fp32 = fp32_peak_tflops(sm_mhz)
     fam = {}
     detail = {}
     for k, (ms_tot, cnt) in per_key.items():
         ms_step, per_step = ms_tot / n, cnt / n
-        ent = {"ms_per_launch": ms_tot / cnt, "launches_per_step": per_step, "ms_per_step": ms_step}
-        if k.startswith("dispu_dense_tf32x3_ex"):
-            f = k.split(" ")
-            M_, K_, N_ = int(f[1][1:]), int(f[2][1:]), int(f[3][1:])
-            fl = 2.0 * M_ * K_ * N_
-            for tok in f[4:]:
-                if tok.startswith("x") and tok.endswith("blocks"):
-                    fl *= int(tok[1:-6])  # column blocks: N per block
-                if tok == "+weightnet":
-                    fl += 2.0 * M_ * N_ * 16  # transposed product with the weight net in the epilogue
-            ent["TFLOPs_algorithmic"] = fl / (ms_tot / cnt) / 1e9
-            fm = fam.setdefault("dense_tf32x3_kernel", {"ms": 0.0, "launches": 0.0, "flops": 0.0})
-            fm["flops"] += fl * per_step
-        else:
-            ab = alg_bytes(k)
-            if ab is not None:
-                ent["alg_bytes"] = ab
-                ent["GBps"] = ab / (ms_tot / cnt * 1e-3) / 1e9
-                ent["frac_of_hbm"] = ent["GBps"] / hbm
-            fm = fam.setdefault(k.split(" ")[0], {"ms": 0.0, "launches": 0.0, "bytes": 0.0})
-            fm["bytes"] = fm.get("bytes", 0.0) + (ab or 0) * per_step
+        ms_l = ms_tot / cnt
+        ent = {"ms_per_launch": ms_l, "launches_per_step": per_step, "ms_per_step": ms_step}
+        nm = k.split(" ")[0]
+        a = wl.alg(k)
+        tensor_fam = nm in ("dispu_dense_tf32x3_ex", "dispu_attention_tf32x3", "dispu_sa_mlp")
+        fname = {"dispu_dense_tf32x3_ex": "dense_tf32x3_kernel", "dispu_attention_tf32x3": "attention_tf32x3_kernel",
+                 "dispu_sa_mlp": "sa_mlp_tc_kernel"}.get(nm, nm)
+        fm = fam.setdefault(fname, {"ms": 0.0, "launches": 0.0, "flops": 0.0, "bytes": 0.0, "tensor": tensor_fam})
+        if a is not None and a[0] == "flops":
+            ent["TFLOPs_algorithmic"] = a[1] / ms_l / 1e9
+            fm["flops"] += a[1] * per_step
+        elif a is not None:
+            ent["alg_bytes"] = a[1]
+            ent["GBps"] = a[1] / (ms_l * 1e-3) / 1e9
+            ent["frac_of_hbm"] = ent["GBps"] / hbm
+        if a is not None and a[0] == "bytes":
+            fm["bytes"] += a[1] * per_step
+        ints = [int(x) for x in k.split(" ")[1].split(",")] if (" " in k and k.split(" ")[1][:1].isdigit()) else []
+        if nm == "dispu_fps" and len(ints) >= 3:
+            b, nn, m = ints[:3]
+            # the cloud is register / shared-memory resident: the sweep-model bytes never reach HBM.  What bounds the kernel is
+            # the dependent step (m-1 of them) and, inside a step, the FP32 distance updates:
+            ent["point_updates_per_ns"] = b * (m - 1) * nn / ms_l / 1e6
+            ent["frac_of_fp32_peak"] = b * (m - 1) * nn * 10.0 / (ms_l * 1e-3) / 1e12 / fp32  # ~10 flop per update
+            ent["us_per_dependent_step"] = ms_l * 1e3 / max(m - 1, 1)
+            ent["compulsory_hbm_bytes"] = b * (12 * nn + 4 * m)
+        if nm in ("dispu_query_ball_point", "dispu_query_ball_point_ws", "dispu_knn", "dispu_chamfer", "dispu_chamfer_ex") and len(ints) >= 3:
+            b, nn, m = ints[:3]
+            pairs = (2.0 if nm.startswith("dispu_chamfer") else 1.0) * b * nn * m
+            # brute-force-equivalent distance tests (the grid ball query visits far fewer candidates: an ALGORITHMIC rate)
+            ent["equiv_distance_tests_per_ns"] = pairs / ms_l / 1e6
+            ent["equiv_frac_of_fp32_peak"] = pairs * 8.0 / (ms_l * 1e-3) / 1e12 / fp32
         fm["ms"] += ms_step
         fm["launches"] += per_step
         detail[k] = ent
@@ -468,24 +838,24 @@ def dominant_kernel_roofline(gen, d_inp, d_gt, stream, flush, reps=10):
     common = {"ms_per_launch": top["ms"] / top["launches"], "launches_per_step": top["launches"],
               "ms_per_step": top["ms"], "library_ms_per_step": lib_ms, "share_of_library_time": shares,
               "how": f"CUDA-event pair around every launch of the step, eager behind a 12 ms device spin, {n} steps, L2 flushed per step",
-              "all": detail}
-    if name == "dense_tf32x3_kernel":
+              "fp32_peak_tflops": fp32, "all": detail}
+    if top["tensor"]:
         achieved = top["flops"] / top["ms"] / 1e9
-        traffic = None  # DRAM bytes per launch from the committed ncu --set full capture of the same step
-        tp = os.path.join(ROOT, "profiles", "r01_dense_traffic.json")
-        if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        return {"bound": "tensor", "kernel": "dense_tf32x3_kernel (tcgen05.mma kind::tf32 TS form, 3xTF32, A operand + FP32 accumulators in TMEM)",
+        traffic, tsrc = kernel_traffic(name)
+        return {"bound": "tensor", "kernel": name + " (tcgen05.mma kind::tf32, 3xTF32, A operand + FP32 accumulators in TMEM)",
                 "achieved": achieved, "peak": bf16_peak, "unit": "TFLOP/s", "frac": achieved / bf16_peak, "traffic": traffic,
-                "traffic_source": "profiles/r01_dense_traffic.json (ncu dram__bytes_read+write, average over the step's dense launches)",
-                "peak_source": which + " dense bf16 burst",
+                "traffic_source": tsrc, "peak_source": which + " dense bf16 burst",
                 "algorithmic_flops_per_launch": top["flops"] / top["launches"],
                 "note": "algorithmic FLOPs = 2*M*K*N of the fp32 contraction; the kernel issues 3x that on the tensor pipe at the TF32 "
                         "rate (half the bf16 rate), so the ceiling for this figure is peak/6; X is read from HBM as fp32 and split on the fly",
                 **common}
     achieved = top["bytes"] / (top["ms"] * 1e-3) / 1e9
+    note = None
+    if name == "dispu_fps":
+        note = ("sweep-model bytes B(m-1)n*16 (SURVEY.md §8d-i: what the reference streams per step); the cloud is on chip here, so the real "
+                "bounds are the dependent-step latency and FP32 updates: see all[...].us_per_dependent_step / frac_of_fp32_peak / compulsory_hbm_bytes")
     return {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-            "traffic": None, "peak_source": which, "algorithmic_bytes_per_launch": top["bytes"] / top["launches"], **common}
+            "traffic": None, "peak_source": which, "algorithmic_bytes_per_launch": top["bytes"] / top["launches"], "note": note, **common}
 
 
 def main():
@@ -494,6 +864,8 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="dispu", choices=["dispu", "reference"])
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"],
+                    help="BASELINE.json config: c2 (default, the headline), c3 set abstraction, c4 two-stage 16x, c5 FPS + ball-query sweep")
     ap.add_argument("--ref-sample", type=int, default=8, help="patches per CPU step (bounded sample of the batch)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--eager-collective", action="store_true", help="issue the all-reduce from the host after the graph replay (round-1 form)")

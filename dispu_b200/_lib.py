@@ -69,6 +69,7 @@ SIGNATURES = {
     "dispu_dense_tf32x3_ex": ([C.POINTER(DenseArgs), _p], _i),
     "dispu_dense_args_size": ([], _sz),
     "dispu_dense_pack_strided": ([_i, _i, _p, _ll, _ll, _i, _ll, _p, _ll, _p], _i),
+    "dispu_attention_tf32x3": ([_i, _i, _p, _ll, _p, _p, _p, _ll, _p], _i),
     "dispu_feature_knn": ([_i, _i, _i, _i, _i, _i, _p, _i, _p, _i, _p, _p, _p], _i),
     "dispu_dense_conv_workspace_bytes": ([_i, _i], _sz),
     "dispu_dense_conv": ([_i, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _sz, _p], _i),

@@ -139,8 +139,10 @@ __device__ __noinline__ void knn_insertion_scan(int n, int k, const float *__res
     }
 }
 
+// __launch_bounds__(.., 4): 64 registers per thread (the compiler settles at 128 otherwise) -> four CTAs = 32 warps per SM;
+// the kernel is a chain of dependent shuffles and shared-memory round trips, so it needs the extra warps to hide them.
 template <bool kTma>
-__global__ void __launch_bounds__(kKsWarps * 32)
+__global__ void __launch_bounds__(kKsWarps * 32, 4)
 knn_select_kernel(int n, int m, int k, const float *__restrict__ data, const float *__restrict__ query,
                   float *__restrict__ dist, int *__restrict__ idx) {
     __shared__ float4 s_tile[kKsChunk];
@@ -207,12 +209,16 @@ knn_select_kernel(int n, int m, int k, const float *__restrict__ data, const flo
                 }
                 continue;
             }
-            // 32 candidates per lane: c = s*32 + lane (conflict-free LDS.128), distances in registers
+            // 32 candidates per lane, distances in registers.  Lane `lane` takes candidate c = s*32 + ((lane + s) & 31) of
+            // slot s: the rotation by s spreads index-periodic structure over the lanes (the generator's coarse cloud is
+            // 4 near-copies of each input point at indices i, i+n/4, ...: unrotated, all copies of a point fall into ONE
+            // lane, the lane minima stop being a useful threshold and the survivor list balloons: 147 vs 84 us at c2);
+            // still one conflict-free LDS.128 per slot (a permutation of the 32 consecutive float4s)
             float d[32];
             float lmin = inf;
 #pragma unroll
             for (int sI = 0; sI < 32; ++sI) {
-                const int c = sI * 32 + lane;
+                const int c = sI * 32 + ((lane + sI) & 31);
                 float v = inf;
                 if (c < tn) {
                     const float4 p = s_tile[c];
@@ -240,7 +246,7 @@ knn_select_kernel(int n, int m, int k, const float *__restrict__ data, const flo
                 const unsigned mask = __ballot_sync(kFull, keep);
                 if (mask) {
                     const int pos = S + __popc(mask & lt_mask);
-                    if (keep && pos < kKsCap) { bd[pos] = d[sI]; bi[pos] = t0 + sI * 32 + lane; }
+                    if (keep && pos < kKsCap) { bd[pos] = d[sI]; bi[pos] = t0 + sI * 32 + ((lane + sI) & 31); }
                     S += __popc(mask);
                 }
             }

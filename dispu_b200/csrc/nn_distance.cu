@@ -127,13 +127,18 @@ __device__ __forceinline__ nn_f32x2 nn_fma2(nn_f32x2 a, nn_f32x2 b, nn_f32x2 c) 
     return r;
 }
 
-// Shape of the launch: kNmThreads queries per CTA against ALL candidates of the other cloud.  Small CTAs on purpose:
-// at the c2 shape (32 clouds x 2 directions x 1024 queries) 128-thread CTAs give 512 CTAs = 3.5 per SM, all resident
-// at once, instead of 256 CTAs of 256 threads in 1.7 waves (the round-1 form, warps active 20 %).
+// Shape of the launch: a CTA of four warps owns kNmQueries = 32 * kNmQt queries; lane l holds kNmQt of them in registers
+// (queries l, l+32, ...), and each WARP scans its own quarter of every candidate tile, so one broadcast LDS.64 triple
+// (x, y, z of a candidate pair) feeds kNmQt * 2 distance evaluations instead of 2: the round-1 form (one query per
+// thread, every thread scanning all candidates) was bound by the shared-memory pipe, not by FP32 (7.8 pair evaluations
+// per clock and SM).  The four partial minima of a query meet in shared memory.  Small CTAs on purpose: 512 CTAs at the
+// c2 shape = 3.5 per SM, all resident at once.
 // kTma: candidate tiles arrive by cp.async.bulk into a raw AoS landing buffer (double-buffered: the copy of tile i+1
 // flies while tile i is searched), completion on an mbarrier (tile_stage.cuh); the CTA then transposes the tile to
 // the x / y / z arrays the packed inner loop reads.  Otherwise the threads stage with __ldg.
 constexpr int kNmThreads = 128;
+constexpr int kNmQt = 4;
+constexpr int kNmQueries = 32 * kNmQt;
 
 template <bool kTma>
 __global__ void __launch_bounds__(kNmThreads)
@@ -143,11 +148,12 @@ nn_min_reduce_kernel(int n, int m, const float *__restrict__ xyz1, const float *
     constexpr int kArr = (kNnTile + 2 + 3) & ~3;
     float *s_x = s_dyn, *s_y = s_dyn + kArr, *s_z = s_dyn + 2 * kArr;
     float *s_raw = s_dyn + 3 * kArr;
+    __shared__ float s_part[kNmThreads / 32][kNmQueries];
     __shared__ float s_red[2][kNmThreads / 32];
     __shared__ __align__(8) uint64_t s_bar[2];
     const int cloud = blockIdx.y, dir = blockIdx.z;
     const int nq = dir == 0 ? n : m, nc = dir == 0 ? m : n;
-    if ((int)blockIdx.x * kNmThreads >= nq) {  // this direction has fewer query chunks
+    if ((int)blockIdx.x * kNmQueries >= nq) {  // this direction has fewer query chunks
         if (threadIdx.x == 0 && (int)blockIdx.x < chunks)
             partials[((size_t)cloud * 2 + dir) * chunks + blockIdx.x] = make_float2(0.f, -1.f);
         return;
@@ -164,16 +170,17 @@ nn_min_reduce_kernel(int n, int m, const float *__restrict__ xyz1, const float *
         }
         __syncthreads();
     }
-    const int j = blockIdx.x * kNmThreads + threadIdx.x;
-    const bool active = j < nq;
-    float qx = 0.f, qy = 0.f, qz = 0.f;
-    if (active) {
-        qx = __ldg(qs + (size_t)j * 3); qy = __ldg(qs + (size_t)j * 3 + 1); qz = __ldg(qs + (size_t)j * 3 + 2);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q0 = blockIdx.x * kNmQueries;
+    nn_f32x2 qx2[kNmQt], qy2[kNmQt], qz2[kNmQt];
+    float best[kNmQt];
+#pragma unroll
+    for (int u = 0; u < kNmQt; ++u) {
+        const int j = min(q0 + u * 32 + lane, nq - 1);
+        const float qx = __ldg(qs + (size_t)j * 3), qy = __ldg(qs + (size_t)j * 3 + 1), qz = __ldg(qs + (size_t)j * 3 + 2);
+        qx2[u] = nn_pack(qx, qx); qy2[u] = nn_pack(qy, qy); qz2[u] = nn_pack(qz, qz);
+        best[u] = __int_as_float(0x7f800000);
     }
-    const nn_f32x2 qx2 = nn_pack(qx, qx), qy2 = nn_pack(qy, qy), qz2 = nn_pack(qz, qz);
-    // candidate 0 apart (tf_nndistance_g.cu:29 initialises with it unconditionally)
-    const float d0 = d2_ref_gpu(__fsub_rn(__ldg(cs), qx), __fsub_rn(__ldg(cs + 1), qy), __fsub_rn(__ldg(cs + 2), qz));
-    float best = __int_as_float(0x7f800000);
     for (int i = 0; i < ntiles; ++i) {
         const int t0 = i * kNnTile;
         const int tn = min(kNnTile, nc - t0);
@@ -199,22 +206,41 @@ nn_min_reduce_kernel(int n, int m, const float *__restrict__ xyz1, const float *
         __syncthreads();
         const nn_f32x2 *x2 = reinterpret_cast<const nn_f32x2 *>(s_x), *y2 = reinterpret_cast<const nn_f32x2 *>(s_y),
                        *z2 = reinterpret_cast<const nn_f32x2 *>(s_z);
-#pragma unroll 8
-        for (int e = 0; e < tn2 / 2; ++e) {
-            const nn_f32x2 dx = nn_sub2(x2[e], qx2), dy = nn_sub2(y2[e], qy2), dz = nn_sub2(z2[e], qz2);
-            const nn_f32x2 d = nn_fma2(dz, dz, nn_fma2(dx, dx, nn_mul2(dy, dy)));
-            float da, db;
-            asm("mov.b64 {%0, %1}, %2;" : "=f"(da), "=f"(db) : "l"(d));
-            best = fminf(best, fminf(da, db));
+        const int npairs = tn2 / 2;
+        const int e_lo = (npairs * warp) / (kNmThreads / 32), e_hi = (npairs * (warp + 1)) / (kNmThreads / 32);
+#pragma unroll 4
+        for (int e = e_lo; e < e_hi; ++e) {
+            const nn_f32x2 cx = x2[e], cy = y2[e], cz = z2[e];
+#pragma unroll
+            for (int u = 0; u < kNmQt; ++u) {
+                const nn_f32x2 dx = nn_sub2(cx, qx2[u]), dy = nn_sub2(cy, qy2[u]), dz = nn_sub2(cz, qz2[u]);
+                const nn_f32x2 d = nn_fma2(dz, dz, nn_fma2(dx, dx, nn_mul2(dy, dy)));
+                float da, db;
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(da), "=f"(db) : "l"(d));
+                best[u] = fminf(best[u], fminf(da, db));
+            }
         }
     }
-    // reference semantics: the result is d0 if d0 is NaN, else the minimum (fminf drops later NaNs, like '<' does)
-    best = (d0 != d0) ? d0 : fminf(best, d0);
-    float s = active ? best : 0.f;
-    float mx = active ? best : -1.f;  // distances are >= 0
+#pragma unroll
+    for (int u = 0; u < kNmQt; ++u) s_part[warp][u * 32 + lane] = best[u];
+    __syncthreads();
+    // thread t = query q0 + t: merge the four warps' minima; candidate 0 apart (tf_nndistance_g.cu:29 initialises with it
+    // unconditionally): the result is d0 if d0 is NaN, else the minimum (fminf drops later NaNs, like '<' does)
+    const int j = q0 + threadIdx.x;
+    const bool active = threadIdx.x < kNmQueries && j < nq;
+    float bq = 0.f;
+    if (active) {
+        const float qx = __ldg(qs + (size_t)j * 3), qy = __ldg(qs + (size_t)j * 3 + 1), qz = __ldg(qs + (size_t)j * 3 + 2);
+        const float d0 = d2_ref_gpu(__fsub_rn(__ldg(cs), qx), __fsub_rn(__ldg(cs + 1), qy), __fsub_rn(__ldg(cs + 2), qz));
+        bq = s_part[0][threadIdx.x];
+#pragma unroll
+        for (int w = 1; w < kNmThreads / 32; ++w) bq = fminf(bq, s_part[w][threadIdx.x]);
+        bq = (d0 != d0) ? d0 : fminf(bq, d0);
+    }
+    float s = active ? bq : 0.f;
+    float mx = active ? bq : -1.f;  // distances are >= 0
     s = warp_sum(s);
     mx = warp_max(mx);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) {
         s_red[0][warp] = s;
         s_red[1][warp] = mx;
@@ -294,7 +320,7 @@ nn_distance_grad_kernel(int n, int m, const float *__restrict__ xyz1, const floa
     }
 }
 
-static inline int nn_chunks(int n, int m) { return ceil_div(n > m ? n : m, kNmThreads); }
+static inline int nn_chunks(int n, int m) { return ceil_div(n > m ? n : m, kNmQueries); }
 
 }  // namespace dispu
 

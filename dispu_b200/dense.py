@@ -201,21 +201,17 @@ class BlockedLinear:
         return out if split is None else (out, out2)
 
 
-def attention_fused(kvq, m_block=128):
-    """EXPERIMENTAL (csrc/attention_tc.cu: compiled, not yet validated on hardware; nothing calls it by default).
-    kvq (b,m,256) = [key 64 | value 64 | query 64 pre-scaled by 1/sqrt(64) | pad]: softmax(q.k^T).v -> (b,m,64) in ONE
-    kernel, the (b,m,m) score tensor is never written.  m % 128 == 0."""
-    import ctypes as C2
+def attention_fused(kvq, m_block=128, out=None):
+    """PointNonLocalCell's softmax(q.k^T).v (Common/ops.py:326-339) in ONE tcgen05 kernel (csrc/attention_tc.cu,
+    dispu_attention_tf32x3): kvq (b,m,256) = [key 64 | value 64 | query 64 pre-scaled by 1/sqrt(64) | pad] -> (b,m,64);
+    the (b,m,m) score tensor is never written.  m % 128 == 0."""
     if kvq.dim() != 3 or kvq.shape[2] != 256 or not kvq.is_contiguous() or kvq.shape[1] % 128:
         raise ValueError("attention_fused expects a contiguous (b, m, 256) tensor with m % 128 == 0")
     b, m, _ = kvq.shape
     nb = m // m_block
     kop = BatchedOperand(b * nb, 64, 128, kvq.device).pack(kvq, 0, 1, 256, m_block * 256)      # N = keys, K = channels
     vop = BatchedOperand(b * nb, 128, 64, kvq.device).pack(kvq, 64, 256, 1, m_block * 256)     # N = channels, K = keys
-    out = torch.empty((b, m, 64), dtype=torch.float32, device=kvq.device)
-    fn = _lib.lib().dispu_attention_tf32x3_experimental
-    fn.argtypes = [C2.c_int, C2.c_int, C2.c_void_p, C2.c_longlong, C2.c_void_p, C2.c_void_p, C2.c_void_p, C2.c_longlong, C2.c_void_p]
-    fn.restype = C2.c_int
-    _lib.check("dispu_attention_tf32x3_experimental",
-               fn(b, m, kvq.data_ptr() + 4 * 128, 256, ptr(kop.packed), ptr(vop.packed), ptr(out), 64, stream_ptr()))
+    if out is None:
+        out = torch.empty((b, m, 64), dtype=torch.float32, device=kvq.device)
+    call("dispu_attention_tf32x3", b, m, kvq.data_ptr() + 4 * 128, 256, ptr(kop.packed), ptr(vop.packed), ptr(out), 64, stream_ptr())
     return out

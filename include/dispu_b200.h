@@ -318,6 +318,15 @@ int dispu_dense_pack_strided(int K, int N, const float *W, long long stride_k, l
                              long long w_batch_stride, void *packed, long long packed_batch_stride,
                              dispu_stream_t stream);
 
+/* Non-local attention of PointNonLocalCell (Common/ops.py:326-339) as ONE tcgen05 kernel, 3xTF32 on both products:
+ *     out[i,:] = sum_j softmax_j(q_i . k_j) v_j     per cloud, channels d = 64, m keys (m % 128 == 0)
+ * so the (b,m,m) score tensor is never written.  q (b,m,64) float, row stride ldq, ALREADY scaled by 1/sqrt(d);
+ * k_packed / v_packed: b*(m/128) packed operands of 64 KB each from dispu_dense_pack_strided, one per (cloud, block of
+ * 128 keys): K as (K=64 channels, N=128 keys), V as (K=128 keys, N=64 channels); out (b,m,64), row stride ldo.
+ * q, out and the packed operands must be 16-byte aligned, ldq and ldo multiples of 4. */
+int dispu_attention_tf32x3(int b, int m, const float *q, long long ldq, const void *k_packed, const void *v_packed,
+                           float *out, long long ldo, dispu_stream_t stream);
+
 /* ---- feature-space kNN + EdgeConv dense block --------------------------------------------- */
 
 /* knn_point_2 (tf_ops/grouping/tf_grouping.py:95-114) as get_edge_feature calls it (Common/ops.py:1866-1868):
