@@ -28,6 +28,14 @@ class DenseArgs(C.Structure):
     ]
 
 
+class MlpChainArgs(C.Structure):
+    """dispu_mlp_chain_args of include/dispu_b200.h (host struct)."""
+    _fields_ = [
+        ("M", _ll), ("K0", _i), ("X", _p), ("ldx", _ll), ("n_layers", _i), ("N", _i * 3), ("W", _p * 3), ("bias", _p * 3),
+        ("relu", _i * 3), ("head", _i), ("Yh", _p * 3), ("ldh", _ll * 3), ("head_base", _p), ("ldb", _ll), ("Yt", _p), ("ldt", _ll),
+    ]
+
+
 # name -> argtypes, exactly the prototypes of include/dispu_b200.h
 SIGNATURES = {
     "dispu_abi_version": ([], C.c_int),
@@ -69,6 +77,8 @@ SIGNATURES = {
     "dispu_dense_tf32x3_ex": ([C.POINTER(DenseArgs), _p], _i),
     "dispu_dense_args_size": ([], _sz),
     "dispu_dense_pack_strided": ([_i, _i, _p, _ll, _ll, _i, _ll, _p, _ll, _p], _i),
+    "dispu_mlp_chain_tf32x3": ([C.POINTER(MlpChainArgs), _p], _i),
+    "dispu_mlp_chain_args_size": ([], _sz),
     "dispu_attention_tf32x3": ([_i, _i, _p, _ll, _p, _p, _p, _ll, _p], _i),
     "dispu_feature_knn": ([_i, _i, _i, _i, _i, _i, _p, _i, _p, _i, _p, _p, _p], _i),
     "dispu_dense_conv_workspace_bytes": ([_i, _i], _sz),
@@ -105,6 +115,8 @@ def lib():
             raise RuntimeError("libdispu_b200.so ABI version mismatch")
         if l.dispu_dense_args_size() != C.sizeof(DenseArgs):
             raise RuntimeError("dispu_dense_args layout mismatch between include/dispu_b200.h and dispu_b200/_lib.py")
+        if l.dispu_mlp_chain_args_size() != C.sizeof(MlpChainArgs):
+            raise RuntimeError("dispu_mlp_chain_args layout mismatch between include/dispu_b200.h and dispu_b200/_lib.py")
         _lib = l
     return _lib
 

@@ -215,3 +215,85 @@ def attention_fused(kvq, m_block=128, out=None):
         out = torch.empty((b, m, 64), dtype=torch.float32, device=kvq.device)
     call("dispu_attention_tf32x3", b, m, kvq.data_ptr() + 4 * 128, 256, ptr(kop.packed), ptr(vop.packed), ptr(out), 64, stream_ptr())
     return out
+
+
+class ChainedMLP:
+    """Two or three dense layers as ONE launch (csrc/mlp_chain_tc.cu, dispu_mlp_chain_tf32x3): the intermediate
+    activations stay in tensor memory.  layers: [(W (K,N), bias | None, relu: bool), ...] with N1 <= 256, N2 <= 64,
+    N3 <= 256.  `head` (1..4): the LAST layer's first `head` output columns are the "head" (e.g. the 3 coordinates of the
+    regressor, Common/ops.py:1089-1110); the remaining columns of the last layer, if any, are the "tail".
+    __call__(x, head_out=[tensors (..., head)], head_base=None | (..., head) tensor, tail_out=None) -> (head tensor, tail
+    tensor | None); with head_base the head is head_base + sigmoid(x) - 0.5 (the offset regressor + generator.py:78-81)."""
+
+    def __init__(self, layers, head=0):
+        if len(layers) not in (2, 3):
+            raise ValueError("ChainedMLP takes two or three layers")
+        self.L = len(layers)
+        self.head = head
+        dev = layers[0][0].device
+        self.packed, self.bias, self.relu, self.N = [], [], [], []
+        k_prev = None
+        for i, (w, bb, relu) in enumerate(layers):
+            w = req(w, torch.float32, 2, f"weight[{i}]")
+            K, N = w.shape
+            if k_prev is not None and K != k_prev:
+                raise ValueError(f"layer {i}: K={K} does not match the previous layer's width {k_prev}")
+            bb = torch.zeros((N,), dtype=torch.float32, device=dev) if bb is None else req(bb, torch.float32, 1, f"bias[{i}]")
+            if i == self.L - 1 and head > 0:
+                # last layer laid out as [16-column head block | tail]: head columns first, zero padding up to 16
+                if not (0 < head <= 4) or head > N:
+                    raise ValueError("head must be in 1..4 and <= the last layer's width")
+                pad = torch.zeros((K, 16 - head), dtype=torch.float32, device=dev)
+                w = torch.cat([w[:, :head], pad, w[:, head:]], dim=1).contiguous()
+                bb = torch.cat([bb[:head], torch.zeros((16 - head,), device=dev), bb[head:]]).contiguous()
+                self.tail = N - head
+                N = w.shape[1]
+            elif i == self.L - 1:
+                self.tail = N
+            nbytes = int(_lib.lib().dispu_dense_packed_bytes(K, N))
+            if nbytes == 0:
+                raise ValueError("ChainedMLP: layer wider than 256 columns")
+            pk = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+            call("dispu_dense_pack", K, N, ptr(w), ptr(pk), stream_ptr())
+            self.packed.append(pk)
+            self.bias.append(bb)
+            self.relu.append(1 if relu else 0)
+            self.N.append(N)
+            k_prev = layers[i][0].shape[1]
+        self.K0 = layers[0][0].shape[0]
+
+    def __call__(self, x, head_out=(), head_base=None, tail_out=None):
+        if x.shape[-1] != self.K0:
+            raise ValueError(f"ChainedMLP expects last dim {self.K0}, got {tuple(x.shape)}")
+        a = _lib.MlpChainArgs()
+        xp, xm, ldx = rows(x, "x")
+        a.M, a.K0, a.X, a.ldx, a.n_layers, a.head = xm, self.K0, xp, ldx, self.L, self.head
+        for l in range(self.L):
+            a.N[l], a.W[l], a.bias[l], a.relu[l] = self.N[l], ptr(self.packed[l]), ptr(self.bias[l]), self.relu[l]
+        head_t = None
+        if self.head > 0:
+            outs = list(head_out)
+            if not outs:
+                outs = [torch.empty((*x.shape[:-1], self.head), dtype=torch.float32, device=x.device)]
+            if len(outs) > 3:
+                raise ValueError("at most three head destinations")
+            for d, o in enumerate(outs):
+                op, om, ldo = rows(o, "head_out")
+                if om != xm or o.shape[-1] != self.head:
+                    raise ValueError("head_out: expected (..., head) tensors with one row per input row")
+                a.Yh[d], a.ldh[d] = op, ldo
+            head_t = outs[0]
+            if head_base is not None:
+                bp, bm, ldb = rows(head_base, "head_base")
+                if bm != xm or head_base.shape[-1] != self.head:
+                    raise ValueError("head_base shape mismatch")
+                a.head_base, a.ldb = bp, ldb
+        tail_t = None
+        if self.tail > 0:
+            tail_t = tail_out if tail_out is not None else torch.empty((*x.shape[:-1], self.tail), dtype=torch.float32, device=x.device)
+            tp, tm, ldt = rows(tail_t, "tail_out")
+            if tm != xm or tail_t.shape[-1] != self.tail:
+                raise ValueError("tail_out shape mismatch")
+            a.Yt, a.ldt = tp, ldt
+        call("dispu_mlp_chain_tf32x3", C.byref(a), stream_ptr())
+        return head_t, tail_t

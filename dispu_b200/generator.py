@@ -73,6 +73,8 @@ class Generator:
         self.fused = fused
         self.fuse_weightnet = os.environ.get("DISPU_FUSE_WEIGHTNET", "1") == "1"
         self.attention = os.environ.get("DISPU_ATTENTION", "fused")  # "fused" (one kernel) | "two_products"
+        # coordinate regressors (fc0 -> fc1 -> fc2) as ONE launch each, activations in tensor memory (csrc/mlp_chain_tc.cu)
+        self.chain = os.environ.get("DISPU_CHAIN", "1") == "1"
         self._bufs = {}
         self._streams = {}
         # independent branches (the 3-D kNN of the coarse cloud, the caller's coarse-loss hook) run on side streams so
@@ -336,8 +338,24 @@ class Generator:
         coarse_feat = xf[..., 4:132]
         self._fx(h, "up_conv2", gather=(dup_idx, dup_q, 1.0), out=coarse_feat.view(b, self.up_ratio, n, 128))
         # ---- coarse coordinate_regressor
-        coarse = self._fx(self._fx(self._fx(coarse_feat, "coarse_fc0"), "coarse_fc1"), "coarse_fc2", act=False)
-        xf[..., 1:4].copy_(coarse)
+        if self.chain:
+            # fc0 -> fc1 -> [fc2 | fc2.Wa] in one launch: the 3 coordinates go straight to every place the next stage reads them
+            # (the dense coarse tensor, columns 1:4 of xf, columns 132:135 of mxz), and the centre term of the hoisted conv0,
+            # qm = coarse.Wa = h2.(W_fc2 Wa) + b_fc2 Wa (exact reassociation), leaves as the tail of the same last layer
+            ch = self._packed.get("_chain_coarse")
+            if ch is None:
+                from .dense import ChainedMLP
+                (w0_, b0_), (w1_, b1_), (w2_, b2_) = P["coarse_fc0"], P["coarse_fc1"], P["coarse_fc2"]
+                wa = P["_f_psq"][0]
+                w2q = torch.cat([w2_, (w2_.double() @ wa.double()).float()], dim=1).contiguous()
+                b2q = torch.cat([b2_, (b2_.double() @ wa.double()).float()]).contiguous()
+                ch = self._packed["_chain_coarse"] = ChainedMLP([(w0_, b0_, True), (w1_, b1_, True), (w2q, b2q, False)], head=3)
+            coarse = torch.empty((b, m, 3), dtype=torch.float32, device=dev)
+            _, qm = ch(coarse_feat, head_out=[coarse, xf[..., 1:4], mxz[..., 132:135]])
+        else:
+            coarse = self._fx(self._fx(self._fx(coarse_feat, "coarse_fc0"), "coarse_fc1"), "coarse_fc2", act=False)
+            xf[..., 1:4].copy_(coarse)
+            qm = None
         # ---- PointShuffle2 (ops.py:1012-1087)
         main = torch.cuda.current_stream(dev)
         forks = []
@@ -396,7 +414,8 @@ class Generator:
             att_v = vop.matmul(scores, softmax_stats=stats)
         nonlocal_pt = self._fx(att_v, "nl_back")
         # local cell: conv0 hoisted to per-point products, gathered + ReLU'd inside conv1's operand load
-        qm = self._fx(coarse, "_f_psq", act=False)   # (b,m,128) = x_i Wa
+        if qm is None:
+            qm = self._fx(coarse, "_f_psq", act=False)   # (b,m,128) = x_i Wa
         # conv1 with the gather fused into its operand load AND the weight net + transposed product fused into its epilogue:
         # neither relu(conv0) nor conv1's (b,m,16,128) output is ever materialised.  (With the A operand in tensor memory the
         # fused epilogue no longer competes with the MMAs for shared-memory bandwidth: 0.23 ms vs 0.21 + 0.12 ms unfused;
@@ -411,12 +430,21 @@ class Generator:
             H = O.weightnet_aggregate(coarse, idx, gf, ww, bw, 1.0 / math.sqrt(1.0 + BN_EPS))  # (b,m,2048)
         # skip connection: max over the group commutes with the centre shift
         self.ops.group_max(xf, idx, out=mxz[..., 0:132])
-        mxz[..., 132:135].copy_(coarse)
+        if not self.chain:
+            mxz[..., 132:135].copy_(coarse)
         skip = self._fx(mxz, "_f_skip")
         g = self._fx(H, "after_conv", residuals=(skip, nonlocal_pt))
         fine_feat = self._fx(g, "aggregation")
-        off = self._fx(self._fx(self._fx(fine_feat, "fine_fc0"), "fine_fc1"), "fine_fc2", act=False)
-        fine = coarse + (torch.sigmoid(off) - 0.5)
+        if self.chain:
+            # fine regressor fc0 -> fc1 -> fc2 in one launch; its epilogue applies sigmoid(x) - 0.5 and adds the coarse cloud
+            ch = self._packed.get("_chain_fine")
+            if ch is None:
+                from .dense import ChainedMLP
+                ch = self._packed["_chain_fine"] = ChainedMLP([(*P["fine_fc0"], True), (*P["fine_fc1"], True), (*P["fine_fc2"], False)], head=3)
+            fine, _ = ch(fine_feat, head_base=coarse)
+        else:
+            off = self._fx(self._fx(self._fx(fine_feat, "fine_fc0"), "fine_fc1"), "fine_fc2", act=False)
+            fine = coarse + (torch.sigmoid(off) - 0.5)
         for st in forks[1:]:
             main.wait_stream(st)
         return coarse, fine

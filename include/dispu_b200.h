@@ -318,6 +318,36 @@ int dispu_dense_pack_strided(int K, int N, const float *W, long long stride_k, l
                              long long w_batch_stride, void *packed, long long packed_batch_stride,
                              dispu_stream_t stream);
 
+/* A chain of two or three dense layers in ONE launch, intermediate activations kept in tensor memory (3xTF32):
+ *     H1 = act1(X . W1 + b1),  H2 = act2(H1 . W2 + b2)  [,  H3 = act3(H2 . W3 + b3)]
+ * — the coordinate regressor of the generator (Common/ops.py:1089-1110) behind its input layer.  HOST struct,
+ * zero-initialise.  X (M,K0) row stride ldx (0 = dense); N[0] <= 256, N[1] <= 64, N[2] <= 256; W[l] packed by
+ * dispu_dense_pack(K_l, N[l]) with K_0 = K0, K_l = N[l-1]; bias[l] (N[l]) or NULL; relu[l] 0/1.
+ * Result of the last layer: with head == 0 all N_last columns go to Yt (row stride ldt, 0 = dense).  With head in 1..4
+ * the last layer is laid out as [16-column head block | tail]: its first `head` columns are written to every non-NULL
+ * Yh[d] (row stride ldh[d], 0 = head) — optionally as head_base[row*ldb + j] + sigmoid(x) - 0.5, the offset regressor
+ * of Common/ops.py:1106-1108 + generator.py:78-81 — and columns 16.. (N_last - 16 of them) go to Yt. */
+typedef struct dispu_mlp_chain_args {
+    long long M;
+    int K0;
+    const float *X;
+    long long ldx;
+    int n_layers;
+    int N[3];
+    const void *W[3];
+    const float *bias[3];
+    int relu[3];
+    int head;
+    float *Yh[3];
+    long long ldh[3];
+    const float *head_base;
+    long long ldb;
+    float *Yt;
+    long long ldt;
+} dispu_mlp_chain_args;
+int dispu_mlp_chain_tf32x3(const dispu_mlp_chain_args *args, dispu_stream_t stream);
+size_t dispu_mlp_chain_args_size(void);
+
 /* Non-local attention of PointNonLocalCell (Common/ops.py:326-339) as ONE tcgen05 kernel, 3xTF32 on both products:
  *     out[i,:] = sum_j softmax_j(q_i . k_j) v_j     per cloud, channels d = 64, m keys (m % 128 == 0)
  * so the (b,m,m) score tensor is never written.  q (b,m,64) float, row stride ldq, ALREADY scaled by 1/sqrt(d);

@@ -1152,3 +1152,35 @@ def test_dense_split_output_blocks(rng):
     np.testing.assert_allclose(y1.cpu().numpy(), np.concatenate(want[:2], -1), rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(y2.cpu().numpy(), want[2], rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(lin(T(x)).cpu().numpy(), np.concatenate(want, -1), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("M,K0,widths,head,base", [(1000, 128, [256, 64, 3], 3, False), (4100, 256, [256, 64, 3], 3, True),
+                                                   (300, 128, [256, 64, 131], 3, False), (777, 40, [48, 24], 0, False),
+                                                   (20000, 128, [256, 64, 160], 0, False), (129, 7, [16, 16, 1], 1, True)])
+def test_mlp_chain_tc(rng, M, K0, widths, head, base):
+    """Two / three dense layers in one launch with the activations kept in tensor memory (csrc/mlp_chain_tc.cu) vs the
+    float64 layer sequence; head columns to several destinations (strided), sigmoid offset on a base, tail columns."""
+    from dispu_b200.dense import ChainedMLP
+    x = rng.standard_normal((M, K0)).astype(np.float32)
+    dims = [K0] + widths
+    ws = [(rng.standard_normal((dims[i], dims[i + 1])) / np.sqrt(dims[i])).astype(np.float32) for i in range(len(widths))]
+    bs = [(rng.standard_normal(dims[i + 1]) * 0.1).astype(np.float32) for i in range(len(widths))]
+    relus = [True] * (len(widths) - 1) + [False]
+    ch = ChainedMLP([(T(w), T(bb), r) for w, bb, r in zip(ws, bs, relus)], head=head)
+    h = x.astype(np.float64)
+    for w, bb, r in zip(ws, bs, relus):
+        h = h @ w.astype(np.float64) + bb
+        h = np.maximum(h, 0) if r else h
+    bt = rng.standard_normal((M, head)).astype(np.float32) if base else None
+    wide = torch.full((M, 10), -7.0, device=dev)
+    outs = [torch.empty((M, head), device=dev), wide[:, 2:2 + head]] if head else []
+    got_h, got_t = ch(T(x), head_out=outs, head_base=None if bt is None else T(bt))
+    if head:
+        want_h = h[:, :head] if bt is None else bt + 1.0 / (1.0 + np.exp(-h[:, :head])) - 0.5
+        np.testing.assert_allclose(got_h.cpu().numpy(), want_h, rtol=2e-5, atol=2e-5)
+        np.testing.assert_allclose(wide[:, 2:2 + head].cpu().numpy(), want_h, rtol=2e-5, atol=2e-5)
+        assert float(wide[:, :2].min()) == -7.0 and float(wide[:, 2 + head:].max()) == -7.0  # neighbours untouched
+    if widths[-1] - head > 0:
+        np.testing.assert_allclose(got_t.cpu().numpy(), h[:, head:], rtol=2e-5, atol=2e-5)
+    else:
+        assert got_t is None

@@ -14,7 +14,7 @@ from dispu_b200 import _lib  # noqa: E402
 from dispu_b200.dense import PackedLinear  # noqa: E402
 
 dev = torch.device("cuda", 0)
-for (M, K, N) in [(32768, 2048, 256), (524288, 128, 128), (32768, 1024, 64)]:
+for (M, K, N) in [tuple(int(v) for v in a.split("x")) for a in sys.argv[1:]] or [(32768, 2048, 256), (524288, 128, 128), (32768, 1024, 64)]:
     x = torch.randn((M, K), device=dev)
     lin = PackedLinear(torch.randn((K, N), device=dev) / K ** 0.5, torch.zeros((N,), device=dev))
     y = torch.empty((M, N), device=dev)
