@@ -79,6 +79,8 @@ SIGNATURES = {
     "dispu_dense_pack_strided": ([_i, _i, _p, _ll, _ll, _i, _ll, _p, _ll, _p], _i),
     "dispu_mlp_chain_tf32x3": ([C.POINTER(MlpChainArgs), _p], _i),
     "dispu_mlp_chain_args_size": ([], _sz),
+    "dispu_attention_pack": ([_i, _i, _p, _ll, _p, _p, _p], _i),
+    "dispu_linear_small": ([_ll, _i, _i, _p, _ll, _p, _p, _i, _p, _ll, _p], _i),
     "dispu_attention_tf32x3": ([_i, _i, _p, _ll, _p, _p, _p, _ll, _p], _i),
     "dispu_feature_knn": ([_i, _i, _i, _i, _i, _i, _p, _i, _p, _i, _p, _p, _p], _i),
     "dispu_dense_conv_workspace_bytes": ([_i, _i], _sz),

@@ -18,6 +18,8 @@
 //  * dispu_weightnet_aggregate — PointShuffle2's weight net + transposed product (Common/ops.py:1062-1067,
 //    weight_net_hidden :181-191): H[i] = transpose(G[i]) . relu(bn(gx.Ww + bw)) without the (b,m,ns,3),
 //    (b,m,ns,ns) and transposed (b,m,C,ns) intermediates.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dispu {
@@ -29,6 +31,7 @@ constexpr int kEcProjW = 4 * kEcG;  // pn | pc | t1 | t2
 struct EcProjArgs {
     const float *w0, *b0, *w1, *b1, *w2, *b2;
     float *proj;  // (b*n, 96); nullptr = no projection
+    long long *dbg;  // development only: clock64 samples of CTA (0,0), thread 0
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -87,6 +90,10 @@ feature_knn_kernel(int n, int m, int c, int k, int skip, const float *__restrict
 #pragma unroll
     for (int u = 0; u < kFkQueriesPerWarp; ++u) { bd[u] = inf; bi[u] = 0x7fffffff; }
 
+    int dbg_i = 0;
+    const bool tr = pj.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
+#define FK_MARK() do { if (tr && dbg_i < 60) pj.dbg[dbg_i++] = clock64(); } while (0)
+    FK_MARK();
     for (int t0 = 0; t0 < n; t0 += kChunk) {
         const int tn = min(kChunk, n - t0);
         __syncthreads();
@@ -95,6 +102,7 @@ feature_knn_kernel(int n, int m, int c, int k, int skip, const float *__restrict
             s_ft[(size_t)l * kStride + p] = __ldg(pts + (size_t)(t0 + p) * ldp + l);
         }
         __syncthreads();
+        FK_MARK();
         for (int p = threadIdx.x; p < kChunk; p += kFkWarps * 32) {
             float r = 0.f;
             if (p < tn)
@@ -102,6 +110,7 @@ feature_knn_kernel(int n, int m, int c, int k, int skip, const float *__restrict
             s_r[p] = r;
         }
         __syncthreads();
+        FK_MARK();
         if (q0 >= m) continue;
 #pragma unroll
         for (int u0 = 0; u0 < kFkQueriesPerWarp; u0 += kQ) {
@@ -121,6 +130,7 @@ feature_knn_kernel(int n, int m, int c, int k, int skip, const float *__restrict
 #pragma unroll
                 for (int w = 0; w < kQ; ++w) rq[w] = __fmaf_rn(sq[w * c + l], sq[w * c + l], rq[w]);
             }
+            FK_MARK();
             float d[kQ][P];
 #pragma unroll
             for (int w = 0; w < kQ; ++w)
@@ -145,6 +155,7 @@ feature_knn_kernel(int n, int m, int c, int k, int skip, const float *__restrict
 #pragma unroll
                 for (int w = 0; w < kQ; ++w) d[w][t] = p < tn ? __fadd_rn(__fmaf_rn(-2.f, d[w][t], rq[w]), rp) : inf;
             }
+            FK_MARK();
             float cd[kQ], nd[kQ];
             int ci[kQ], ni[kQ];
 #pragma unroll
@@ -235,6 +246,7 @@ feature_knn_kernel(int n, int m, int c, int k, int skip, const float *__restrict
             }
 #pragma unroll
             for (int w = 0; w < kQ; ++w) { bd[u0 + w] = nd[w]; bi[u0 + w] = ni[w]; }
+            FK_MARK();
         }
     }
 #pragma unroll
@@ -246,6 +258,7 @@ feature_knn_kernel(int n, int m, int c, int k, int skip, const float *__restrict
             idx[o] = bi[u];
         }
     }
+    FK_MARK();
     if (pj.proj == nullptr) return;
     // ---- EdgeConv projection of this CTA's 32 query points (queries == points here): saves the separate projection
     // launch of dispu_dense_conv.  Same derived weights and the same accumulation order as edge_proj_kernel.
@@ -271,6 +284,7 @@ feature_knn_kernel(int n, int m, int c, int k, int skip, const float *__restrict
         }
     }
     __syncthreads();
+    FK_MARK();
     {   // thread -> (row = tid / 8 of the CTA's 32 queries, 12 of the 96 columns)
         const int rq = tid >> 3, cg = tid & 7;
         const int j = blockIdx.x * (kFkWarps * kFkQueriesPerWarp) + rq;
@@ -296,6 +310,8 @@ feature_knn_kernel(int n, int m, int c, int k, int skip, const float *__restrict
             for (int q4 = 0; q4 < 3; ++q4) o4[q4] = make_float4(acc[4 * q4], acc[4 * q4 + 1], acc[4 * q4 + 2], acc[4 * q4 + 3]);
         }
     }
+    FK_MARK();
+#undef FK_MARK
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -631,6 +647,18 @@ extern "C" size_t dispu_dense_conv_workspace_bytes(int b, int n) {
     return (size_t)b * n * kEcProjW * sizeof(float);
 }
 
+static long long *g_fk_dbg = nullptr;
+extern "C" int dispu__fk_debug_trace(long long *host_out) {  // development only
+    if (!g_fk_dbg || !host_out) return DISPU_EUNSUPPORTED;
+    return (int)cudaMemcpy(host_out, g_fk_dbg, 64 * sizeof(long long), cudaMemcpyDeviceToHost);
+}
+
+namespace dispu {
+// tensor-core form of the per-edge MLP (edgeconv_tc.cu); returns false when the shape is not one it is built for
+bool edge_mlp_tc_launch(long long rows, int n, int c, int k, int growth, const float *proj, const int *idx, const float *w1,
+                        const float *w2, const float *feat, int ldf, float *out, int ldo, cudaStream_t stream, int *rc);
+}  // namespace dispu
+
 static int dense_conv_impl(int b, int n, int c, int k, int growth, const float *feat, int ldf, const int *idx, int *idx_out,
                            const float *w0, const float *b0, const float *w1, const float *b1, const float *w2, const float *b2,
                            float *out, int ldo, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
@@ -647,7 +675,10 @@ static int dense_conv_impl(int b, int n, int c, int k, int growth, const float *
     if (idx_out) {
         // neighbour search and projection in ONE kernel (get_edge_feature: k+1 nearest in feature space, self dropped)
         DISPU_REQUIRE(k + 1 <= n && k + 1 <= 32, DISPU_EUNSUPPORTED);
-        EcProjArgs pj{w0, b0, w1, b1, w2, b2, proj};
+        static long long *dbg = nullptr;  // development only (DISPU_FK_TRACE)
+        if (getenv("DISPU_FK_TRACE") && !dbg) { cudaMalloc(&dbg, 64 * sizeof(long long)); g_fk_dbg = dbg; }
+        if (dbg) cudaMemsetAsync(dbg, 0, 64 * sizeof(long long), stream);
+        EcProjArgs pj{w0, b0, w1, b1, w2, b2, proj, dbg};
         const int rc = feature_knn_dispatch(b, n, n, c, k + 1, 1, feat, ldf, feat, ldf, nullptr, idx_out, stream, pj);
         if (rc != DISPU_OK) return rc;
         idx = idx_out;
@@ -658,6 +689,10 @@ static int dense_conv_impl(int b, int n, int c, int k, int growth, const float *
         count_launch();
         edge_proj_kernel<<<(unsigned)ceil_div64(rows, kEcProjRows), kEcThreads, smem, stream>>>(rows, c, feat, ldf, w0, b0, w1, b1,
                                                                                               w2, b2, proj);
+    }
+    {   // k = 16: the per-edge products run on tcgen05 (activations in tensor memory); other k: packed-FFMA2 kernel below
+        int rc = DISPU_OK;
+        if (edge_mlp_tc_launch(rows, n, c, k, growth, proj, idx, w1, w2, feat, ldf, out, ldo, stream, &rc)) return rc;
     }
     count_launch();
     const unsigned g2 = (unsigned)ceil_div64(rows, kEcThreads / kEcLanes);

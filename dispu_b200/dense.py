@@ -201,19 +201,47 @@ class BlockedLinear:
         return out if split is None else (out, out2)
 
 
-def attention_fused(kvq, m_block=128, out=None):
+def attention_fused(kvq, out=None):
     """PointNonLocalCell's softmax(q.k^T).v (Common/ops.py:326-339) in ONE tcgen05 kernel (csrc/attention_tc.cu,
     dispu_attention_tf32x3): kvq (b,m,256) = [key 64 | value 64 | query 64 pre-scaled by 1/sqrt(64) | pad] -> (b,m,64);
     the (b,m,m) score tensor is never written.  m % 128 == 0."""
     if kvq.dim() != 3 or kvq.shape[2] != 256 or not kvq.is_contiguous() or kvq.shape[1] % 128:
         raise ValueError("attention_fused expects a contiguous (b, m, 256) tensor with m % 128 == 0")
     b, m, _ = kvq.shape
-    nb = m // m_block
-    kop = BatchedOperand(b * nb, 64, 128, kvq.device).pack(kvq, 0, 1, 256, m_block * 256)      # N = keys, K = channels
-    vop = BatchedOperand(b * nb, 128, 64, kvq.device).pack(kvq, 64, 256, 1, m_block * 256)     # N = channels, K = keys
+    nb = m // 128
+    key = (b, m, str(kvq.device))
+    bufs = _attn_operands.get(key)
+    if bufs is None:  # packed K / V operands: 64 KB per (cloud, 128-key block) each
+        bufs = _attn_operands[key] = (torch.empty((b * nb * 65536,), dtype=torch.uint8, device=kvq.device),
+                                      torch.empty((b * nb * 65536,), dtype=torch.uint8, device=kvq.device))
+    kp, vp = bufs
+    if os.environ.get("DISPU_ATTENTION_PACK", "fused") == "fused":
+        call("dispu_attention_pack", b, m, ptr(kvq), 256, ptr(kp), ptr(vp), stream_ptr())
+    else:  # the generic strided pack kernel, twice (kept for A/B)
+        call("dispu_dense_pack_strided", 64, 128, ptr(kvq), 1, 256, b * nb, 128 * 256, ptr(kp), 65536, stream_ptr())
+        call("dispu_dense_pack_strided", 128, 64, kvq.data_ptr() + 4 * 64, 256, 1, b * nb, 128 * 256, ptr(vp), 65536, stream_ptr())
     if out is None:
         out = torch.empty((b, m, 64), dtype=torch.float32, device=kvq.device)
-    call("dispu_attention_tf32x3", b, m, kvq.data_ptr() + 4 * 128, 256, ptr(kop.packed), ptr(vop.packed), ptr(out), 64, stream_ptr())
+    call("dispu_attention_tf32x3", b, m, kvq.data_ptr() + 4 * 128, 256, ptr(kp), ptr(vp), ptr(out), 64, stream_ptr())
+    return out
+
+
+_attn_operands = {}
+
+
+def linear_small(x, w, bias=None, relu=False, out=None):
+    """y = act(x . W + b) for K <= 8 input channels on CUDA cores (dispu_linear_small): the generator's 3 -> 24 layer0."""
+    w = req(w, torch.float32, 2, "weight")
+    K, N = w.shape
+    if x.shape[-1] != K:
+        raise ValueError(f"linear_small expects last dim {K}")
+    xp, xm, ldx = rows(x, "x")
+    if out is None:
+        out = torch.empty((*x.shape[:-1], N), dtype=torch.float32, device=x.device)
+    yp, ym, ldy = rows(out, "out")
+    if ym != xm or out.shape[-1] != N:
+        raise ValueError("linear_small: out shape mismatch")
+    call("dispu_linear_small", xm, K, N, xp, ldx, ptr(w), ptr(bias), 1 if relu else 0, yp, ldy, stream_ptr())
     return out
 
 

@@ -321,7 +321,8 @@ class Generator:
         feat, xf, mxz = buf["feat"], buf["xf"], buf["mxz"]
         # ---- feature_extraction_GCN (ops.py:1437-1486): feat = [blk4 | blk3 | blk2 | blk1 (96) | l0 (24)]
         l0 = feat[..., 456:480]
-        self._fx(inputs, "layer0", act=False, out=l0)
+        from .dense import linear_small
+        linear_small(inputs, *P["layer0"], relu=False, out=l0)  # 3 -> 24: a 3-term dot product stays on CUDA cores
         O.dense_conv(l0, [P[f"layer1_l{i}"] for i in range(3)], out=feat[..., 360:456])
         for blk, lo in ((2, 240), (3, 120), (4, 0)):
             prep = self._fx(feat[..., lo + 120:480], f"layer{blk}_prep")

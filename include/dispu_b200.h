@@ -357,6 +357,18 @@ size_t dispu_mlp_chain_args_size(void);
 int dispu_attention_tf32x3(int b, int m, const float *q, long long ldq, const void *k_packed, const void *v_packed,
                            float *out, long long ldo, dispu_stream_t stream);
 
+/* The K and V operands of dispu_attention_tf32x3 in ONE pass from the projected features: kv (b,m,>=128) row stride ld,
+ * columns [0,64) = key, [64,128) = value; k_packed / v_packed receive b*(m/128) operands of 64 KB each, bit-identical
+ * to dispu_dense_pack_strided's.  m % 128 == 0, ld % 4 == 0, 16-byte aligned pointers. */
+int dispu_attention_pack(int b, int m, const float *kv, long long ld, void *k_packed, void *v_packed,
+                         dispu_stream_t stream);
+
+/* y = act(x . W + b) for K <= 8 input channels on CUDA cores (FP32 FMA chain in ascending k): the 3 -> 24 layer0 of
+ * the feature extractor (Common/ops.py:1449-1452).  X (M,K) row stride ldx, W (K,N) row-major, Y (M,N) row stride ldy
+ * (0 = dense). */
+int dispu_linear_small(long long M, int K, int N, const float *X, long long ldx, const float *W, const float *bias,
+                       int relu, float *Y, long long ldy, dispu_stream_t stream);
+
 /* ---- feature-space kNN + EdgeConv dense block --------------------------------------------- */
 
 /* knn_point_2 (tf_ops/grouping/tf_grouping.py:95-114) as get_edge_feature calls it (Common/ops.py:1866-1868):

@@ -1184,3 +1184,26 @@ def test_mlp_chain_tc(rng, M, K0, widths, head, base):
         np.testing.assert_allclose(got_t.cpu().numpy(), h[:, head:], rtol=2e-5, atol=2e-5)
     else:
         assert got_t is None
+
+
+def test_attention_pack_and_linear_small(rng):
+    """dispu_attention_pack writes the same bytes as two dispu_dense_pack_strided calls; dispu_linear_small vs float64."""
+    from dispu_b200._t import call, ptr, stream_ptr
+    from dispu_b200.dense import linear_small
+    b, m = 3, 384
+    kvq = T(rng.standard_normal((b, m, 256)).astype(np.float32))
+    nb = m // 128
+    kp, vp, kr, vr = (torch.zeros((b * nb * 65536,), dtype=torch.uint8, device=dev) for _ in range(4))
+    call("dispu_attention_pack", b, m, ptr(kvq), 256, ptr(kp), ptr(vp), stream_ptr())
+    call("dispu_dense_pack_strided", 64, 128, ptr(kvq), 1, 256, b * nb, 128 * 256, ptr(kr), 65536, stream_ptr())
+    call("dispu_dense_pack_strided", 128, 64, kvq.data_ptr() + 4 * 64, 256, 1, b * nb, 128 * 256, ptr(vr), 65536, stream_ptr())
+    assert torch.equal(kp, kr) and torch.equal(vp, vr)
+    x = rng.standard_normal((2, 999, 3)).astype(np.float32)
+    w = rng.standard_normal((3, 24)).astype(np.float32)
+    bb = rng.standard_normal(24).astype(np.float32)
+    wide = torch.zeros((2, 999, 40), device=dev)
+    linear_small(T(x), T(w), T(bb), relu=True, out=wide[..., 8:32])
+    np.testing.assert_allclose(wide[..., 8:32].cpu().numpy(), np.maximum(x.astype(np.float64) @ w + bb, 0), rtol=1e-6, atol=1e-6)
+    assert float(wide[..., :8].abs().max()) == 0 and float(wide[..., 32:].abs().max()) == 0
+    got = linear_small(T(x[..., :2].copy()), T(w[:2, :5].copy())).cpu().numpy()
+    np.testing.assert_allclose(got, x[..., :2].astype(np.float64) @ w[:2, :5], rtol=1e-6, atol=1e-6)
