@@ -78,8 +78,10 @@ class Generator:
         self._bufs = {}
         self._streams = {}
         # independent branches (the 3-D kNN of the coarse cloud, the caller's coarse-loss hook) run on side streams so
-        # they overlap the non-local branch; inside a CUDA graph this becomes a fork/join.  DISPU_STREAMS=0: one stream.
-        self.use_streams = os.environ.get("DISPU_STREAMS", "1") == "1"
+        # they can overlap the non-local branch; inside a CUDA graph this becomes a fork/join.  Opt-in (DISPU_STREAMS=1): measured
+        # neutral on B200 — the persistent tensor-core kernels fill every SM (registers, shared and tensor memory), so the side
+        # stream's CTAs only run in the gaps they would have had anyway.
+        self.use_streams = os.environ.get("DISPU_STREAMS", "0") == "1"
         self._dup_idx = {}
         self._packed = {}
         self.hoist = hoist  # use the fused / hoisted grouped-layer formulation when the backend offers it

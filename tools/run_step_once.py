@@ -17,6 +17,7 @@ dev = torch.device("cuda", 0)
 inp, gt = bench.synth_batch(0)
 x, g = torch.from_numpy(inp).to(dev), torch.from_numpy(gt).to(dev)
 gen = Generator(device=dev)
+gen.use_streams = False
 out = torch.zeros((4,), device=dev)
 with torch.no_grad():
     for _ in range(steps):
