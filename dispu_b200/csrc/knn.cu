@@ -209,8 +209,8 @@ knn_select_kernel(int n, int m, int k, const float *__restrict__ data, const flo
                 }
                 continue;
             }
-            // 32 candidates per lane, distances in registers.  Lane `lane` takes candidate c = s*32 + ((lane + s) & 31) of
-            // slot s: the rotation by s spreads index-periodic structure over the lanes (the generator's coarse cloud is
+            // 32 candidates per lane, distances in registers.  Lane `lane` takes candidate c = s*32 + (lane ^ s) of
+            // slot s: the permutation by s spreads index-periodic structure over the lanes (the generator's coarse cloud is
             // 4 near-copies of each input point at indices i, i+n/4, ...: unrotated, all copies of a point fall into ONE
             // lane, the lane minima stop being a useful threshold and the survivor list balloons: 147 vs 84 us at c2);
             // still one conflict-free LDS.128 per slot (a permutation of the 32 consecutive float4s)
@@ -218,7 +218,7 @@ knn_select_kernel(int n, int m, int k, const float *__restrict__ data, const flo
             float lmin = inf;
 #pragma unroll
             for (int sI = 0; sI < 32; ++sI) {
-                const int c = sI * 32 + ((lane + sI) & 31);
+                const int c = sI * 32 + (lane ^ sI);
                 float v = inf;
                 if (c < tn) {
                     const float4 p = s_tile[c];
@@ -246,7 +246,7 @@ knn_select_kernel(int n, int m, int k, const float *__restrict__ data, const flo
                 const unsigned mask = __ballot_sync(kFull, keep);
                 if (mask) {
                     const int pos = S + __popc(mask & lt_mask);
-                    if (keep && pos < kKsCap) { bd[pos] = d[sI]; bi[pos] = t0 + sI * 32 + ((lane + sI) & 31); }
+                    if (keep && pos < kKsCap) { bd[pos] = d[sI]; bi[pos] = t0 + sI * 32 + (lane ^ sI); }
                     S += __popc(mask);
                 }
             }
@@ -284,6 +284,120 @@ knn_select_kernel(int n, int m, int k, const float *__restrict__ data, const flo
             const size_t o = ((size_t)cloud * m + j) * k + lane;
             if (dist) dist[o] = ld[u];
             idx[o] = li[u];
+        }
+    }
+}
+
+// ---- single-chunk form (n <= 1024, the generator's clouds): everything of a query lives in registers -------------------
+// The generic kernel above carries per-query state across chunks in arrays indexed by the query loop (local memory at
+// 64 registers) and compacts survivors with one ballot per candidate slot; an instruction-level profile (ncu source page,
+// profiles/r02_step_others_ncu.md: issue-bound at 76 %, 1618 warp instructions per query) put 40 % of the work into the
+// distance loop's index / guard / local-memory overhead and 27 % into the 32 ballots.  With the whole cloud in ONE
+// chunk there is no carried list: the query is three scalars, a lane marks its survivors in a 32-bit mask (one compare
+// per slot), a warp prefix sum over the 32 counts gives every lane its write offset, and the ranked result goes straight
+// to global memory.  Same selection rule and the same fallback as the generic kernel.
+template <bool kTma>
+__global__ void __launch_bounds__(kKsWarps * 32, 4)
+knn_select1_kernel(int n, int m, int k, const float *__restrict__ data, const float *__restrict__ query,
+                   float *__restrict__ dist, int *__restrict__ idx) {
+    __shared__ float4 s_tile[kKsChunk];
+    extern __shared__ __align__(16) float s_raw[];  // kTma: one 12 KB landing buffer (cp.async.bulk)
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ float s_bd[kKsWarps][kKsCap];
+    __shared__ int s_bi[kKsWarps][kKsCap];
+    __shared__ float s_od[kKsWarps][32];
+    __shared__ int s_oi[kKsWarps][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cloud = blockIdx.y;
+    const float *pts = data + (size_t)cloud * n * 3;
+    const int q0 = (blockIdx.x * kKsWarps + warp) * kKsQueriesPerWarp;
+    const float inf = __int_as_float(0x7f800000);
+    float *bd = s_bd[warp];
+    int *bi = s_bi[warp];
+    ts::stage_begin<kTma>(s_raw, s_bar, pts, n, kKsChunk);
+    const int tn = ts::stage_tile<kTma>(s_tile, s_raw, s_bar, pts, n, kKsChunk, 0, 1);
+    if (q0 >= m) return;
+#pragma unroll 1
+    for (int u = 0; u < kKsQueriesPerWarp; ++u) {
+        const int j = q0 + u;
+        if (j >= m) break;
+        const float *q = query + ((size_t)cloud * m + j) * 3;
+        const float qx = __ldg(q), qy = __ldg(q + 1), qz = __ldg(q + 2);
+        // candidate of slot s for this lane: c = s*32 + (lane ^ s) (see the generic kernel: spreads index-periodic clouds)
+        float d[32];
+        float lmin = inf;
+        if (tn == kKsChunk) {
+#pragma unroll
+            for (int sI = 0; sI < 32; ++sI) {
+                const float4 p = s_tile[sI * 32 + (lane ^ sI)];
+                // diff = query - data, accumulated dimension by dimension (nanoflann.hpp:323-348)
+                d[sI] = d2_ref_cpu(__fsub_rn(qx, p.x), __fsub_rn(qy, p.y), __fsub_rn(qz, p.z));
+                lmin = fminf(lmin, d[sI]);
+            }
+        } else {
+#pragma unroll
+            for (int sI = 0; sI < 32; ++sI) {
+                const int c = sI * 32 + (lane ^ sI);
+                const float4 p = s_tile[c < tn ? c : 0];
+                const float v = d2_ref_cpu(__fsub_rn(qx, p.x), __fsub_rn(qy, p.y), __fsub_rn(qz, p.z));
+                d[sI] = c < tn ? v : inf;
+                lmin = fminf(lmin, d[sI]);
+            }
+        }
+        const float tau = __shfl_sync(kFull, warp_sort32_asc(lmin, lane), k - 1);
+        // my survivors as a bit mask, then a warp prefix sum of the counts
+        unsigned mine = 0;
+#pragma unroll
+        for (int sI = 0; sI < 32; ++sI) mine |= (d[sI] <= tau && d[sI] < inf) ? (1u << sI) : 0u;
+        const int cnt = __popc(mine);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int S = __shfl_sync(kFull, incl, 31);
+        float rd = inf;
+        int ri = 0;
+        if (S > kKsCap) {  // masses of exactly equal distances: the serial definition
+            knn_insertion_scan(n, k, pts, qx, qy, qz, lane, rd, ri);
+        } else {
+            int pos = incl - cnt;
+#pragma unroll
+            for (int sI = 0; sI < 32; ++sI) {
+                if (mine & (1u << sI)) {
+                    bd[pos] = d[sI];
+                    bi[pos] = sI * 32 + (lane ^ sI);
+                    ++pos;
+                }
+            }
+            __syncwarp();
+            // rank by counting on the (d, idx) key; ranks < 32 are the answer, ascending
+            for (int e0 = 0; e0 < S; e0 += 32) {
+                const int e = e0 + lane;
+                const float de = e < S ? bd[e] : inf;
+                const int ie = e < S ? bi[e] : 0x7fffffff;
+                int rank = 0;
+                for (int f = 0; f < S; ++f) {
+                    const float df = bd[f];
+                    const int jf = bi[f];
+                    rank += (df < de) || (df == de && jf < ie);
+                }
+                if (e < S && rank < 32) {
+                    s_od[warp][rank] = de;
+                    s_oi[warp][rank] = ie;
+                }
+            }
+            __syncwarp();
+            const int have = min(S, 32);
+            rd = lane < have ? s_od[warp][lane] : inf;
+            ri = lane < have ? s_oi[warp][lane] : 0;
+            __syncwarp();
+        }
+        if (lane < k) {
+            const size_t o = ((size_t)cloud * m + j) * k + lane;
+            if (dist) dist[o] = rd;
+            idx[o] = ri;
         }
     }
 }
@@ -459,6 +573,15 @@ extern "C" int dispu_knn(int b, int n, int m, int k, const float *xyz1, const fl
     DISPU_REQUIRE(b <= 65535, DISPU_EUNSUPPORTED);
     if (k <= 32) {
         const dim3 grid(ceil_div(m, kKsWarps * kKsQueriesPerWarp), b);
+        static const bool generic = getenv("DISPU_KNN_GENERIC") != nullptr;  // development switch (A/B timing)
+        if (n <= kKsChunk && !generic) {  // whole cloud in one chunk: the register-resident form
+            count_launch();
+            if (knn_use_tma(xyz1, n))
+                knn_select1_kernel<true><<<grid, kKsWarps * 32, (size_t)kKsChunk * 12, stream>>>(n, m, k, xyz1, xyz2, dist, idx);
+            else
+                knn_select1_kernel<false><<<grid, kKsWarps * 32, 0, stream>>>(n, m, k, xyz1, xyz2, dist, idx);
+            return finish_launch();
+        }
         if (knn_use_tma(xyz1, n)) {
             const cudaError_t e = cudaFuncSetAttribute(knn_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kKsChunk * 12);
             if (e != cudaSuccess) return (int)e;
