@@ -21,6 +21,7 @@ namespace dispu {
 constexpr int kBqWarps = 8;
 constexpr int kBqThreads = kBqWarps * 32;
 constexpr int kBqMaxQpc = 64;   // queries per CTA (<= 8 per warp)
+constexpr int kBqQi = 4;        // queries a warp scans together (independent ballot / count chains)
 constexpr int kBqTile = 4096;   // points per shared-memory tile (48 KB)
 
 __device__ __forceinline__ float ball_s_max(float r, bool &any) {
@@ -97,33 +98,59 @@ ball_query_kernel(int n, int m, const float *__restrict__ radius, int ns, const 
             __syncthreads();
         }
         bool all_done = true;
-        for (int q = warp; q < nq; q += kBqWarps) {
-            int cnt = s_cnt[q];
-            if (cnt >= ns) continue;
-            int first = s_first[q];
-            const float qx = __ldg(qs + q * 3), qy = __ldg(qs + q * 3 + 1), qz = __ldg(qs + q * 3 + 2);
-            int *row = rows + (size_t)q * ns;
-            for (int k0 = 0; k0 < tn && cnt < ns; k0 += 32) {
+        // kBqQi queries per warp at a time: one candidate load feeds kBqQi distance tests and the kBqQi ballot -> count ->
+        // store chains are independent, so their latencies overlap (a single query's scan is one long dependent chain:
+        // ballot, popc, the slot store and the exit test all wait for the previous step's count)
+        for (int qb = warp * kBqQi; qb < nq; qb += kBqWarps * kBqQi) {
+            int cnt[kBqQi], first[kBqQi];
+            float qx[kBqQi], qy[kBqQi], qz[kBqQi];
+            int *row[kBqQi];
+#pragma unroll
+            for (int u = 0; u < kBqQi; ++u) {
+                const int q = min(qb + u, nq - 1);
+                cnt[u] = qb + u < nq ? s_cnt[q] : ns;  // queries past the end count as finished
+                first[u] = s_first[q];
+                qx[u] = __ldg(qs + q * 3); qy[u] = __ldg(qs + q * 3 + 1); qz[u] = __ldg(qs + q * 3 + 2);
+                row[u] = rows + (size_t)q * ns;
+            }
+            for (int k0 = 0; k0 < tn; k0 += 32) {
+                bool open = false;
+#pragma unroll
+                for (int u = 0; u < kBqQi; ++u) open = open || cnt[u] < ns;
+                if (!open) break;
                 const int k = k0 + lane;
-                bool hit = false;
+                float px = 0.f, py = 0.f, pz = 0.f;
                 if (k < tn) {
-                    const float px = kTma ? raw[3 * k] : sx[k], py = kTma ? raw[3 * k + 1] : sy[k], pz = kTma ? raw[3 * k + 2] : sz[k];
-                    const float s = d2_ref_gpu(__fsub_rn(qx, px), __fsub_rn(qy, py), __fsub_rn(qz, pz));
-                    hit = any && !(s > smax);
+                    px = kTma ? raw[3 * k] : sx[k]; py = kTma ? raw[3 * k + 1] : sy[k]; pz = kTma ? raw[3 * k + 2] : sz[k];
                 }
-                const unsigned mask = __ballot_sync(kFull, hit);
-                if (mask) {
-                    if (cnt == 0) first = t0 + k0 + __ffs(mask) - 1;
-                    const int pos = cnt + __popc(mask & lt_mask);
-                    if (hit && pos < ns) row[pos] = t0 + k;
-                    cnt += __popc(mask);
+                unsigned mask[kBqQi];
+                bool hit[kBqQi];
+#pragma unroll
+                for (int u = 0; u < kBqQi; ++u) {
+                    const float s = d2_ref_gpu(__fsub_rn(qx[u], px), __fsub_rn(qy[u], py), __fsub_rn(qz[u], pz));
+                    hit[u] = k < tn && any && !(s > smax) && cnt[u] < ns;
+                    mask[u] = __ballot_sync(kFull, hit[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < kBqQi; ++u) {
+                    if (mask[u]) {
+                        if (cnt[u] == 0) first[u] = t0 + k0 + __ffs(mask[u]) - 1;
+                        const int pos = cnt[u] + __popc(mask[u] & lt_mask);
+                        if (hit[u] && pos < ns) row[u][pos] = t0 + k;
+                        cnt[u] += __popc(mask[u]);
+                    }
                 }
             }
-            if (lane == 0) {
-                s_cnt[q] = cnt;
-                s_first[q] = first;
+#pragma unroll
+            for (int u = 0; u < kBqQi; ++u) {
+                if (qb + u < nq) {
+                    if (lane == 0) {
+                        s_cnt[qb + u] = cnt[u];
+                        s_first[qb + u] = first[u];
+                    }
+                    all_done = all_done && (cnt[u] >= ns);
+                }
             }
-            all_done = all_done && (cnt >= ns);
         }
         if (__syncthreads_and(all_done)) break;
         pending = -1;  // the next iteration waits for it
@@ -152,9 +179,9 @@ extern "C" int dispu_query_ball_point(int b, int n, int m, const float *radius, 
     if (b == 0 || m == 0) return DISPU_OK;
     DISPU_REQUIRE(radius && xyz1 && xyz2 && idx && pts_cnt, DISPU_ENULL);
     DISPU_REQUIRE(b <= 65535, DISPU_EUNSUPPORTED);
-    // queries per CTA: as many as keeps >= 2 CTAs per SM in flight, 8..64
+    // queries per CTA: as many as keeps >= 2 CTAs per SM in flight, 32..64
     int qpw = (int)(((long long)b * m) / ((long long)kBqWarps * 2 * kNumSMs));
-    qpw = qpw < 1 ? 1 : (qpw > 8 ? 8 : qpw);
+    qpw = qpw < kBqQi ? kBqQi : (qpw > 8 ? 8 : qpw);  // at least kBqQi: a warp scans kBqQi queries together
     const int qpc = qpw * kBqWarps;
     const int tile = n < kBqTile ? ((n + 31) & ~31) : kBqTile;
     static const bool no_tma = getenv("DISPU_NO_TMA") != nullptr;  // development switch (A/B timing)

@@ -78,8 +78,9 @@ __device__ __forceinline__ void epilogue_hidden(uint32_t tmem_row, int dcol, int
 
 // Last-layer epilogue: max over the NS rows (= lanes) of my group for COLS columns, then bias + ReLU on
 // the winner only.  max_rows(relu(x+b)) == relu(max_rows(x)+b) exactly (fp add is monotone in x), so
-// the reduction runs on the RAW accumulator through an order-preserving float->int key and ONE
-// redux.sync.max.s32 per column; lane (c % NS) of the group keeps column c and stores it coalesced.
+// the reduction runs on the RAW accumulator through an order-preserving float->int key — ONE
+// redux.sync.max.s32 per column when a group is a whole warp, a shuffle butterfly otherwise; lane (c % NS) of the group
+// keeps column c and stores it coalesced.
 template <int NS, int COLS>
 __device__ __forceinline__ void epilogue_pool(uint32_t tmem_d_row, int N, int c0, const float *sb, unsigned gmask,
                                               int lane, bool gvalid, float *out_row) {
@@ -94,8 +95,16 @@ __device__ __forceinline__ void epilogue_pool(uint32_t tmem_d_row, int N, int c0
 #pragma unroll
     for (int j = 0; j < COLS; ++j) {
         const int b = (int)v[j];
-        const int key = b ^ ((b >> 31) & 0x7fffffff);  // signed-int order == float order
-        const int mx = __reduce_max_sync(gmask, key);
+        int mx = b ^ ((b >> 31) & 0x7fffffff);  // signed-int order == float order
+        if (NS == 32) {
+            mx = __reduce_max_sync(gmask, mx);
+        } else {
+            // groups smaller than a warp: xor-shuffle butterfly over the NS lanes of the group.  (redux.sync with one member
+            // mask per group returns through a UNIFORM register, so the compiler serialises the groups of a warp behind
+            // divergence code — measured ~10x slower than the shuffles in edgeconv_tc.cu's trace)
+#pragma unroll
+            for (int off = NS / 2; off > 0; off >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+        }
         if ((j % NS) == lm) keep[j / NS] = mx;
     }
     if (gvalid) {
