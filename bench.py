@@ -625,11 +625,25 @@ def run_product(args, rank, world, local_rank):
     has_coll = world > 1 and wl.collective is not None
     in_graph_collective = has_coll and not args.eager_collective
 
+    peer = None
+    if has_coll and args.collective == "peer":
+        # this library's own NVLink peer-memory all-reduce kernel (csrc/peer_reduce.cu); every rank takes the same
+        # decision inside PeerAllReduce, so a fallback to NCCL is collective too
+        from dispu_b200.dist import PeerAllReduce
+        try:
+            peer = PeerAllReduce(dev)
+        except RuntimeError as e:
+            if rank == 0:
+                print(f"[bench] {e}; using ncclAllReduce", file=sys.stderr)
+
     def allreduce():
         # ONE collective on the path: sum of the per-rank Chamfer partials, enqueued on the step's
-        # stream — inside the captured CUDA graph, so a replay contains the ncclAllReduce kernel and no host work;
+        # stream — inside the captured CUDA graph, so a replay contains the all-reduce kernel and no host work;
         # (Hausdorff is only logged by the trainer — max over ranks is taken on the host from the same 4 floats)
-        dist.all_reduce(wl.collective, op=dist.ReduceOp.SUM)
+        if peer is not None:
+            peer(wl.collective)
+        else:
+            dist.all_reduce(wl.collective, op=dist.ReduceOp.SUM)
 
     def step_body():
         wl.step_body()
@@ -722,7 +736,8 @@ def run_product(args, rank, world, local_rank):
         cfg.update({"cuda_graph": graph is not None,
                     "l2": "flushed between timed steps (192 MiB memset outside the event pairs)",
                     "sharding": ("single GPU" if world == 1 else
-                                 (f"batch-sharded x{world}, one all-reduce of 2 Chamfer partial sums "
+                                 (f"batch-sharded x{world}, one all-reduce of 2 Chamfer partial sums, "
+                                  f"{'dispu_peer_allreduce_sum (own kernel, NVLink peer stores)' if peer is not None else 'ncclAllReduce'} "
                                   f"({'captured in the CUDA graph' if (in_graph_collective and graph is not None) else 'eager, after the replay'})")
                                  if wl.collective is not None else f"clouds sharded x{world}, no data-path collective")})
         line = {
@@ -868,6 +883,8 @@ def main():
                     help="BASELINE.json config: c2 (default, the headline), c3 set abstraction, c4 two-stage 16x, c5 FPS + ball-query sweep")
     ap.add_argument("--ref-sample", type=int, default=8, help="patches per CPU step (bounded sample of the batch)")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--collective", choices=("peer", "nccl"), default="peer",
+                    help="the path's one all-reduce: this library's NVLink peer-memory kernel (default; single node) or ncclAllReduce")
     ap.add_argument("--eager-collective", action="store_true", help="issue the all-reduce from the host after the graph replay (round-1 form)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     args = ap.parse_args()

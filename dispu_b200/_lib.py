@@ -79,6 +79,12 @@ SIGNATURES = {
     "dispu_dense_pack_strided": ([_i, _i, _p, _ll, _ll, _i, _ll, _p, _ll, _p], _i),
     "dispu_mlp_chain_tf32x3": ([C.POINTER(MlpChainArgs), _p], _i),
     "dispu_mlp_chain_args_size": ([], _sz),
+    "dispu_peer_mailbox_bytes": ([], _sz),
+    "dispu_peer_alloc": ([C.POINTER(_p), C.c_char_p], _i),
+    "dispu_peer_open": ([C.c_char_p, C.POINTER(_p)], _i),
+    "dispu_peer_close": ([_p], _i),
+    "dispu_peer_free": ([_p], _i),
+    "dispu_peer_allreduce_sum": ([_i, _i, _p, _p, _p, _p, _i, _p], _i),
     "dispu_attention_pack": ([_i, _i, _p, _ll, _p, _p, _p], _i),
     "dispu_linear_small": ([_ll, _i, _i, _p, _ll, _p, _p, _i, _p, _ll, _p], _i),
     "dispu_attention_tf32x3": ([_i, _i, _p, _ll, _p, _p, _p, _ll, _p], _i),

@@ -369,6 +369,23 @@ int dispu_attention_pack(int b, int m, const float *kv, long long ld, void *k_pa
 int dispu_linear_small(long long M, int K, int N, const float *X, long long ldx, const float *W, const float *bias,
                        int relu, float *Y, long long ldy, dispu_stream_t stream);
 
+/* ---- the path's one collective over NVLink peer memory ------------------------------------------ */
+
+/* Sum over the ranks of ONE node of a handful of floats (the per-rank Chamfer partials) as a single small kernel per rank:
+ * every rank stores its values into its slot of every peer's "mailbox" (device memory mapped through CUDA IPC), waits
+ * for the peers' slots of its own mailbox, and sums in rank order (bit-identical on every rank).  Setup, once, outside
+ * the timed path: dispu_peer_alloc -> exchange the 64-byte handles through the host process group -> dispu_peer_open for
+ * every other rank -> a DEVICE array `peers` of the `world` mailbox pointers (entry `rank` = the own mailbox) and one
+ * zeroed device uint32 `epoch_ctr`.  dispu_peer_allreduce_sum is CUDA-graph capturable (the epoch advances on the device).
+ * world <= 32, n <= 6.  A missing peer makes the call return NaNs after ~2 s instead of hanging. */
+size_t dispu_peer_mailbox_bytes(void);
+int dispu_peer_alloc(void **mailbox, unsigned char handle_out[64]);
+int dispu_peer_open(const unsigned char handle[64], void **mailbox);
+int dispu_peer_close(void *mailbox);
+int dispu_peer_free(void *mailbox);
+int dispu_peer_allreduce_sum(int world, int rank, void *const *peers, unsigned *epoch_ctr, const float *in, float *out, int n,
+                             dispu_stream_t stream);
+
 /* ---- feature-space kNN + EdgeConv dense block --------------------------------------------- */
 
 /* knn_point_2 (tf_ops/grouping/tf_grouping.py:95-114) as get_edge_feature calls it (Common/ops.py:1866-1868):
