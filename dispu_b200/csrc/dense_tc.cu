@@ -159,6 +159,14 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uin
                  : "memory");
 }
 
+// D (16 x 8, fp32) += A (16 x 8, tf32, row) . B (8 x 8, tf32, col): the warp-level tensor-core instruction, used by the
+// weight-net epilogue for its small per-point contractions (operands are already in registers / shared memory there)
+__device__ __forceinline__ void mma_sync_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
 constexpr int kDnEpiStride = 20;  // floats per staged epilogue row (16 + 4: 16-byte aligned, conflict-free stores)
 
 // kResident: the whole packed weight stays in shared memory for the CTA's lifetime (small K*N) and the pipeline
@@ -180,7 +188,6 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
     __shared__ uint32_t s_tmem;
     __shared__ __align__(16) float s_bias[1024];  // bias of every column block (n_blocks * N <= 1024 when a bias is given)
     __shared__ __align__(16) float s_epi[kDnEpiWarps][32 * kDnEpiStride];
-    __shared__ __align__(16) float s_wn[kEpi == 1 ? 4 : 1][kEpi == 1 ? 32 * 16 : 4];  // weight-net rows of each epilogue warp
     __shared__ float s_wnw[64];                                                          // wn_w (3x16) | wn_b (16)
     __shared__ float s_rsum[2][128][2];  // softmax operand mode: row sums of the two K-halves, per tile parity
 
@@ -481,75 +488,102 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
             }
             if (prm.dbg & 64) {
             } else if (kEpi == 1) {
-                // ---- weight-net epilogue: this warp's 32 rows are two points x 16 samples.  Lane (p, s) first builds
-                // its row of wn from the grouped xyz (both warps of the quarter write identical values); then, per
-                // 16-channel block, lane (p, channel) contracts the staged activations with wn over the 16 samples
-                // and writes its channel's 16 hidden units (64 B; a point's block is 1 KB contiguous).
-                float *wn = s_wn[kEpi == 1 ? q : 0];
+                // ---- weight-net epilogue: this warp's 32 rows are two points x 16 samples.  Lane (p, s) holds its row's
+                // neighbour offset; per 16-channel block the raw accumulators are staged in shared memory and each point's
+                // 16 x 16 (channel x hidden unit) result is contracted over the 16 samples and written 64 B per channel.
+                float gx, gy, gz;  // my row's neighbour offset (lane = (point, sample))
                 {
                     const long long rowc = row < M ? row : 0;
                     const long long cloud = dn_div(rowc, prm.g_rows_per_cloud);
                     const float *ctr = prm.wn_xyz + (rowc >> 4) * 3;
                     const float *nbp = prm.wn_xyz + (cloud * prm.g_n + __ldg(prm.gidx + rowc)) * 3;
-                    const float gx = __fsub_rn(__ldg(nbp), __ldg(ctr)), gy = __fsub_rn(__ldg(nbp + 1), __ldg(ctr + 1)),
-                                gz = __fsub_rn(__ldg(nbp + 2), __ldg(ctr + 2));
-#pragma unroll
-                    for (int t4 = 0; t4 < 16; t4 += 4) {
-                        float o[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int t = t4 + u;
-                            float w = __fmaf_rn(gz, s_wnw[32 + t], __fmaf_rn(gy, s_wnw[16 + t], __fmul_rn(gx, s_wnw[t])));
-                            w = __fmul_rn(__fadd_rn(w, s_wnw[48 + t]), prm.wn_scale);
-                            o[u] = fmaxf(w, 0.f);
-                        }
-                        *reinterpret_cast<float4 *>(wn + lane * 16 + t4) = make_float4(o[0], o[1], o[2], o[3]);
-                    }
+                    gx = __fsub_rn(__ldg(nbp), __ldg(ctr));
+                    gy = __fsub_rn(__ldg(nbp + 1), __ldg(ctr + 1));
+                    gz = __fsub_rn(__ldg(nbp + 2), __ldg(ctr + 2));
                 }
-                const int p = lane >> 4, chq = (lane & 15) >> 2, tq = lane & 3;  // 4 channels x 4 hidden units per lane
+                // The 16-sample contraction runs on the WARP-level tensor-core path (mma.sync.m16n8k8 tf32, 3xTF32 like the
+                // main product): per point and 16-channel block, H^T[c][t] = sum_s G^T[c][s] . wn[s][t] is a 16 x 16 x 16
+                // product whose A fragments are read straight from the staged activations (8 conflict-light LDS.32) and
+                // whose B fragments (wn) stay in registers for the whole tile.  The CUDA-core form of this loop re-read
+                // activations and wn from shared memory for every sample — 4.1 k of the kernel's ~10 k L1 wavefronts per
+                // tile, with the L1 data pipe the kernel's limiter (ncu: 83 %) — and issued 2.4x the instructions.
+                const int fg = lane >> 2, ft = lane & 3;  // mma fragment coordinates: group id, thread in group
+                // The mma's K index is a PERMUTATION of the samples (k = ft -> s = 8 ks + 2 ft, k = ft + 4 -> s = 8 ks + 2 ft + 1,
+                // the same for A and B — a sum does not care): with 20-float rows the four rows a fragment load touches
+                // then start 8 banks apart, so both the float4 staging stores and the scalar fragment loads are conflict-free.
+                // B fragments = wn[s][t] = relu(((g_s . Ww[:, t]) + bw[t]) * scale) for my (s, t) pairs, built once per tile
+                // from the owning lanes' offsets (shuffles): no shared-memory copy of wn at all.
+                uint32_t bh[2][2][2][2], bl[2][2][2][2];  // [point][k-step][n-block][b0 | b1]: wn[s = 8 ks + 2 ft (+1)][t = 8 nb + fg]
+                {
+                    float w0[2], w1[2], w2[2], wb[2];
+#pragma unroll
+                    for (int nbk = 0; nbk < 2; ++nbk) {
+                        const int t = nbk * 8 + fg;
+                        w0[nbk] = s_wnw[t]; w1[nbk] = s_wnw[16 + t]; w2[nbk] = s_wnw[32 + t]; wb[nbk] = s_wnw[48 + t];
+                    }
+#pragma unroll
+                    for (int pp = 0; pp < 2; ++pp)
+#pragma unroll
+                        for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+                            for (int u = 0; u < 2; ++u) {
+                                const int src = pp * 16 + ks * 8 + 2 * ft + u;
+                                const float sx = __shfl_sync(kFull, gx, src), sy = __shfl_sync(kFull, gy, src), sz = __shfl_sync(kFull, gz, src);
+#pragma unroll
+                                for (int nbk = 0; nbk < 2; ++nbk) {
+                                    float w = __fmaf_rn(sz, w2[nbk], __fmaf_rn(sy, w1[nbk], __fmul_rn(sx, w0[nbk])));
+                                    w = fmaxf(__fmul_rn(__fadd_rn(w, wb[nbk]), prm.wn_scale), 0.f);
+                                    const float wh = tf32_round_finite(w);
+                                    bh[pp][ks][nbk][u] = __float_as_uint(wh);
+                                    bl[pp][ks][nbk][u] = __float_as_uint(__fsub_rn(w, wh));
+                                }
+                            }
+                }
                 for (int c0 = half * 16; c0 < npad; c0 += 32) {
                     uint32_t v[32];
                     tmem_ld16(trow + c0, v);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
-                        const float4 bv = *reinterpret_cast<const float4 *>(sb + c0 + j);
-                        float4 o = make_float4(__fadd_rn(__uint_as_float(v[j]), bv.x), __fadd_rn(__uint_as_float(v[j + 1]), bv.y),
-                                               __fadd_rn(__uint_as_float(v[j + 2]), bv.z), __fadd_rn(__uint_as_float(v[j + 3]), bv.w));
-                        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                        *reinterpret_cast<float4 *>(stg + lane * kDnEpiStride + j) = o;
-                    }
+                    for (int j = 0; j < 16; j += 4)  // raw accumulators; bias + activation are applied to the fragments (2 bias loads per block)
+                        *reinterpret_cast<uint4 *>(stg + lane * kDnEpiStride + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    const float bias0 = sb[c0 + fg], bias1 = sb[c0 + fg + 8];
                     __syncwarp();
-                    // 4 channels x 4 hidden units per lane on packed FFMA2: acc2[i][h] = (t = 2h, 2h+1) of channel i
-                    unsigned long long acc2[4][2];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) { acc2[i][0] = 0ull; acc2[i][1] = 0ull; }
+                    for (int pp = 0; pp < 2; ++pp) {
+                        float acc[2][4];
 #pragma unroll
-                    for (int sI = 0; sI < 16; ++sI) {
-                        const float4 g = *reinterpret_cast<const float4 *>(stg + (p * 16 + sI) * kDnEpiStride + 4 * chq);
-                        const ulonglong2 w = *reinterpret_cast<const ulonglong2 *>(wn + (p * 16 + sI) * 16 + 4 * tq);
-                        const float gv[4] = {g.x, g.y, g.z, g.w};
+                        for (int nbk = 0; nbk < 2; ++nbk) { acc[nbk][0] = 0.f; acc[nbk][1] = 0.f; acc[nbk][2] = 0.f; acc[nbk][3] = 0.f; }
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            unsigned long long g2;
-                            asm("mov.b64 %0, {%1, %1};" : "=l"(g2) : "f"(gv[i]));
-                            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[i][0]) : "l"(g2), "l"(w.x));
-                            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[i][1]) : "l"(g2), "l"(w.y));
+                        for (int ks = 0; ks < 2; ++ks) {
+                            // A = G^T (16 channels x 8 samples): a0 (c = fg, s = 2 ft), a1 (fg + 8, 2 ft), a2 (fg, 2 ft + 1), a3 (fg + 8, 2 ft + 1)
+                            const float *gp = stg + (pp * 16 + ks * 8 + 2 * ft) * kDnEpiStride + fg;
+                            float a[4] = {__fadd_rn(gp[0], bias0), __fadd_rn(gp[8], bias1), __fadd_rn(gp[kDnEpiStride], bias0),
+                                          __fadd_rn(gp[kDnEpiStride + 8], bias1)};
+                            uint32_t ah[4], al[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                if (relu) a[i] = fmaxf(a[i], 0.f);
+                                const float hh = tf32_round_finite(a[i]);
+                                ah[i] = __float_as_uint(hh);
+                                al[i] = __float_as_uint(__fsub_rn(a[i], hh));
+                            }
+#pragma unroll
+                            for (int nbk = 0; nbk < 2; ++nbk) {
+                                mma_sync_tf32(acc[nbk], al, bh[pp][ks][nbk]);
+                                mma_sync_tf32(acc[nbk], ah, bl[pp][ks][nbk]);
+                                mma_sync_tf32(acc[nbk], ah, bh[pp][ks][nbk]);
+                            }
                         }
-                    }
-                    float acc[4][4];
+                        // C = H^T (16 channels x 8 hidden units per n-block): c0,c1 (c = fg, t = 2 ft, 2 ft + 1), c2,c3 (c = fg + 8)
+                        const long long pt = (row0 >> 4) + pp;
+                        if (row0 + pp * 16 < M) {
+                            float *o = prm.Y + pt * prm.ldy + (long long)(c0 + fg) * 16 + 2 * ft;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[i][0]), "=f"(acc[i][1]) : "l"(acc2[i][0]));
-                        asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[i][2]), "=f"(acc[i][3]) : "l"(acc2[i][1]));
-                    }
-                    const long long pt = (row0 >> 4) + p;
-                    const int ch = c0 + 4 * chq;
-                    if (row0 + p * 16 < M) {
-                        float *o = prm.Y + pt * prm.ldy + (long long)ch * 16 + 4 * tq;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            if (ch + i < N) *reinterpret_cast<float4 *>(o + i * 16) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+                            for (int nbk = 0; nbk < 2; ++nbk) {
+                                if (c0 + fg < N) *reinterpret_cast<float2 *>(o + nbk * 8) = make_float2(acc[nbk][0], acc[nbk][1]);
+                                if (c0 + fg + 8 < N) *reinterpret_cast<float2 *>(o + 8 * 16 + nbk * 8) = make_float2(acc[nbk][2], acc[nbk][3]);
+                            }
+                        }
                     }
                     __syncwarp();
                 }
