@@ -173,7 +173,7 @@ constexpr int kDnEpiStride = 20;  // floats per staged epilogue row (16 + 4: 16-
 // stages hold only X chunks; otherwise every stage carries its X chunk and the matching weight chunk.  Weights
 // always arrive by TMA bulk copies (one elected thread, mbarrier transaction bytes): the pre-packed planes are
 // contiguous, so a chunk is ONE copy and no thread touches the bytes.
-template <bool kResident, bool kGather, int kEpi>
+template <bool kResident, bool kGather, int kEpi, bool kLean = false>
 __global__ void __launch_bounds__(kDnThreads, 1)
 dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
     const long long M = prm.M;
@@ -205,7 +205,8 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
 
     if (tid == 0) {
         for (int s = 0; s < kDnMaxStages; ++s) {
-            mbar_init(&s_full[s], kDnProducerWarps + (kResident ? 0 : 1));  // producer warps (+ the TMA issuer's expect_tx)
+            // arrivals per stage: the producer warps that fill it (one 4-warp group in the lean loop, all 8 otherwise) + the TMA issuer's expect_tx
+            mbar_init(&s_full[s], (kLean ? kDnProducerWarps / 2 : kDnProducerWarps) + (kResident ? 0 : 1));
             mbar_init(&s_empty[s], 1);                                      // tcgen05.commit
         }
         for (int a = 0; a < 2; ++a) {
@@ -231,8 +232,118 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
     tc_fence_after_sync();
     const uint32_t tmem_base = s_tmem;
 
-    if (warp < kDnProducerWarps) {
-        // ================= producers =================
+    if (warp < kDnProducerWarps && kLean) {
+        // ================= producers, streamed operand, lean loop =================
+        // (kLean: no gather front-end, no softmax transform, 16-byte aligned rows, K % 4 == 0 — every plain layer of the step.)
+        // Two groups of four warps take ALTERNATE K-chunks: thread (r, g) owns row r = tid & 127 (= TMEM lane r) and converts
+        // the whole 32-column chunk of its row for chunks g, g + 2, ... of the CTA's flat (tile, chunk) sequence, so the
+        // per-chunk fixed costs (empty-barrier round trip, tcgen05 fences, cursor arithmetic, the arrive) are paid once per
+        // 32 columns and a group has two chunk-times per iteration.  The loop is kept SMALL on purpose: the general
+        // producer below carries scalar-load fallbacks, bounds checks, the gather / softmax transforms and probes, a
+        // body of ~1500 instructions that the four warps of a scheduler stream through the instruction caches once per
+        // chunk — its trivial cursor arithmetic alone took ~450 cycles per chunk in the clock64 trace.
+        // Register ring of ONE own chunk with immediate refill: as soon as a 16-column half has been read out of its
+        // registers the same half of the NEXT own chunk is requested, so every load has a full group period to land;
+        // prefetch.global.L2 runs kPf chunks ahead of that for the HBM latency.
+        // Nothing of this loop may live in local memory: a spilled cursor variable costs an L1 round trip queued BEHIND the
+        // eight 16-byte global loads of the refill (ncu: 20 % of all warp samples sat on LDL consumers), hence the
+        // minimal state, the leader-only weight cursor and the absence of probes here.
+        const int r = tid & 127, g = tid >> 7;
+        const bool leader = !kResident && r == 0;
+        const uint32_t tm_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 256u;
+        const int nb = prm.n_blocks;
+        const int G = (int)gridDim.x;
+        const int my_tiles = (int)blockIdx.x < n_tiles ? (n_tiles - 1 - (int)blockIdx.x) / G + 1 : 0;
+        const int total = my_tiles * nchunks;
+        int left = total > g ? (total - g + 1) / 2 : 0;  // own chunks still to convert
+        constexpr int kPf = 8;
+        auto prefetch_l2 = [&](const float *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); };
+        auto row_of = [&](int t) -> long long { return (long long)(nb == 1 ? t : t / nb) * 128 + r; };
+        auto load4 = [&](float4 &a, const float *p, bool ok) {  // K % 4 == 0: a float4 is inside the row or wholly past it
+            a = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok) asm volatile("ld.global.nc.L2::256B.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(p));
+        };
+        // cursor of the chunk whose values sit in xb: tile, chunk c, row pointer xr (nullptr: row past M -> zeros)
+        int tile = blockIdx.x, c = g;
+        while (c >= nchunks) { c -= nchunks; tile += G; }
+        const float *xr = nullptr;
+        if (left > 0 && tile < n_tiles && row_of(tile) < M) xr = X + row_of(tile) * prm.ldx;
+        float4 xb[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) load4(xb[q], xr + c * kDnKC + q * 4, xr != nullptr && c * kDnKC + q * 4 < K);
+        if (xr) {  // the L2 lines my later chunks of this row will ask for, and the head of my row in the CTA's next tile
+            for (int cc = c + 2; cc < nchunks && cc < c + 2 + kPf; cc += 2) prefetch_l2(xr + cc * kDnKC);
+            if (tile + G < n_tiles && row_of(tile + G) < M)
+                for (int cc = g; cc < nchunks && cc < kPf; cc += 2) prefetch_l2(X + row_of(tile + G) * prm.ldx + cc * kDnKC);
+        }
+        uint32_t s = g;       // stage of flat chunk g (n_stages >= 3 > g)
+        uint32_t ph = 1;      // parity to wait for on the stage's empty barrier (first pass: passes immediately)
+        const uint8_t *wsrc = packed;  // leader only: packed weight chunk of (tile, c)
+        bool wnew = true;
+        for (; left > 0; --left) {
+            if (leader) {
+                if (wnew) {
+                    const int mt = nb == 1 ? tile : tile / nb;
+                    wsrc = packed + (long long)(tile - mt * nb) * prm.packed_block_stride;
+                    if (prm.rows_per_batch > 0) wsrc += dn_div((long long)mt * 128, prm.rows_per_batch) * prm.packed_batch_stride;
+                }
+            }
+            const uint32_t c_cur = (uint32_t)c;
+            // the next own chunk (its loads are issued while this one is converted)
+            c += 2;
+            wnew = false;
+            if (c >= nchunks) {  // rare path: my next chunk lies in a later tile of this CTA
+                do { c -= nchunks; tile += G; } while (c >= nchunks);
+                xr = nullptr;
+                if (left > 1 && tile < n_tiles && row_of(tile) < M) {
+                    xr = X + row_of(tile) * prm.ldx;
+                    if (tile + G < n_tiles && row_of(tile + G) < M)  // head of my row in the tile after that one
+                        for (int cc = g; cc < nchunks && cc < kPf; cc += 2) prefetch_l2(X + row_of(tile + G) * prm.ldx + cc * kDnKC);
+                }
+                wnew = true;
+            }
+            const float *np = (left > 1 && xr) ? xr + c * kDnKC : nullptr;
+            const int krem = K - c * kDnKC;  // columns of the next chunk that exist
+            mbar_wait(&s_empty[s], ph);
+            tc_fence_after_sync();
+            if (leader) {  // weight chunk: one TMA bulk copy of the pre-packed [hi | lo] planes
+                mbar_arrive_expect_tx(&s_full[s], 2u * b_plane);
+                bulk_g2s(smem_base + s * stage_bytes, wsrc + (size_t)c_cur * 2u * b_plane, 2u * b_plane, &s_full[s]);
+            }
+            const uint32_t tm = tm_row + s * 64u;
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 v = xb[4 * hf + q];
+                    hi[4 * q] = __float_as_uint(tf32_round_finite(v.x)); hi[4 * q + 1] = __float_as_uint(tf32_round_finite(v.y));
+                    hi[4 * q + 2] = __float_as_uint(tf32_round_finite(v.z)); hi[4 * q + 3] = __float_as_uint(tf32_round_finite(v.w));
+                }
+                tmem_st16(tm + (uint32_t)hf * 16u, hi);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {  // lo is rounded (not left to the tensor core's truncation): halves the error of the lo*w_hi term
+                    const float4 v = xb[4 * hf + q];
+                    lo[4 * q] = __float_as_uint(tf32_round_finite(__fsub_rn(v.x, __uint_as_float(hi[4 * q]))));
+                    lo[4 * q + 1] = __float_as_uint(tf32_round_finite(__fsub_rn(v.y, __uint_as_float(hi[4 * q + 1]))));
+                    lo[4 * q + 2] = __float_as_uint(tf32_round_finite(__fsub_rn(v.z, __uint_as_float(hi[4 * q + 2]))));
+                    lo[4 * q + 3] = __float_as_uint(tf32_round_finite(__fsub_rn(v.w, __uint_as_float(hi[4 * q + 3]))));
+                }
+                tmem_st16(tm + 32u + (uint32_t)hf * 16u, lo);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)  // refill this half: the loads have a whole group period (two chunk-times) to land
+                    load4(xb[4 * hf + q], np + hf * 16 + q * 4, np != nullptr && hf * 16 + q * 4 < krem);
+            }
+            tmem_st_wait();  // my part of the A operand has landed in tensor memory
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_full[s]);
+            if (np != nullptr && c + kPf < nchunks) prefetch_l2(np + kPf * kDnKC);
+            s += 2;
+            if (s >= (uint32_t)n_stages) { s -= (uint32_t)n_stages; ph ^= 1; }
+        }
+    } else if (warp < kDnProducerWarps) {
+        // ================= producers, gather front-end =================
         // Thread (r, h): row r = tid & 127 of the tile (= TMEM lane r: tcgen05.st can only write the issuing warp's
         // lane quarter, warp % 4) and K-columns 16h..16h+15 of the chunk.  The A operand is written STRAIGHT INTO TENSOR
         // MEMORY (TS-form tcgen05.mma): no shared-memory A planes, no generic->async proxy fence, and the tensor core
@@ -808,6 +919,9 @@ extern "C" int dispu_dense_tf32x3_ex(const dispu_dense_args *a, dispu_stream_t s
         return finish_launch();
     };
     if (wnet) return resident ? launch(dense_tf32x3_kernel<true, true, 1>) : launch(dense_tf32x3_kernel<false, true, 1>);
+    const bool lean = !p.gidx && !p.stat_in && !p.dbg && (reinterpret_cast<uintptr_t>(p.X) & 15u) == 0 && ldx % 4 == 0 && K % 4 == 0 &&
+                      !getenv("DISPU_DENSE_GENERIC");
+    if (lean) return resident ? launch(dense_tf32x3_kernel<true, false, 0, true>) : launch(dense_tf32x3_kernel<false, false, 0, true>);
     if (resident) return p.gidx ? launch(dense_tf32x3_kernel<true, true, 0>) : launch(dense_tf32x3_kernel<true, false, 0>);
     return p.gidx ? launch(dense_tf32x3_kernel<false, true, 0>) : launch(dense_tf32x3_kernel<false, false, 0>);
 }
