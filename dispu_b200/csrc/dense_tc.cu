@@ -35,6 +35,7 @@ constexpr int kDnMaxStages = 4;
 constexpr int kDnProducerWarps = 8;
 constexpr int kDnEpiWarps = 8;      // two per TMEM lane quarter, alternating 16-column blocks
 constexpr int kDnThreads = (kDnProducerWarps + kDnEpiWarps + 1) * 32;  // producers | epilogue | MMA issuer
+constexpr int kDnXposeBytes = 32 * 128 + 2 * 128;  // lean gather producer, per warp and buffer: 32 operand rows + 2 centre rows of one K-chunk
 constexpr int kDnSmemBudget = 192 * 1024;  // + <= 29 KB static (epilogue staging, weight-net rows, bias, barriers) <= 227 KB
 
 __host__ __device__ __forceinline__ int dn_npad(int N) { return (N + 15) & ~15; }
@@ -119,6 +120,7 @@ struct DenseParams {
     long long ldy2;
     int y2_block;
     int n_tiles, n_stages;
+    uint32_t xpose_off;  // lean gather producer: byte offset of the per-warp transposition buffers in dynamic shared memory
     long long *dbg_buf;  // development only: clock64 samples of CTA 0 (3 roles x 64 iterations x 8 slots)
     int dbg;  // development only (DISPU_DENSE_DBG): 1 = no A loads, 2 = no weight TMA, 4 = no MMA issue; results are garbage
 };
@@ -232,7 +234,131 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
     tc_fence_after_sync();
     const uint32_t tmem_base = s_tmem;
 
-    if (warp < kDnProducerWarps && kLean) {
+    if (warp < kDnProducerWarps && kLean && kGather) {
+        // ================= producers, gather front-end, lean loop =================
+        // Operand row r of a tile = relu(X[cloud(r), gidx[r], :] + sign * Q[r / g_ns, :]).  Same two-group structure as the
+        // streamed lean loop below, plus COALESCED, REGISTER-FREE gathers: a thread fetching its own row touches one
+        // 128-byte line per lane, 32 L1 wavefronts per load instruction, and the SM's single L1 wavefront queue (~1-2 cycles
+        // per line) then bounds the kernel (conv1: 2.7 k cycles per chunk against 1.4 k of MMAs, unchanged with the epilogue
+        // masked out).  Here the eight lanes of a quarter-warp share a row — copy m of lane (a, j) moves columns 4j..4j+3 of
+        // warp row 8a + m, four lines per instruction, row addresses handed around with one shuffle each — and the bytes go
+        // straight to shared memory with cp.async (zero-filled past the end), one own chunk ahead, into a double-buffered
+        // per-warp tile whose 16-byte chunks are XOR-swizzled by the row so that both the copies and the row-per-thread
+        // reads (thread r = TMEM lane r needs row r) are conflict-free.  The centre rows (at most two per warp:
+        // g_ns % 16 == 0) ride the same way and are read back as shared-memory broadcasts.
+        const int r = tid & 127, g = tid >> 7;
+        const bool leader = !kResident && r == 0;
+        const uint32_t tm_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 256u;
+        uint8_t *xbuf = smem + prm.xpose_off + (size_t)warp * (2 * kDnXposeBytes);
+        const uint32_t xbuf_s = smem_u32(xbuf);
+        const int la = lane >> 3, lj = lane & 7;
+        const int nb = prm.n_blocks;
+        const int G = (int)gridDim.x;
+        const int my_tiles = (int)blockIdx.x < n_tiles ? (n_tiles - 1 - (int)blockIdx.x) / G + 1 : 0;
+        const int total = my_tiles * nchunks;
+        int left = total > g ? (total - g + 1) / 2 : 0;  // own chunks still to convert
+        const int *__restrict__ gidx = prm.gidx;
+        auto cp16 = [&](uint32_t dst, const float *src, bool ok) {  // 16 bytes global -> shared, zeros when !ok
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(ok ? src : X), "r"(ok ? 16 : 0) : "memory");
+        };
+        // gathered table row of my operand row in `t` (-1: past the end -> zeros)
+        auto fetch_ridx = [&](int t) -> int {
+            const long long row = (long long)(nb == 1 ? t : t / nb) * 128 + r;
+            if (t >= n_tiles || row >= M) return -1;
+            return (int)(dn_div(row, prm.g_rows_per_cloud) * prm.g_n) + __ldg(gidx + row);
+        };
+        // centre row my lane copies for tile t (lanes 0-7: the warp's rows 0-15, lanes 8-15: rows 16-31; -1: none)
+        auto fetch_qrow = [&](int t) -> int {
+            const long long row = (long long)(nb == 1 ? t : t / nb) * 128 + (warp & 3) * 32 + (la & 1) * 16;
+            if (!prm.Q || lane >= 16 || t >= n_tiles || row >= M) return -1;
+            return (int)dn_div(row, prm.g_ns);
+        };
+        int tile = blockIdx.x, c = g;
+        while (c >= nchunks) { c -= nchunks; tile += G; }
+        int ridx = left > 0 ? fetch_ridx(tile) : -1;
+        int ridx_nxt = left > 0 ? fetch_ridx(tile + G) : -1;
+        int qrow = left > 0 ? fetch_qrow(tile) : -1;
+        auto issue_copies = [&](int cc, uint32_t buf) {  // chunk cc of the tile `ridx` / `qrow` describe -> buffer `buf`
+            const int k = cc * kDnKC + lj * 4;
+            const uint32_t dst0 = xbuf_s + buf * kDnXposeBytes + (uint32_t)(8 * la) * 128u;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const int src = __shfl_sync(kFull, ridx, (lane & 24) + m);
+                cp16(dst0 + (uint32_t)m * 128u + (uint32_t)((lj ^ m) << 4), X + (long long)src * prm.ldx + k, src >= 0 && k < K);
+            }
+            if (lane < 16)
+                cp16(xbuf_s + buf * kDnXposeBytes + 4096u + (uint32_t)la * 128u + (uint32_t)lj * 16u, prm.Q + (long long)qrow * prm.ldq + k,
+                     qrow >= 0 && k < K);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        uint32_t buf = 0;
+        if (left > 0) issue_copies(c, 0);
+        uint32_t s = g;       // stage of flat chunk g (n_stages >= 2 > g)
+        uint32_t ph = 1;      // parity to wait for on the stage's empty barrier (first pass: passes immediately)
+        const uint8_t *wsrc = packed;  // leader only: packed weight chunk of (tile, c)
+        bool wnew = true;
+        const float sign = prm.sign;
+        for (; left > 0; --left) {
+            if (leader && wnew) {
+                const int mt = nb == 1 ? tile : tile / nb;
+                wsrc = packed + (long long)(tile - mt * nb) * prm.packed_block_stride;
+                if (prm.rows_per_batch > 0) wsrc += dn_div((long long)mt * 128, prm.rows_per_batch) * prm.packed_batch_stride;
+            }
+            const uint32_t c_cur = (uint32_t)c;
+            asm volatile("cp.async.wait_group 0;" ::: "memory");  // my copies of this chunk have landed ...
+            __syncwarp();                                          // ... and so have everyone else's; the other buffer is free
+            // point the cursor at the next own chunk and request it
+            c += 2;
+            wnew = false;
+            if (c >= nchunks) {  // my next chunk lies in a later tile of this CTA
+                int skipped = 0;
+                do { c -= nchunks; tile += G; ++skipped; } while (c >= nchunks);
+                ridx = (left > 1) ? (skipped == 1 ? ridx_nxt : fetch_ridx(tile)) : -1;
+                ridx_nxt = (left > 1) ? fetch_ridx(tile + G) : -1;
+                qrow = (left > 1) ? fetch_qrow(tile) : -1;
+                wnew = true;
+            }
+            if (left > 1) issue_copies(c, buf ^ 1u);
+            mbar_wait(&s_empty[s], ph);
+            tc_fence_after_sync();
+            if (leader) {  // weight chunk: one TMA bulk copy of the pre-packed [hi | lo] planes
+                mbar_arrive_expect_tx(&s_full[s], 2u * b_plane);
+                bulk_g2s(smem_base + s * stage_bytes, wsrc + (size_t)c_cur * 2u * b_plane, 2u * b_plane, &s_full[s]);
+            }
+            const uint32_t tm = tm_row + s * 64u;
+            const uint8_t *myx = xbuf + buf * kDnXposeBytes + lane * 128;
+            const uint8_t *myq = xbuf + buf * kDnXposeBytes + 4096 + (lane >> 4) * 128;
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                float vv[16];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {  // relu(x + sign*q); q is zero when there is no Q (x + sign*0 == x exactly)
+                    const int jj = hf * 4 + q;
+                    const float4 v = *reinterpret_cast<const float4 *>(myx + ((jj ^ (lane & 7)) << 4));
+                    const float4 qq = *reinterpret_cast<const float4 *>(myq + (jj << 4));
+                    vv[4 * q] = fmaxf(__fmaf_rn(sign, qq.x, v.x), 0.f);
+                    vv[4 * q + 1] = fmaxf(__fmaf_rn(sign, qq.y, v.y), 0.f);
+                    vv[4 * q + 2] = fmaxf(__fmaf_rn(sign, qq.z, v.z), 0.f);
+                    vv[4 * q + 3] = fmaxf(__fmaf_rn(sign, qq.w, v.w), 0.f);
+                }
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) hi[u] = __float_as_uint(tf32_round_finite(vv[u]));
+                tmem_st16(tm + (uint32_t)hf * 16u, hi);
+#pragma unroll
+                for (int u = 0; u < 16; ++u)  // lo is rounded (not left to the tensor core's truncation): halves the error of the lo*w_hi term
+                    lo[u] = __float_as_uint(tf32_round_finite(__fsub_rn(vv[u], __uint_as_float(hi[u]))));
+                tmem_st16(tm + 32u + (uint32_t)hf * 16u, lo);
+            }
+            tmem_st_wait();  // my part of the A operand has landed in tensor memory
+            tc_fence_before_sync();
+            __syncwarp();    // (also: every lane has read its row before the buffer is refilled two iterations on)
+            if (lane == 0) mbar_arrive(&s_full[s]);
+            buf ^= 1u;
+            s += 2;
+            if (s >= (uint32_t)n_stages) { s -= (uint32_t)n_stages; ph ^= 1; }
+        }
+    } else if (warp < kDnProducerWarps && kLean) {
         // ================= producers, streamed operand, lean loop =================
         // (kLean: no gather front-end, no softmax transform, 16-byte aligned rows, K % 4 == 0 — every plain layer of the step.)
         // Two groups of four warps take ALTERNATE K-chunks: thread (r, g) owns row r = tid & 127 (= TMEM lane r) and converts
@@ -877,6 +1003,23 @@ extern "C" int dispu_dense_tf32x3_ex(const dispu_dense_args *a, dispu_stream_t s
         if (stages > kDnMaxStages) stages = kDnMaxStages;
         smem = stages * b_chunk;
     }
+    static const bool no_lean = getenv("DISPU_DENSE_GENERIC") != nullptr;
+    // lean gather producer (coalesced gathers transposed through per-warp shared-memory buffers): aligned rows, K % 4 == 0,
+    // centre rows shared by multiples of 16 operand rows
+    const bool lean_gather = a->gather_idx && !no_lean && !a->stat_in && (reinterpret_cast<uintptr_t>(a->X) & 15u) == 0 && ldx % 4 == 0 &&
+                             K % 4 == 0 && (a->gather_ns > 0 ? a->gather_ns : 1) % 16 == 0 &&
+                             (!a->Q || ((reinterpret_cast<uintptr_t>(a->Q) & 15u) == 0 && (a->ldq > 0 ? a->ldq : K) % 4 == 0));
+    if (lean_gather) {
+        const size_t xp = (size_t)kDnProducerWarps * 2 * kDnXposeBytes;
+        if (!resident) {
+            stages = (int)(((size_t)kDnSmemBudget - xp) / b_chunk);
+            if (stages > kDnMaxStages) stages = kDnMaxStages;
+            smem = stages * b_chunk;
+        }
+    }
+    const bool lean_gather_ok = lean_gather && (resident ? w_all + (size_t)kDnProducerWarps * 2 * kDnXposeBytes <= (size_t)kDnSmemBudget + 8 * 1024 : stages >= 2);
+    const uint32_t xpose_off = (uint32_t)((smem + 15) & ~(size_t)15);
+    if (lean_gather_ok) smem = xpose_off + (size_t)kDnProducerWarps * 2 * kDnXposeBytes;
     if (smem < 1024) smem = 1024;
     int dev = 0, sms = kNumSMs;
     cudaGetDevice(&dev);
@@ -904,6 +1047,7 @@ extern "C" int dispu_dense_tf32x3_ex(const dispu_dense_args *a, dispu_stream_t s
     p.ldy2 = a->ldy2 > 0 ? a->ldy2 : (long long)(n_blocks - a->y2_block) * N;
     if (wnet) p.ldy = a->ldy > 0 ? a->ldy : (long long)N * 16;
     p.n_tiles = n_tiles; p.n_stages = stages;
+    p.xpose_off = xpose_off;
     {
         static const int dbg = [] { const char *e = getenv("DISPU_DENSE_DBG"); return e ? atoi(e) : 0; }();
         p.dbg = dbg;
@@ -918,9 +1062,12 @@ extern "C" int dispu_dense_tf32x3_ex(const dispu_dense_args *a, dispu_stream_t s
         kern<<<grid, kDnThreads, smem, (cudaStream_t)stream>>>(p);
         return finish_launch();
     };
+    if (lean_gather_ok && !p.dbg) {
+        if (wnet) return resident ? launch(dense_tf32x3_kernel<true, true, 1, true>) : launch(dense_tf32x3_kernel<false, true, 1, true>);
+        return resident ? launch(dense_tf32x3_kernel<true, true, 0, true>) : launch(dense_tf32x3_kernel<false, true, 0, true>);
+    }
     if (wnet) return resident ? launch(dense_tf32x3_kernel<true, true, 1>) : launch(dense_tf32x3_kernel<false, true, 1>);
-    const bool lean = !p.gidx && !p.stat_in && !p.dbg && (reinterpret_cast<uintptr_t>(p.X) & 15u) == 0 && ldx % 4 == 0 && K % 4 == 0 &&
-                      !getenv("DISPU_DENSE_GENERIC");
+    const bool lean = !p.gidx && !p.stat_in && !p.dbg && (reinterpret_cast<uintptr_t>(p.X) & 15u) == 0 && ldx % 4 == 0 && K % 4 == 0 && !no_lean;
     if (lean) return resident ? launch(dense_tf32x3_kernel<true, false, 0, true>) : launch(dense_tf32x3_kernel<false, false, 0, true>);
     if (resident) return p.gidx ? launch(dense_tf32x3_kernel<true, true, 0>) : launch(dense_tf32x3_kernel<true, false, 0>);
     return p.gidx ? launch(dense_tf32x3_kernel<false, true, 0>) : launch(dense_tf32x3_kernel<false, false, 0>);
