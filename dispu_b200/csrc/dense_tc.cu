@@ -914,6 +914,7 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
     if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
 }
 
+
 }  // namespace dispu
 
 using namespace dispu;
