@@ -169,6 +169,24 @@ __device__ __forceinline__ void mma_sync_tf32(float (&d)[4], const uint32_t (&a)
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
+// D (16 x 8, fp32) += A (16 x 16, f16, row) . B (16 x 8, f16, col): the whole 16-sample contraction of the weight-net
+// epilogue in ONE warp-level instruction per operand pair (the tf32 form above needs two k = 8 steps)
+__device__ __forceinline__ void mma_sync_f16(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// x0, x1 -> packed f16 pair hi = rn(x) and the SCALED remainder lo = rn((x - hi) * 2^11): x = hi + lo * 2^-11 to ~2^-22 |x|
+// (f16 has TF32's 11-bit significand; the scaling keeps the remainder out of the f16 subnormal range, and the products
+// that carry it are accumulated separately and weighted by 2^-11 at the end).  |x| must stay below 65504.
+__device__ __forceinline__ void f16_split2(float x0, float x1, uint32_t &hi, uint32_t &lo) {
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+    float h0, h1;
+    asm("{\n\t.reg .f16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(h0), "=f"(h1) : "r"(hi));
+    const float r0 = __fmul_rn(__fsub_rn(x0, h0), 2048.f), r1 = __fmul_rn(__fsub_rn(x1, h1), 2048.f);
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
+}
+
 constexpr int kDnEpiStride = 20;  // floats per staged epilogue row (16 + 4: 16-byte aligned, conflict-free stores)
 
 // kResident: the whole packed weight stays in shared memory for the CTA's lifetime (small K*N) and the pipeline
@@ -745,12 +763,15 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
                 // activations and wn from shared memory for every sample — 4.1 k of the kernel's ~10 k L1 wavefronts per
                 // tile, with the L1 data pipe the kernel's limiter (ncu: 83 %) — and issued 2.4x the instructions.
                 const int fg = lane >> 2, ft = lane & 3;  // mma fragment coordinates: group id, thread in group
-                // The mma's K index is a PERMUTATION of the samples (k = ft -> s = 8 ks + 2 ft, k = ft + 4 -> s = 8 ks + 2 ft + 1,
-                // the same for A and B — a sum does not care): with 20-float rows the four rows a fragment load touches
-                // then start 8 banks apart, so both the float4 staging stores and the scalar fragment loads are conflict-free.
+                // One m16n8k16 f16 instruction spans all 16 samples (k = s).  3-term split like the main product, on f16 pairs
+                // (hi, scaled lo): hi*hi goes to the main accumulator, lo*hi + hi*lo to a correction accumulator weighted by
+                // 2^-11 at the end — half the warp-level MMAs of the k = 8 tf32 form, whose issue rate (~26 cycles per
+                // instruction and scheduler, ncu: stall_math) bounded this epilogue, and the B fragments fit 16 registers.
+                // With 20-float rows the rows a fragment load touches (s = 2 ft [+1] [+8]) start 8 banks apart: the float4
+                // staging stores and the scalar fragment loads are conflict-free.
                 // B fragments = wn[s][t] = relu(((g_s . Ww[:, t]) + bw[t]) * scale) for my (s, t) pairs, built once per tile
                 // from the owning lanes' offsets (shuffles): no shared-memory copy of wn at all.
-                uint32_t bh[2][2][2][2], bl[2][2][2][2];  // [point][k-step][n-block][b0 | b1]: wn[s = 8 ks + 2 ft (+1)][t = 8 nb + fg]
+                uint32_t bh[2][2][2], bl[2][2][2];  // [point][n-block][b0 | b1]: wn[s = 2 ft (+1) | 2 ft + 8 (+1)][t = 8 nb + fg]
                 {
                     float w0[2], w1[2], w2[2], wb[2];
 #pragma unroll
@@ -761,20 +782,21 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
 #pragma unroll
                     for (int pp = 0; pp < 2; ++pp)
 #pragma unroll
-                        for (int ks = 0; ks < 2; ++ks)
+                        for (int kh = 0; kh < 2; ++kh) {
+                            float wv[2][2];  // [u][nbk]
 #pragma unroll
                             for (int u = 0; u < 2; ++u) {
-                                const int src = pp * 16 + ks * 8 + 2 * ft + u;
+                                const int src = pp * 16 + kh * 8 + 2 * ft + u;
                                 const float sx = __shfl_sync(kFull, gx, src), sy = __shfl_sync(kFull, gy, src), sz = __shfl_sync(kFull, gz, src);
 #pragma unroll
                                 for (int nbk = 0; nbk < 2; ++nbk) {
-                                    float w = __fmaf_rn(sz, w2[nbk], __fmaf_rn(sy, w1[nbk], __fmul_rn(sx, w0[nbk])));
-                                    w = fmaxf(__fmul_rn(__fadd_rn(w, wb[nbk]), prm.wn_scale), 0.f);
-                                    const float wh = tf32_round_finite(w);
-                                    bh[pp][ks][nbk][u] = __float_as_uint(wh);
-                                    bl[pp][ks][nbk][u] = __float_as_uint(__fsub_rn(w, wh));
+                                    const float w = __fmaf_rn(sz, w2[nbk], __fmaf_rn(sy, w1[nbk], __fmul_rn(sx, w0[nbk])));
+                                    wv[u][nbk] = fmaxf(__fmul_rn(__fadd_rn(w, wb[nbk]), prm.wn_scale), 0.f);
                                 }
                             }
+#pragma unroll
+                            for (int nbk = 0; nbk < 2; ++nbk) f16_split2(wv[0][nbk], wv[1][nbk], bh[pp][nbk][kh], bl[pp][nbk][kh]);
+                        }
                 }
                 for (int c0 = half * 16; c0 < npad; c0 += 32) {
                     uint32_t v[32];
@@ -787,38 +809,39 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
                     __syncwarp();
 #pragma unroll
                     for (int pp = 0; pp < 2; ++pp) {
-                        float acc[2][4];
+                        // A = G^T (16 channels x 16 samples): a0 (c = fg; s = 2 ft, 2 ft + 1), a1 (fg + 8; same), a2 (fg; s + 8), a3 (fg + 8; s + 8)
+                        uint32_t ah[4], al[4];
 #pragma unroll
-                        for (int nbk = 0; nbk < 2; ++nbk) { acc[nbk][0] = 0.f; acc[nbk][1] = 0.f; acc[nbk][2] = 0.f; acc[nbk][3] = 0.f; }
+                        for (int kh = 0; kh < 2; ++kh) {
+                            const float *gp = stg + (pp * 16 + kh * 8 + 2 * ft) * kDnEpiStride + fg;
+                            float x00 = __fadd_rn(gp[0], bias0), x01 = __fadd_rn(gp[kDnEpiStride], bias0);
+                            float x10 = __fadd_rn(gp[8], bias1), x11 = __fadd_rn(gp[kDnEpiStride + 8], bias1);
+                            if (relu) { x00 = fmaxf(x00, 0.f); x01 = fmaxf(x01, 0.f); x10 = fmaxf(x10, 0.f); x11 = fmaxf(x11, 0.f); }
+                            f16_split2(x00, x01, ah[2 * kh], al[2 * kh]);
+                            f16_split2(x10, x11, ah[2 * kh + 1], al[2 * kh + 1]);
+                        }
+                        float acc[2][4], cor[2][4];
 #pragma unroll
-                        for (int ks = 0; ks < 2; ++ks) {
-                            // A = G^T (16 channels x 8 samples): a0 (c = fg, s = 2 ft), a1 (fg + 8, 2 ft), a2 (fg, 2 ft + 1), a3 (fg + 8, 2 ft + 1)
-                            const float *gp = stg + (pp * 16 + ks * 8 + 2 * ft) * kDnEpiStride + fg;
-                            float a[4] = {__fadd_rn(gp[0], bias0), __fadd_rn(gp[8], bias1), __fadd_rn(gp[kDnEpiStride], bias0),
-                                          __fadd_rn(gp[kDnEpiStride + 8], bias1)};
-                            uint32_t ah[4], al[4];
+                        for (int nbk = 0; nbk < 2; ++nbk) {
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                if (relu) a[i] = fmaxf(a[i], 0.f);
-                                const float hh = tf32_round_finite(a[i]);
-                                ah[i] = __float_as_uint(hh);
-                                al[i] = __float_as_uint(__fsub_rn(a[i], hh));
-                            }
-#pragma unroll
-                            for (int nbk = 0; nbk < 2; ++nbk) {
-                                mma_sync_tf32(acc[nbk], al, bh[pp][ks][nbk]);
-                                mma_sync_tf32(acc[nbk], ah, bl[pp][ks][nbk]);
-                                mma_sync_tf32(acc[nbk], ah, bh[pp][ks][nbk]);
-                            }
+                            for (int i = 0; i < 4; ++i) { acc[nbk][i] = 0.f; cor[nbk][i] = 0.f; }
+                            mma_sync_f16(acc[nbk], ah, bh[pp][nbk]);
+                            mma_sync_f16(cor[nbk], al, bh[pp][nbk]);
+                            mma_sync_f16(cor[nbk], ah, bl[pp][nbk]);
                         }
                         // C = H^T (16 channels x 8 hidden units per n-block): c0,c1 (c = fg, t = 2 ft, 2 ft + 1), c2,c3 (c = fg + 8)
                         const long long pt = (row0 >> 4) + pp;
                         if (row0 + pp * 16 < M) {
                             float *o = prm.Y + pt * prm.ldy + (long long)(c0 + fg) * 16 + 2 * ft;
+                            constexpr float kInv = 1.f / 2048.f;
 #pragma unroll
                             for (int nbk = 0; nbk < 2; ++nbk) {
-                                if (c0 + fg < N) *reinterpret_cast<float2 *>(o + nbk * 8) = make_float2(acc[nbk][0], acc[nbk][1]);
-                                if (c0 + fg + 8 < N) *reinterpret_cast<float2 *>(o + 8 * 16 + nbk * 8) = make_float2(acc[nbk][2], acc[nbk][3]);
+                                if (c0 + fg < N)
+                                    *reinterpret_cast<float2 *>(o + nbk * 8) =
+                                        make_float2(__fmaf_rn(cor[nbk][0], kInv, acc[nbk][0]), __fmaf_rn(cor[nbk][1], kInv, acc[nbk][1]));
+                                if (c0 + fg + 8 < N)
+                                    *reinterpret_cast<float2 *>(o + 8 * 16 + nbk * 8) =
+                                        make_float2(__fmaf_rn(cor[nbk][2], kInv, acc[nbk][2]), __fmaf_rn(cor[nbk][3], kInv, acc[nbk][3]));
                             }
                         }
                     }
