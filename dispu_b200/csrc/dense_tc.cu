@@ -161,16 +161,8 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uin
                  : "memory");
 }
 
-// D (16 x 8, fp32) += A (16 x 8, tf32, row) . B (8 x 8, tf32, col): the warp-level tensor-core instruction, used by the
-// weight-net epilogue for its small per-point contractions (operands are already in registers / shared memory there)
-__device__ __forceinline__ void mma_sync_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
-
 // D (16 x 8, fp32) += A (16 x 16, f16, row) . B (16 x 8, f16, col): the whole 16-sample contraction of the weight-net
-// epilogue in ONE warp-level instruction per operand pair (the tf32 form above needs two k = 8 steps)
+// epilogue in ONE warp-level instruction per operand pair (a tf32 m16n8k8 form needs two k = 8 steps)
 __device__ __forceinline__ void mma_sync_f16(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
@@ -756,12 +748,11 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
                     gy = __fsub_rn(__ldg(nbp + 1), __ldg(ctr + 1));
                     gz = __fsub_rn(__ldg(nbp + 2), __ldg(ctr + 2));
                 }
-                // The 16-sample contraction runs on the WARP-level tensor-core path (mma.sync.m16n8k8 tf32, 3xTF32 like the
-                // main product): per point and 16-channel block, H^T[c][t] = sum_s G^T[c][s] . wn[s][t] is a 16 x 16 x 16
-                // product whose A fragments are read straight from the staged activations (8 conflict-light LDS.32) and
-                // whose B fragments (wn) stay in registers for the whole tile.  The CUDA-core form of this loop re-read
-                // activations and wn from shared memory for every sample — 4.1 k of the kernel's ~10 k L1 wavefronts per
-                // tile, with the L1 data pipe the kernel's limiter (ncu: 83 %) — and issued 2.4x the instructions.
+                // The 16-sample contraction runs on the WARP-level tensor-core path (mma.sync): per point and 16-channel block,
+                // H^T[c][t] = sum_s G^T[c][s] . wn[s][t] is a 16 x 16 x 16 product whose A fragments are read straight from the
+                // staged activations (8 conflict-free LDS.32) and whose B fragments (wn) stay in registers for the whole tile.
+                // A CUDA-core form (4 channels x 4 hidden units per lane on FFMA2, wn rows in shared memory) measures 174 us
+                // against 162 us for this one at c2.
                 const int fg = lane >> 2, ft = lane & 3;  // mma fragment coordinates: group id, thread in group
                 // One m16n8k16 f16 instruction spans all 16 samples (k = s).  3-term split like the main product, on f16 pairs
                 // (hi, scaled lo): hi*hi goes to the main accumulator, lo*hi + hi*lo to a correction accumulator weighted by
