@@ -31,6 +31,7 @@ constexpr int kEcProjW = 4 * kEcG;  // pn | pc | t1 | t2
 struct EcProjArgs {
     const float *w0, *b0, *w1, *b1, *w2, *b2;
     float *proj;  // (b*n, 96); nullptr = no projection
+    int raw_async;  // weights are 16-byte aligned: their raw rows are fetched with cp.async at kernel start (off the critical path)
     long long *dbg;  // development only: clock64 samples of CTA (0,0), thread 0
 };
 
@@ -77,8 +78,20 @@ feature_knn_kernel(int n, int m, int c, int k, int skip, const float *__restrict
     int *s_si = reinterpret_cast<int *>(s_sd + kFkWarps * kFkCap);                // [warps][kFkCap] survivor indices
     float *s_od = reinterpret_cast<float *>(s_si + kFkWarps * kFkCap);            // [warps][32] ranked output
     int *s_oi = reinterpret_cast<int *>(s_od + kFkWarps * 32);
+    float *s_raw = reinterpret_cast<float *>(s_oi + kFkWarps * 32);               // projection tail: raw W0 | W1[g:] | W2[2g:] rows (96 c floats)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cloud = blockIdx.y;
+    if (pj.proj != nullptr && pj.raw_async) {
+        // the projection's weight rows travel to shared memory while the neighbour search runs: 16-byte cp.async, no registers
+        const int n4 = 24 * c;  // float4s: W0 (2c x 24) | W1 rows g.. (c x 24) | W2 rows 2g.. (c x 24)
+        for (int e = threadIdx.x; e < n4; e += kFkWarps * 32) {
+            const float *src = e < 12 * c ? pj.w0 + 4 * e
+                               : e < 18 * c ? pj.w1 + (size_t)kEcG * kEcG + 4 * (e - 12 * c)
+                                            : pj.w2 + (size_t)2 * kEcG * kEcG + 4 * (e - 18 * c);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(s_raw + 4 * e)), "l"(src) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     const float *pts = points + (size_t)cloud * n * ldp;
     const float *qry = queries + (size_t)cloud * m * ldq;
     const int q0 = (blockIdx.x * kFkWarps + warp) * kFkQueriesPerWarp;
@@ -97,9 +110,21 @@ feature_knn_kernel(int n, int m, int c, int k, int skip, const float *__restrict
     for (int t0 = 0; t0 < n; t0 += kChunk) {
         const int tn = min(kChunk, n - t0);
         __syncthreads();
-        for (int e = threadIdx.x; e < tn * c; e += kFkWarps * 32) {
-            const int p = e / c, l = e - p * c;
-            s_ft[(size_t)l * kStride + p] = __ldg(pts + (size_t)(t0 + p) * ldp + l);
+        if (((c | ldp) & 3) == 0 && (reinterpret_cast<uintptr_t>(pts) & 15u) == 0) {
+            // 16-byte loads, four in flight per thread; the transposing stores see at most 2-way conflicts
+            const int c4 = c >> 2;
+#pragma unroll 4
+            for (int e = threadIdx.x; e < tn * c4; e += kFkWarps * 32) {
+                const int p = e / c4, l4 = e - p * c4;
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(pts + (size_t)(t0 + p) * ldp) + l4);
+                float *dst = s_ft + (size_t)(4 * l4) * kStride + p;
+                dst[0] = v.x; dst[kStride] = v.y; dst[2 * kStride] = v.z; dst[3 * kStride] = v.w;
+            }
+        } else {
+            for (int e = threadIdx.x; e < tn * c; e += kFkWarps * 32) {
+                const int p = e / c, l = e - p * c;
+                s_ft[(size_t)l * kStride + p] = __ldg(pts + (size_t)(t0 + p) * ldp + l);
+            }
         }
         __syncthreads();
         FK_MARK();
@@ -118,17 +143,30 @@ feature_knn_kernel(int n, int m, int c, int k, int skip, const float *__restrict
             // stage the kQ query vectors (rows past m clamp to a valid row; their results are discarded)
             float *sq = s_q + (size_t)warp * kFkQueriesPerWarp * c;
             __syncwarp();
-            for (int e = lane; e < kQ * c; e += 32) {
-                const int w = e / c, l = e - w * c;
-                sq[e] = __ldg(qry + (size_t)min(q0 + u0 + w, m - 1) * ldq + l);
+            // queries that ARE points of the staged chunk (the EdgeConv case) come from the transposed tile, not from global memory
+            const bool self_q = qry == pts && ldq == ldp && t0 == 0 && q0 + kFkQueriesPerWarp <= tn;
+            if (self_q) {
+#pragma unroll
+                for (int w = 0; w < kQ; ++w)
+                    for (int l = lane; l < c; l += 32) sq[w * c + l] = s_ft[(size_t)l * kStride + q0 + u0 + w];
+            } else {
+                for (int e = lane; e < kQ * c; e += 32) {
+                    const int w = e / c, l = e - w * c;
+                    sq[e] = __ldg(qry + (size_t)min(q0 + u0 + w, m - 1) * ldq + l);
+                }
             }
             __syncwarp();
             float rq[kQ];
+            if (self_q) {  // the point norms were accumulated in exactly this order
 #pragma unroll
-            for (int w = 0; w < kQ; ++w) rq[w] = 0.f;
-            for (int l = 0; l < c; ++l) {
+                for (int w = 0; w < kQ; ++w) rq[w] = s_r[q0 + u0 + w];
+            } else {
 #pragma unroll
-                for (int w = 0; w < kQ; ++w) rq[w] = __fmaf_rn(sq[w * c + l], sq[w * c + l], rq[w]);
+                for (int w = 0; w < kQ; ++w) rq[w] = 0.f;
+                for (int l = 0; l < c; ++l) {
+#pragma unroll
+                    for (int w = 0; w < kQ; ++w) rq[w] = __fmaf_rn(sq[w * c + l], sq[w * c + l], rq[w]);
+                }
             }
             FK_MARK();
             float d[kQ][P];
@@ -265,7 +303,27 @@ feature_knn_kernel(int n, int m, int c, int k, int skip, const float *__restrict
     __syncthreads();  // every warp is done with the staged features: reuse the region for [c][96] weights + 96 biases
     float *s_w = fk_smem, *s_b = fk_smem + (size_t)c * kEcProjW;
     const int tid = threadIdx.x;
-    if (tid < 2 * kEcProjW) {
+    if (pj.raw_async) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        const float *r0 = s_raw, *r1 = s_raw + 48 * c, *r2 = s_raw + 72 * c;
+        if (tid < 2 * kEcProjW) {  // thread = (output column o, parity of the input row): no index arithmetic in the loop
+            const int o = tid % kEcProjW, l0 = tid / kEcProjW;
+            const int part = o / kEcG, oc = o - part * kEcG;
+            const float *src = part == 0 ? r0 + c * kEcG : part == 1 ? r0 : part == 2 ? r1 : r2;
+            if (part == 1) {
+#pragma unroll 4
+                for (int l = l0; l < c; l += 2) s_w[l * kEcProjW + o] = __fsub_rn(src[l * kEcG + oc], src[(c + l) * kEcG + oc]);
+            } else {
+#pragma unroll 8
+                for (int l = l0; l < c; l += 2) s_w[l * kEcProjW + o] = src[l * kEcG + oc];
+            }
+            if (l0 == 0) {
+                const float *bsrc = part == 1 ? pj.b0 : part == 2 ? pj.b1 : part == 3 ? pj.b2 : nullptr;
+                s_b[o] = bsrc ? __ldg(bsrc + oc) : 0.f;
+            }
+        }
+    } else if (tid < 2 * kEcProjW) {
         const int o = tid % kEcProjW, l0 = tid / kEcProjW;
         const int part = o / kEcG, oc = o - part * kEcG;
         const float *src = part == 0 ? pj.w0 + (size_t)c * kEcG : part == 1 ? pj.w0 : part == 2 ? pj.w1 + (size_t)kEcG * kEcG
@@ -294,15 +352,31 @@ feature_knn_kernel(int n, int m, int c, int k, int skip, const float *__restrict
 #pragma unroll
             for (int o = 0; o < 12; ++o) acc[o] = s_b[cg * 12 + o];
             const float4 *w4 = reinterpret_cast<const float4 *>(s_w) + cg * 3;
-            for (int l = 0; l < c; ++l) {
-                const float fv = __ldg(f + l);
+            const bool fvec = ((c | ldq) & 3) == 0 && (reinterpret_cast<uintptr_t>(qry) & 15u) == 0;
+#pragma unroll 4
+            for (int l0 = 0; l0 < c; l0 += 4) {  // (unrolled: four 16-byte loads of the row in flight)
+                float fv4[4];
+                if (fvec) {
+                    const float4 t4 = __ldg(reinterpret_cast<const float4 *>(f + l0));
+                    fv4[0] = t4.x; fv4[1] = t4.y; fv4[2] = t4.z; fv4[3] = t4.w;
+                } else {
 #pragma unroll
-                for (int q4 = 0; q4 < 3; ++q4) {
-                    const float4 w = w4[(size_t)l * (kEcProjW / 4) + q4];
-                    acc[4 * q4 + 0] = __fmaf_rn(fv, w.x, acc[4 * q4 + 0]);
-                    acc[4 * q4 + 1] = __fmaf_rn(fv, w.y, acc[4 * q4 + 1]);
-                    acc[4 * q4 + 2] = __fmaf_rn(fv, w.z, acc[4 * q4 + 2]);
-                    acc[4 * q4 + 3] = __fmaf_rn(fv, w.w, acc[4 * q4 + 3]);
+                    for (int i = 0; i < 4; ++i) fv4[i] = l0 + i < c ? __ldg(f + l0 + i) : 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int l = l0 + i;
+                    if (l < c) {
+                        const float fv = fv4[i];
+#pragma unroll
+                        for (int q4 = 0; q4 < 3; ++q4) {
+                            const float4 w = w4[(size_t)l * (kEcProjW / 4) + q4];
+                            acc[4 * q4 + 0] = __fmaf_rn(fv, w.x, acc[4 * q4 + 0]);
+                            acc[4 * q4 + 1] = __fmaf_rn(fv, w.y, acc[4 * q4 + 1]);
+                            acc[4 * q4 + 2] = __fmaf_rn(fv, w.z, acc[4 * q4 + 2]);
+                            acc[4 * q4 + 3] = __fmaf_rn(fv, w.w, acc[4 * q4 + 3]);
+                        }
+                    }
                 }
             }
             float4 *o4 = reinterpret_cast<float4 *>(pj.proj + ((size_t)cloud * m + j) * kEcProjW + cg * 12);
@@ -611,12 +685,17 @@ static int launch_feature_knn(int b, int n, int m, int c, int k, int skip, const
     size_t smem = ((size_t)c * (32 * P + 1) + 32 * P + (size_t)kFkWarps * kFkQueriesPerWarp * c + 2 * kFkWarps * (kFkCap + 32)) * sizeof(float);
     const size_t smem_proj = ((size_t)c * kEcProjW + kEcProjW) * sizeof(float);
     if (pj.proj && smem < smem_proj) smem = smem_proj;
+    EcProjArgs pja = pj;
+    if (pj.proj && pj.raw_async) {  // raw weight rows fetched with cp.async — when they fit next to the staged cloud
+        if (smem + (size_t)96 * c * sizeof(float) <= 220 * 1024) smem += (size_t)96 * c * sizeof(float);
+        else pja.raw_async = 0;
+    }
     if (smem > 220 * 1024) return DISPU_EUNSUPPORTED;
     cudaError_t e = cudaFuncSetAttribute(feature_knn_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     count_launch();
     dim3 grid(ceil_div(m, kFkWarps * kFkQueriesPerWarp), b);
-    feature_knn_kernel<P><<<grid, kFkWarps * 32, smem, stream>>>(n, m, c, k, skip, points, ldp, queries, ldq, dist, idx, pj);
+    feature_knn_kernel<P><<<grid, kFkWarps * 32, smem, stream>>>(n, m, c, k, skip, points, ldp, queries, ldq, dist, idx, pja);
     return finish_launch();
 }
 
@@ -678,7 +757,8 @@ static int dense_conv_impl(int b, int n, int c, int k, int growth, const float *
         static long long *dbg = nullptr;  // development only (DISPU_FK_TRACE)
         if (getenv("DISPU_FK_TRACE") && !dbg) { cudaMalloc(&dbg, 64 * sizeof(long long)); g_fk_dbg = dbg; }
         if (dbg) cudaMemsetAsync(dbg, 0, 64 * sizeof(long long), stream);
-        EcProjArgs pj{w0, b0, w1, b1, w2, b2, proj, dbg};
+        const int raw_async = ec_aligned16(w0) && ec_aligned16(w1) && ec_aligned16(w2);
+        EcProjArgs pj{w0, b0, w1, b1, w2, b2, proj, raw_async, dbg};
         const int rc = feature_knn_dispatch(b, n, n, c, k + 1, 1, feat, ldf, feat, ldf, nullptr, idx_out, stream, pj);
         if (rc != DISPU_OK) return rc;
         idx = idx_out;

@@ -11,7 +11,17 @@ from . import _lib
 from ._t import call, ptr, req, rows, stream_ptr
 
 
-SPLIT_256 = os.environ.get("DISPU_SPLIT_256", "0") == "1"  # measured slower on B200 (A operand re-read, smaller MMAs); kept as a switch
+_SMS = {}
+
+
+def _sm_count(device):
+    key = str(device)
+    if key not in _SMS:
+        _SMS[key] = torch.cuda.get_device_properties(device).multi_processor_count
+    return _SMS[key]
+
+
+SPLIT_256 = os.environ.get("DISPU_SPLIT_256", "0") == "1"  # force the two-block form of every 256-column layer (see PackedLinear)
 
 
 class PackedLinear:
@@ -31,26 +41,39 @@ class PackedLinear:
         if self.N > 256:
             raise ValueError("PackedLinear supports N <= 256")
         self.bias = None if bias is None else req(bias, torch.float32, 1, "bias")
-        # Optional (DISPU_SPLIT_256=1): a 256-column layer as two 128-column blocks, so that two TMEM accumulators fit and
-        # the epilogue of one tile overlaps the MMAs of the next.  Off by default: the doubled A-operand traffic and the
-        # smaller MMAs cost more than the overlap gains on B200 (after_conv 0.30 ms vs 0.19 ms).
-        self.n_blocks = 2 if (self.N == 256 and SPLIT_256) else 1
-        nblk = self.N // self.n_blocks
-        nbytes = int(_lib.lib().dispu_dense_packed_bytes(self.K, nblk))
-        self.block_stride = (nbytes + 15) // 16 * 16
-        self.packed = torch.empty((self.n_blocks * self.block_stride,), dtype=torch.uint8, device=weight.device)
-        # block j = columns [j*nblk, (j+1)*nblk): source element (k, n) at weight[k*N + j*nblk + n]
-        call("dispu_dense_pack_strided", self.K, nblk, ptr(weight), self.N, 1, self.n_blocks, nblk, ptr(self.packed),
-             self.block_stride, stream_ptr())
+        # A 256-column layer can also run as two 128-column blocks (two TMEM accumulators fit, so the epilogue of one tile
+        # overlaps the MMAs of the next, and there are twice as many work units).  That pays when the row tiles alone
+        # cannot fill the SMs (M8192 K480 N256: 33 -> 25 us) and costs otherwise (the A operand is read twice, the MMAs are
+        # smaller: after_conv 174 -> 203 us), so the form is chosen per call; DISPU_SPLIT_256=1 forces it everywhere.
+        self._weight = weight
+        self._packs = {}
+        self._pack(1)
+
+    def _pack(self, n_blocks):
+        pk = self._packs.get(n_blocks)
+        if pk is None:
+            nblk = self.N // n_blocks
+            nbytes = int(_lib.lib().dispu_dense_packed_bytes(self.K, nblk))
+            stride = (nbytes + 15) // 16 * 16
+            packed = torch.empty((n_blocks * stride,), dtype=torch.uint8, device=self._weight.device)
+            # block j = columns [j*nblk, (j+1)*nblk): source element (k, n) at weight[k*N + j*nblk + n]
+            call("dispu_dense_pack_strided", self.K, nblk, ptr(self._weight), self.N, 1, n_blocks, nblk, ptr(packed), stride, stream_ptr())
+            pk = self._packs[n_blocks] = (packed, stride)
+        return pk
 
     def __call__(self, x, relu=False, out=None, gather=None, residuals=(), weightnet=None):
         if x.shape[-1] != self.K:
             raise ValueError(f"PackedLinear expects last dim {self.K}, got {tuple(x.shape)}")
         a = _lib.DenseArgs()
         xp, xm, ldx = rows(x, "x")
-        a.K, a.N, a.X, a.ldx = self.K, self.N // self.n_blocks, xp, ldx
-        a.packed, a.bias, a.relu = ptr(self.packed), ptr(self.bias), 1 if relu else 0
-        a.n_blocks, a.packed_block_stride = self.n_blocks, self.block_stride
+        m_rows = xm if gather is None else gather[0].numel()
+        n_blocks = 1
+        if self.N == 256 and weightnet is None and (SPLIT_256 or 2 * ((m_rows + 127) // 128) <= _sm_count(x.device)):
+            n_blocks = 2
+        packed, block_stride = self._pack(n_blocks)
+        a.K, a.N, a.X, a.ldx = self.K, self.N // n_blocks, xp, ldx
+        a.packed, a.bias, a.relu = ptr(packed), ptr(self.bias), 1 if relu else 0
+        a.n_blocks, a.packed_block_stride = n_blocks, block_stride
         if gather is not None:
             idx, Q, sign = gather
             idx = req(idx, torch.int32, 3, "idx")

@@ -1,7 +1,7 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 o=gpurun_out
-timeout 150 python -m pytest tests -m gpu -q -x -k "dense or generator or attention or chain or linear or weight" > $o/s2c_tests.log 2>&1; echo "tests rc=$?" >> $o/s2c_tests.log
+timeout 150 python -m pytest tests -m gpu -q -x -k "dense or generator or attention or chain or linear or weight or feature or edge or knn" > $o/s2c_tests.log 2>&1; echo "tests rc=$?" >> $o/s2c_tests.log
 tail -4 $o/s2c_tests.log
 timeout 60 python tools/conv1_dbg.py 2>&1 | tail -1
 timeout 120 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > $o/s2c_c2.json 2> $o/s2c_c2.err
