@@ -688,9 +688,13 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
                     const uint32_t ta = tmem_base + 256u + (uint32_t)s * 64u;  // A hi columns of this stage (lo at +32)
                     const uint32_t bh = kResident ? smem_base + w_base + (uint32_t)c * 2 * b_plane : smem_base + (uint32_t)s * stage_bytes;
                     const uint32_t bl = bh + b_plane;
+                    // the last chunk of a K that is not a multiple of 32 holds zero columns: issue only the K-steps that carry data
+                    // (K = 132 / 136, the [xyz | features] layers: 17 instead of 20 K-steps per tile)
+                    const int nks = c == nchunks - 1 ? (K - c * kDnKC + 7) >> 3 : kDnKC / 8;
                     if (!(prm.dbg & 4))
 #pragma unroll
                     for (int ks = 0; ks < kDnKC / 8; ++ks) {
+                        if (ks >= nks) break;
                         const uint64_t dbh = make_smem_desc(bh + ks * 2 * lboB, lboB, 128u);
                         const uint64_t dbl = make_smem_desc(bl + ks * 2 * lboB, lboB, 128u);
                         mma_tf32_ts(d, ta + 32u + ks * 8u, dbh, idesc, (c | ks) != 0);  // a_lo * b_hi
