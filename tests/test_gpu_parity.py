@@ -881,6 +881,53 @@ def test_dense_ex_column_blocks_and_weightnet_epilogue(rng):
     np.testing.assert_allclose(got.cpu().numpy(), sep.cpu().numpy(), rtol=1e-6, atol=1e-6)
 
 
+@pytest.mark.parametrize("ns,K,N,off,m", [(16, 128, 64, 0, 200), (16, 256, 128, 0, 96), (32, 96, 48, 0, 40),   # lean gather loop
+                                         (8, 128, 64, 0, 200), (16, 128, 64, 1, 200), (16, 126, 64, 0, 64)])    # general loop
+def test_dense_gather_lean_and_general_producers(rng, ns, K, N, off, m):
+    """Gather front-end of the dense layer on both producer loops: the lean one (quarter-warp-coalesced cp.async gathers,
+    g_ns % 16 == 0, 16-byte aligned rows, K % 4 == 0) and the general one (anything else: ns = 8, an unaligned column
+    slice, K % 4 != 0), against a float64 reference; Q = None too; rows past the last full tile (b*m*ns % 128 != 0)."""
+    from dispu_b200.dense import PackedLinear
+    b, n = 2, 150
+    wide = rng.standard_normal((b, n, K + 8)).astype(np.float32)
+    Pm = wide[..., off:off + K]
+    Q = rng.standard_normal((b, m, K)).astype(np.float32)
+    idx = rng.integers(0, n, (b, m, ns)).astype(np.int32)
+    w = (rng.standard_normal((K, N)) / np.sqrt(K)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    lin = PackedLinear(T(w), T(bias))
+    tw = T(wide)
+    gath = Pm[np.arange(b)[:, None, None], idx].astype(np.float64)
+    got = lin(tw[..., off:off + K], relu=True, gather=(T(idx), T(Q), -1.0)).cpu().numpy()
+    want = np.maximum(np.maximum(gath - Q[:, :, None, :], 0) @ w + bias, 0)
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=3e-5)
+    got0 = lin(tw[..., off:off + K], relu=False, gather=(T(idx), None, 1.0)).cpu().numpy()
+    np.testing.assert_allclose(got0, np.maximum(gath, 0) @ w + bias, rtol=1e-5, atol=3e-5)
+
+
+@pytest.mark.parametrize("scale", [1e-3, 1.0, 300.0])
+def test_weightnet_epilogue_dynamic_range(rng, scale):
+    """The weight-net epilogue contracts f16 (hi, scaled lo) pairs on warp-level MMAs: fp32-level accuracy must hold for
+    small and large activations alike (the remainder is scaled by 2^11 before it is rounded to f16, so it never enters
+    the f16 subnormal range; |activation| < 65504 is the documented limit)."""
+    from dispu_b200.dense import PackedLinear
+    b, m, ns, K, N = 1, 128, 16, 64, 32
+    xyz = unit_ball(rng, b, m)
+    _, idx = O.knn(ns, xyz, xyz)
+    Pm = (rng.standard_normal((b, m, K)) * scale).astype(np.float32)
+    Q = (rng.standard_normal((b, m, K)) * scale).astype(np.float32)
+    w = (rng.standard_normal((K, N)) / np.sqrt(K)).astype(np.float32)
+    Ww = rng.standard_normal((3, 16)).astype(np.float32)
+    bw = (rng.standard_normal(16) / 4).astype(np.float32)
+    lin = PackedLinear(T(w), None)
+    Gt = lin(T(Pm), relu=True, gather=(T(idx), T(Q), -1.0)).cpu().numpy().astype(np.float64)
+    gx = (xyz[np.arange(b)[:, None, None], idx] - xyz[:, :, None, :]).astype(np.float64)
+    wn = np.maximum(gx @ Ww.astype(np.float64) + bw, 0)                       # (b,m,ns,16)
+    want = np.einsum("bmsc,bmst->bmct", Gt, wn).reshape(b, m, N * 16)
+    got = lin(T(Pm), relu=True, gather=(T(idx), T(Q), -1.0), weightnet=(T(xyz), T(Ww), T(bw), 1.0)).cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=3e-5 * scale)
+
+
 # ---------------------------------------------------------------- §8(f) next rows: uniform loss, patch pipeline, metrics
 @pytest.mark.parametrize("n,m,k", [(2048, 24, 256), (1000, 7, 65), (4096, 48, 256), (300, 5, 300), (5000, 3, 1024)])
 def test_knn_large_k_bit_exact(rng, n, m, k):
