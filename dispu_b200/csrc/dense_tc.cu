@@ -185,7 +185,9 @@ constexpr int kDnEpiStride = 20;  // floats per staged epilogue row (16 + 4: 16-
 // stages hold only X chunks; otherwise every stage carries its X chunk and the matching weight chunk.  Weights
 // always arrive by TMA bulk copies (one elected thread, mbarrier transaction bytes): the pre-packed planes are
 // contiguous, so a chunk is ONE copy and no thread touches the bytes.
-template <bool kResident, bool kGather, int kEpi, bool kLean = false>
+// kLean: 0 = general producer loop, 1 = lean loop with a register ring (streamed operand), 2 = lean loop with cp.async
+// landing tiles (gather front-end, or a streamed operand when the tiles fit next to the weights)
+template <bool kResident, bool kGather, int kEpi, int kLean = 0>
 __global__ void __launch_bounds__(kDnThreads, 1)
 dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
     const long long M = prm.M;
@@ -244,7 +246,7 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
     tc_fence_after_sync();
     const uint32_t tmem_base = s_tmem;
 
-    if (warp < kDnProducerWarps && kLean && kGather) {
+    if (warp < kDnProducerWarps && kLean == 2) {
         // ================= producers, gather front-end, lean loop =================
         // Operand row r of a tile = relu(X[cloud(r), gidx[r], :] + sign * Q[r / g_ns, :]).  Same two-group structure as the
         // streamed lean loop below, plus COALESCED, REGISTER-FREE gathers: a thread fetching its own row touches one
@@ -272,15 +274,16 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(ok ? src : X), "r"(ok ? 16 : 0) : "memory");
         };
         // gathered table row of my operand row in `t` (-1: past the end -> zeros)
-        auto fetch_ridx = [&](int t) -> int {
+        auto fetch_ridx = [&](int t) -> int {  // (a streamed operand is the identity gather)
             const long long row = (long long)(nb == 1 ? t : t / nb) * 128 + r;
             if (t >= n_tiles || row >= M) return -1;
+            if (!kGather) return (int)row;
             return (int)(dn_div(row, prm.g_rows_per_cloud) * prm.g_n) + __ldg(gidx + row);
         };
         // centre row my lane copies for tile t (lanes 0-7: the warp's rows 0-15, lanes 8-15: rows 16-31; -1: none)
         auto fetch_qrow = [&](int t) -> int {
             const long long row = (long long)(nb == 1 ? t : t / nb) * 128 + (warp & 3) * 32 + (la & 1) * 16;
-            if (!prm.Q || lane >= 16 || t >= n_tiles || row >= M) return -1;
+            if (!kGather || !prm.Q || lane >= 16 || t >= n_tiles || row >= M) return -1;
             return (int)dn_div(row, prm.g_ns);
         };
         int tile = blockIdx.x, c = g;
@@ -296,7 +299,7 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
                 const int src = __shfl_sync(kFull, ridx, (lane & 24) + m);
                 cp16(dst0 + (uint32_t)m * 128u + (uint32_t)((lj ^ m) << 4), X + (long long)src * prm.ldx + k, src >= 0 && k < K);
             }
-            if (lane < 16)
+            if (kGather && lane < 16)
                 cp16(xbuf_s + buf * kDnXposeBytes + 4096u + (uint32_t)la * 128u + (uint32_t)lj * 16u, prm.Q + (long long)qrow * prm.ldq + k,
                      qrow >= 0 && k < K);
             asm volatile("cp.async.commit_group;" ::: "memory");
@@ -345,11 +348,15 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
                 for (int q = 0; q < 4; ++q) {  // relu(x + sign*q); q is zero when there is no Q (x + sign*0 == x exactly)
                     const int jj = hf * 4 + q;
                     const float4 v = *reinterpret_cast<const float4 *>(myx + ((jj ^ (lane & 7)) << 4));
-                    const float4 qq = *reinterpret_cast<const float4 *>(myq + (jj << 4));
-                    vv[4 * q] = fmaxf(__fmaf_rn(sign, qq.x, v.x), 0.f);
-                    vv[4 * q + 1] = fmaxf(__fmaf_rn(sign, qq.y, v.y), 0.f);
-                    vv[4 * q + 2] = fmaxf(__fmaf_rn(sign, qq.z, v.z), 0.f);
-                    vv[4 * q + 3] = fmaxf(__fmaf_rn(sign, qq.w, v.w), 0.f);
+                    if (kGather) {
+                        const float4 qq = *reinterpret_cast<const float4 *>(myq + (jj << 4));
+                        vv[4 * q] = fmaxf(__fmaf_rn(sign, qq.x, v.x), 0.f);
+                        vv[4 * q + 1] = fmaxf(__fmaf_rn(sign, qq.y, v.y), 0.f);
+                        vv[4 * q + 2] = fmaxf(__fmaf_rn(sign, qq.z, v.z), 0.f);
+                        vv[4 * q + 3] = fmaxf(__fmaf_rn(sign, qq.w, v.w), 0.f);
+                    } else {
+                        vv[4 * q] = v.x; vv[4 * q + 1] = v.y; vv[4 * q + 2] = v.z; vv[4 * q + 3] = v.w;
+                    }
                 }
                 uint32_t hi[16], lo[16];
 #pragma unroll
@@ -368,7 +375,7 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
             s += 2;
             if (s >= (uint32_t)n_stages) { s -= (uint32_t)n_stages; ph ^= 1; }
         }
-    } else if (warp < kDnProducerWarps && kLean) {
+    } else if (warp < kDnProducerWarps && kLean == 1) {
         // ================= producers, streamed operand, lean loop =================
         // (kLean: no gather front-end, no softmax transform, 16-byte aligned rows, K % 4 == 0 — every plain layer of the step.)
         // Two groups of four warps take ALTERNATE K-chunks: thread (r, g) owns row r = tid & 127 (= TMEM lane r) and converts
@@ -1025,18 +1032,22 @@ extern "C" int dispu_dense_tf32x3_ex(const dispu_dense_args *a, dispu_stream_t s
     static const bool no_lean = getenv("DISPU_DENSE_GENERIC") != nullptr;
     // lean gather producer (coalesced gathers transposed through per-warp shared-memory buffers): aligned rows, K % 4 == 0,
     // centre rows shared by multiples of 16 operand rows
-    const bool lean_gather = a->gather_idx && !no_lean && !a->stat_in && (reinterpret_cast<uintptr_t>(a->X) & 15u) == 0 && ldx % 4 == 0 &&
-                             K % 4 == 0 && (a->gather_ns > 0 ? a->gather_ns : 1) % 16 == 0 &&
+    const bool lean_ok = !no_lean && !a->stat_in && (reinterpret_cast<uintptr_t>(a->X) & 15u) == 0 && ldx % 4 == 0 && K % 4 == 0;
+    const bool lean_gather = a->gather_idx && lean_ok && (a->gather_ns > 0 ? a->gather_ns : 1) % 16 == 0 &&
                              (!a->Q || ((reinterpret_cast<uintptr_t>(a->Q) & 15u) == 0 && (a->ldq > 0 ? a->ldq : K) % 4 == 0));
-    if (lean_gather) {
-        const size_t xp = (size_t)kDnProducerWarps * 2 * kDnXposeBytes;
+    // a streamed operand takes the same cp.async landing tiles when they leave the weight ring at least three stages
+    // (256-column layers with streamed weights keep the register ring: their 64 KB stages need the room)
+    const size_t xp = (size_t)kDnProducerWarps * 2 * kDnXposeBytes;
+    const bool lean_stream_tiles = !a->gather_idx && lean_ok && !getenv("DISPU_DENSE_REGRING") &&
+                                   (resident ? w_all + xp <= (size_t)kDnSmemBudget + 8 * 1024 : ((size_t)kDnSmemBudget - xp) / b_chunk >= 3);
+    if (lean_gather || lean_stream_tiles) {
         if (!resident) {
             stages = (int)(((size_t)kDnSmemBudget - xp) / b_chunk);
             if (stages > kDnMaxStages) stages = kDnMaxStages;
             smem = stages * b_chunk;
         }
     }
-    const bool lean_gather_ok = lean_gather && (resident ? w_all + (size_t)kDnProducerWarps * 2 * kDnXposeBytes <= (size_t)kDnSmemBudget + 8 * 1024 : stages >= 2);
+    const bool lean_gather_ok = (lean_gather || lean_stream_tiles) && (resident ? w_all + xp <= (size_t)kDnSmemBudget + 8 * 1024 : stages >= 2);
     const uint32_t xpose_off = (uint32_t)((smem + 15) & ~(size_t)15);
     if (lean_gather_ok) smem = xpose_off + (size_t)kDnProducerWarps * 2 * kDnXposeBytes;
     if (smem < 1024) smem = 1024;
@@ -1082,12 +1093,13 @@ extern "C" int dispu_dense_tf32x3_ex(const dispu_dense_args *a, dispu_stream_t s
         return finish_launch();
     };
     if (lean_gather_ok && !p.dbg) {
-        if (wnet) return resident ? launch(dense_tf32x3_kernel<true, true, 1, true>) : launch(dense_tf32x3_kernel<false, true, 1, true>);
-        return resident ? launch(dense_tf32x3_kernel<true, true, 0, true>) : launch(dense_tf32x3_kernel<false, true, 0, true>);
+        if (!p.gidx) return resident ? launch(dense_tf32x3_kernel<true, false, 0, 2>) : launch(dense_tf32x3_kernel<false, false, 0, 2>);
+        if (wnet) return resident ? launch(dense_tf32x3_kernel<true, true, 1, 2>) : launch(dense_tf32x3_kernel<false, true, 1, 2>);
+        return resident ? launch(dense_tf32x3_kernel<true, true, 0, 2>) : launch(dense_tf32x3_kernel<false, true, 0, 2>);
     }
     if (wnet) return resident ? launch(dense_tf32x3_kernel<true, true, 1>) : launch(dense_tf32x3_kernel<false, true, 1>);
     const bool lean = !p.gidx && !p.stat_in && !p.dbg && (reinterpret_cast<uintptr_t>(p.X) & 15u) == 0 && ldx % 4 == 0 && K % 4 == 0 && !no_lean;
-    if (lean) return resident ? launch(dense_tf32x3_kernel<true, false, 0, true>) : launch(dense_tf32x3_kernel<false, false, 0, true>);
+    if (lean) return resident ? launch(dense_tf32x3_kernel<true, false, 0, 1>) : launch(dense_tf32x3_kernel<false, false, 0, 1>);
     if (resident) return p.gidx ? launch(dense_tf32x3_kernel<true, true, 0>) : launch(dense_tf32x3_kernel<true, false, 0>);
     return p.gidx ? launch(dense_tf32x3_kernel<false, true, 0>) : launch(dense_tf32x3_kernel<false, false, 0>);
 }
