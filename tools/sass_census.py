@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "dispu_b200", "libdispu_b200.so")
 sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True, check=True).stdout
 demangle = lambda n: subprocess.run(["c++filt", n], capture_output=True, text=True).stdout.strip()  # noqa: E731
-cols = ["UTCHMMA", "LDTM", "STTM", "UTCBAR", "UBLKCP", "SYNCS", "STAS", "UCGABAR", "FFMA2", "REDUX", "HMMA"]
+cols = ["UTCHMMA", "LDTM", "STTM", "UTCBAR", "UBLKCP", "LDGSTS", "SYNCS", "STAS", "UCGABAR", "FFMA2", "REDUX", "HMMA"]
 kern = None
 rows = collections.OrderedDict()
 for line in sass.splitlines():
@@ -30,7 +30,8 @@ for line in sass.splitlines():
                 rows[kern][c] += 1
 print(f"# SASS census of {os.path.basename(so)} (sm_100a), one row per kernel: cuobjdump -sass | tools/sass_census.py")
 print("# UTCHMMA = tcgen05.mma, LDTM/STTM = tcgen05.ld/st, UTCBAR = tcgen05.commit, UBLKCP = cp.async.bulk (TMA), SYNCS = mbarrier ops,")
-print("# STAS = st.async (DSMEM), UCGABAR = cluster barrier, FFMA2 = packed fp32 FMA, REDUX = redux.sync, HMMA = legacy mma.sync (none expected)\n")
+print("# STAS = st.async (DSMEM), UCGABAR = cluster barrier, FFMA2 = packed fp32 FMA, REDUX = redux.sync, LDGSTS = cp.async (gather landing tiles),")
+print("# HMMA = warp-level mma.sync: only the 16-sample weight-net contraction in the dense kernel's epilogue (m16n8k16 f16, scaled hi/lo split)\n")
 print("| kernel | " + " | ".join(cols) + " | instr |")
 print("|---|" + "---|" * (len(cols) + 1))
 tot = collections.Counter()
