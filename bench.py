@@ -773,7 +773,7 @@ def kernel_traffic(family):
     src = os.path.join(ROOT, "dispu_b200", "csrc", ent["source"])
     sha = hashlib.sha256(open(src, "rb").read()).hexdigest()
     if sha != ent.get("source_sha256"):
-        return None, f"profiles/dense_traffic.json was captured from a different {ent['source']} (stale): re-run tools/capture_traffic.sh"
+        return None, f"profiles/dense_traffic.json was captured from a different {ent['source']} (stale): re-capture with tools/gpu_evidence.sh and stamp it with tools/ncu_traffic.py"
     return ent["dram_bytes_per_launch"], f"profiles/dense_traffic.json ({ent.get('how', 'ncu dram__bytes_read+write')})"
 
 

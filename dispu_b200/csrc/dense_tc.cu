@@ -274,11 +274,16 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(ok ? src : X), "r"(ok ? 16 : 0) : "memory");
         };
         // gathered table row of my operand row in `t` (-1: past the end -> zeros)
-        auto fetch_ridx = [&](int t) -> int {  // (a streamed operand is the identity gather)
+        // The index is kept as (table offset of the cloud, raw gathered index): the raw value is a global load whose first
+        // consumer must not sit right behind it (an in-order warp would stall for the whole L2 round trip) — the two are
+        // added only when the cursor reaches that tile, two iterations later.
+        auto fetch_ridx = [&](int t, int &base) -> int {  // (a streamed operand is the identity gather)
             const long long row = (long long)(nb == 1 ? t : t / nb) * 128 + r;
+            base = 0;
             if (t >= n_tiles || row >= M) return -1;
             if (!kGather) return (int)row;
-            return (int)(dn_div(row, prm.g_rows_per_cloud) * prm.g_n) + __ldg(gidx + row);
+            base = (int)(dn_div(row, prm.g_rows_per_cloud) * prm.g_n);
+            return __ldg(gidx + row);
         };
         // centre row my lane copies for tile t (lanes 0-7: the warp's rows 0-15, lanes 8-15: rows 16-31; -1: none)
         auto fetch_qrow = [&](int t) -> int {
@@ -288,17 +293,23 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
         };
         int tile = blockIdx.x, c = g;
         while (c >= nchunks) { c -= nchunks; tile += G; }
-        int ridx = left > 0 ? fetch_ridx(tile) : -1;
-        int ridx_nxt = left > 0 ? fetch_ridx(tile + G) : -1;
+        int ridx = -1, ridx_nxt = -1, base_nxt = 0;
+        if (left > 0) {
+            int b0;
+            const int g0 = fetch_ridx(tile, b0);
+            ridx = g0 < 0 ? -1 : b0 + g0;
+            ridx_nxt = fetch_ridx(tile + G, base_nxt);
+        }
         int qrow = left > 0 ? fetch_qrow(tile) : -1;
         auto issue_copies = [&](int cc, uint32_t buf) {  // chunk cc of the tile `ridx` / `qrow` describe -> buffer `buf`
             const int k = cc * kDnKC + lj * 4;
             const uint32_t dst0 = xbuf_s + buf * kDnXposeBytes + (uint32_t)(8 * la) * 128u;
+            int src[8];  // all eight row handles first: the copies then issue back to back instead of one per shuffle round trip
 #pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const int src = __shfl_sync(kFull, ridx, (lane & 24) + m);
-                cp16(dst0 + (uint32_t)m * 128u + (uint32_t)((lj ^ m) << 4), X + (long long)src * prm.ldx + k, src >= 0 && k < K);
-            }
+            for (int m = 0; m < 8; ++m) src[m] = __shfl_sync(kFull, ridx, (lane & 24) + m);
+#pragma unroll
+            for (int m = 0; m < 8; ++m)
+                cp16(dst0 + (uint32_t)m * 128u + (uint32_t)((lj ^ m) << 4), X + (long long)src[m] * prm.ldx + k, src[m] >= 0 && k < K);
             if (kGather && lane < 16)
                 cp16(xbuf_s + buf * kDnXposeBytes + 4096u + (uint32_t)la * 128u + (uint32_t)lj * 16u, prm.Q + (long long)qrow * prm.ldq + k,
                      qrow >= 0 && k < K);
@@ -326,8 +337,19 @@ dense_tf32x3_kernel(const __grid_constant__ DenseParams prm) {
             if (c >= nchunks) {  // my next chunk lies in a later tile of this CTA
                 int skipped = 0;
                 do { c -= nchunks; tile += G; ++skipped; } while (c >= nchunks);
-                ridx = (left > 1) ? (skipped == 1 ? ridx_nxt : fetch_ridx(tile)) : -1;
-                ridx_nxt = (left > 1) ? fetch_ridx(tile + G) : -1;
+                if (left > 1) {
+                    if (skipped == 1) {
+                        ridx = ridx_nxt < 0 ? -1 : base_nxt + ridx_nxt;
+                    } else {
+                        int b0;
+                        const int g0 = fetch_ridx(tile, b0);
+                        ridx = g0 < 0 ? -1 : b0 + g0;
+                    }
+                    ridx_nxt = fetch_ridx(tile + G, base_nxt);
+                } else {
+                    ridx = -1;
+                    ridx_nxt = -1;
+                }
                 qrow = (left > 1) ? fetch_qrow(tile) : -1;
                 wnew = true;
             }
