@@ -322,8 +322,7 @@ knn_select1_kernel(int n, int m, int k, const float *__restrict__ data, const fl
     __shared__ float4 s_tile[kKsChunk];
     extern __shared__ __align__(16) float s_raw[];  // kTma: one 12 KB landing buffer (cp.async.bulk)
     __shared__ __align__(8) uint64_t s_bar[2];
-    __shared__ float s_bd[kKsWarps][kKsCap];
-    __shared__ int s_bi[kKsWarps][kKsCap];
+    __shared__ unsigned long long s_bk[kKsWarps][kKsCap];  // survivors: (distance bits : index) keys
     __shared__ float s_od[kKsWarps][32];
     __shared__ int s_oi[kKsWarps][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -331,8 +330,7 @@ knn_select1_kernel(int n, int m, int k, const float *__restrict__ data, const fl
     const float *pts = data + (size_t)cloud * n * 3;
     const int q0 = (blockIdx.x * kKsWarps + warp) * kKsQueriesPerWarp;
     const float inf = __int_as_float(0x7f800000);
-    float *bd = s_bd[warp];
-    int *bi = s_bi[warp];
+    unsigned long long *bk = s_bk[warp];
     ts::stage_begin<kTma>(s_raw, s_bar, pts, n, kKsChunk);
     const int tn = ts::stage_tile<kTma>(s_tile, s_raw, s_bar, pts, n, kKsChunk, 0, 1);
     // Full chunk: a second layout for the distance loop — slot pair (2h, 2h + 1) of lane l as three packed pairs
@@ -390,8 +388,13 @@ knn_select1_kernel(int n, int m, int k, const float *__restrict__ data, const fl
         const float tau = __shfl_sync(kFull, warp_sort32_asc(lmin, lane), k - 1);
         // my survivors as a bit mask, then a warp prefix sum of the counts
         unsigned mine = 0;
+        if (tn == kKsChunk) {  // no padding slots: every distance is finite (or NaN, which fails the comparison)
 #pragma unroll
-        for (int sI = 0; sI < 32; ++sI) mine |= (d[sI] <= tau && d[sI] < inf) ? (1u << sI) : 0u;
+            for (int sI = 0; sI < 32; ++sI) mine |= (d[sI] <= tau) ? (1u << sI) : 0u;
+        } else {
+#pragma unroll
+            for (int sI = 0; sI < 32; ++sI) mine |= (d[sI] <= tau && d[sI] < inf) ? (1u << sI) : 0u;
+        }
         const int cnt = __popc(mine);
         int incl = cnt;
 #pragma unroll
@@ -405,30 +408,27 @@ knn_select1_kernel(int n, int m, int k, const float *__restrict__ data, const fl
         if (S > kKsCap) {  // masses of exactly equal distances: the serial definition
             knn_insertion_scan(n, k, pts, qx, qy, qz, lane, rd, ri);
         } else {
+            // survivors as ONE 64-bit key (distance bits : index): squared distances are >= +0, so their bit patterns order
+            // like the values and a single unsigned comparison is the (d, idx) lexicographic order — ties to the lower index
             int pos = incl - cnt;
 #pragma unroll
             for (int sI = 0; sI < 32; ++sI) {
                 if (mine & (1u << sI)) {
-                    bd[pos] = d[sI];
-                    bi[pos] = sI * 32 + (lane ^ sI);
+                    bk[pos] = ((unsigned long long)__float_as_uint(d[sI]) << 32) | (unsigned)(sI * 32 + (lane ^ sI));
                     ++pos;
                 }
             }
             __syncwarp();
-            // rank by counting on the (d, idx) key; ranks < 32 are the answer, ascending
+            // rank by counting; ranks < 32 are the answer, ascending
             for (int e0 = 0; e0 < S; e0 += 32) {
                 const int e = e0 + lane;
-                const float de = e < S ? bd[e] : inf;
-                const int ie = e < S ? bi[e] : 0x7fffffff;
+                const unsigned long long ke = e < S ? bk[e] : ~0ull;
                 int rank = 0;
-                for (int f = 0; f < S; ++f) {
-                    const float df = bd[f];
-                    const int jf = bi[f];
-                    rank += (df < de) || (df == de && jf < ie);
-                }
+#pragma unroll 4
+                for (int f = 0; f < S; ++f) rank += bk[f] < ke;
                 if (e < S && rank < 32) {
-                    s_od[warp][rank] = de;
-                    s_oi[warp][rank] = ie;
+                    s_od[warp][rank] = __uint_as_float((unsigned)(ke >> 32));
+                    s_oi[warp][rank] = (int)(unsigned)ke;
                 }
             }
             __syncwarp();
