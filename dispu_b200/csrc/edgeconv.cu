@@ -45,6 +45,8 @@ __device__ __forceinline__ unsigned ord_key(float f) {
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
+__device__ __forceinline__ float ord_key_inv(unsigned k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
+
 // ascending bitonic sort of one value per lane (15 shuffle steps)
 __device__ __forceinline__ float fk_warp_sort32(float v, int lane) {
 #pragma unroll
@@ -74,7 +76,8 @@ feature_knn_kernel(int n, int m, int c, int k, int skip, const float *__restrict
     float *s_ft = fk_smem;                           // [c][kStride]
     float *s_r = s_ft + (size_t)c * kStride;         // [kChunk]
     float *s_q = s_r + kChunk;                       // [warps][kFkQueriesPerWarp][c]
-    float *s_sd = s_q + (size_t)kFkWarps * kFkQueriesPerWarp * c;                 // [warps][kFkCap] survivor distances
+    float *s_sd = s_q + (size_t)kFkWarps * kFkQueriesPerWarp * c;                 // [warps][kFkCap] survivor keys (with s_si: 64-bit)
+    s_sd += (reinterpret_cast<uintptr_t>(s_sd) >> 2) & 1;                         // 8-byte aligned for any c (2 spare floats allocated)
     int *s_si = reinterpret_cast<int *>(s_sd + kFkWarps * kFkCap);                // [warps][kFkCap] survivor indices
     float *s_od = reinterpret_cast<float *>(s_si + kFkWarps * kFkCap);            // [warps][32] ranked output
     int *s_oi = reinterpret_cast<int *>(s_od + kFkWarps * 32);
@@ -204,8 +207,9 @@ feature_knn_kernel(int n, int m, int c, int k, int skip, const float *__restrict
             // ties to the lower index.  A query whose survivors overflow the buffer (masses of equal distances) takes the
             // round-by-round extraction below instead.
             unsigned slow = 0;  // bit w: query w needs the fallback
-            float *sd = s_sd + warp * kFkCap;
-            int *si = s_si + warp * kFkCap;
+            // survivors as ONE 64-bit key (order-preserving distance key : index): a single unsigned comparison is the
+            // (d, idx) lexicographic order — ties to the lower index — and a survivor is one 8-byte store
+            unsigned long long *sk = reinterpret_cast<unsigned long long *>(s_sd) + warp * kFkCap;  // the s_sd | s_si region: 2 x warps x kFkCap words
             const unsigned lt_mask = (1u << lane) - 1u;
 #pragma unroll
             for (int w = 0; w < kQ; ++w) {
@@ -217,7 +221,7 @@ feature_knn_kernel(int n, int m, int c, int k, int skip, const float *__restrict
                 {
                     const bool keep = cd[w] <= bound && cd[w] < inf;
                     const unsigned mask = __ballot_sync(kFull, keep);
-                    if (keep) { const int pos = __popc(mask & lt_mask); sd[pos] = cd[w]; si[pos] = ci[w]; }
+                    if (keep) { const int pos = __popc(mask & lt_mask); sk[pos] = ((unsigned long long)ord_key(cd[w]) << 32) | (unsigned)ci[w]; }
                     S = __popc(mask);
                 }
 #pragma unroll
@@ -226,7 +230,7 @@ feature_knn_kernel(int n, int m, int c, int k, int skip, const float *__restrict
                     const unsigned mask = __ballot_sync(kFull, keep);
                     if (mask) {
                         const int pos = S + __popc(mask & lt_mask);
-                        if (keep && pos < kFkCap) { sd[pos] = d[w][t]; si[pos] = t0 + t * 32 + lane; }
+                        if (keep && pos < kFkCap) sk[pos] = ((unsigned long long)ord_key(d[w][t]) << 32) | (unsigned)(t0 + t * 32 + lane);
                         S += __popc(mask);
                     }
                 }
@@ -236,15 +240,11 @@ feature_knn_kernel(int n, int m, int c, int k, int skip, const float *__restrict
                 } else {
                     for (int e0 = 0; e0 < S; e0 += 32) {
                         const int e = e0 + lane;
-                        const float de = e < S ? sd[e] : inf;
-                        const int ie = e < S ? si[e] : 0x7fffffff;
+                        const unsigned long long ke = e < S ? sk[e] : ~0ull;
                         int rank = 0;
-                        for (int f = 0; f < S; ++f) {
-                            const float df = sd[f];
-                            const int jf = si[f];
-                            rank += (df < de) || (df == de && jf < ie);
-                        }
-                        if (e < S && rank < 32) { s_od[warp * 32 + rank] = de; s_oi[warp * 32 + rank] = ie; }
+#pragma unroll 4
+                        for (int f = 0; f < S; ++f) rank += sk[f] < ke;
+                        if (e < S && rank < 32) { s_od[warp * 32 + rank] = ord_key_inv((unsigned)(ke >> 32)); s_oi[warp * 32 + rank] = (int)(unsigned)ke; }
                     }
                     __syncwarp();
                     nd[w] = lane < k ? s_od[warp * 32 + lane] : inf;
@@ -682,7 +682,7 @@ using namespace dispu;
 template <int P>
 static int launch_feature_knn(int b, int n, int m, int c, int k, int skip, const float *points, int ldp, const float *queries,
                               int ldq, float *dist, int *idx, cudaStream_t stream, const EcProjArgs &pj = EcProjArgs{}) {
-    size_t smem = ((size_t)c * (32 * P + 1) + 32 * P + (size_t)kFkWarps * kFkQueriesPerWarp * c + 2 * kFkWarps * (kFkCap + 32)) * sizeof(float);
+    size_t smem = ((size_t)c * (32 * P + 1) + 32 * P + (size_t)kFkWarps * kFkQueriesPerWarp * c + 2 * kFkWarps * (kFkCap + 32) + 2) * sizeof(float);
     const size_t smem_proj = ((size_t)c * kEcProjW + kEcProjW) * sizeof(float);
     if (pj.proj && smem < smem_proj) smem = smem_proj;
     EcProjArgs pja = pj;
@@ -703,7 +703,7 @@ static int feature_knn_dispatch(int b, int n, int m, int c, int k, int skip, con
                                 int ldq, float *dist, int *idx, cudaStream_t stream, const EcProjArgs &pj = EcProjArgs{}) {
     // largest chunk (32*P candidates) that covers the cloud and whose transposed features fit in shared memory
     auto fits = [&](int P) {
-        return ((size_t)c * (32 * P + 1) + 32 * P + (size_t)kFkWarps * kFkQueriesPerWarp * c + 2 * kFkWarps * (kFkCap + 32)) * sizeof(float) <= 220 * 1024;
+        return ((size_t)c * (32 * P + 1) + 32 * P + (size_t)kFkWarps * kFkQueriesPerWarp * c + 2 * kFkWarps * (kFkCap + 32) + 2) * sizeof(float) <= 220 * 1024;
     };
     if (n > 512 && fits(32)) return launch_feature_knn<32>(b, n, m, c, k, skip, points, ldp, queries, ldq, dist, idx, stream, pj);
     if (n > 256 && fits(16)) return launch_feature_knn<16>(b, n, m, c, k, skip, points, ldp, queries, ldq, dist, idx, stream, pj);
