@@ -7,20 +7,29 @@
 // instead of separate bias_add / relu passes.
 //
 // Warp-specialised persistent kernel, one CTA per SM, 17 warps (TS form: the A operand lives in tensor memory):
-//   warps 0-7   producers: thread (row, half of the 32-column K-chunk) keeps two chunks of raw global loads in flight
-//               in registers (plus prefetch.global.L2 further ahead), applies the optional gather front-end
-//               (relu(X[idx] + sign*Q)) or softmax transform at consume time, splits into TF32 hi/lo and writes both
-//               planes straight into the TMEM A ring (4 slots x 64 columns) with tcgen05.st;
-//   one of them also issues the TMA bulk copy (cp.async.bulk + mbarrier transaction bytes) of the pre-packed weight
-//               chunk when the weight does not stay resident in shared memory;
+//   warps 0-7   producers: fetch the operand rows, apply the optional gather front-end (relu(X[idx] + sign*Q)) or softmax
+//               transform, split into TF32 hi/lo and write both planes straight into the TMEM A ring (4 slots x 64 columns)
+//               with tcgen05.st.  Three loops (template parameter kLean):
+//                 2  lean, cp.async landing tiles: two 4-warp groups on alternate K-chunks, thread = row; the rows are
+//                    copied global -> shared 16 bytes at a time with the eight lanes of a quarter-warp sharing a row (four
+//                    128-byte lines per instruction instead of 32), into XOR-swizzled per-warp tiles read back row per
+//                    thread — the gather front-end, and streamed operands when the tiles fit next to the weights;
+//                 1  lean, register ring: same two-group structure, one own chunk in registers with immediate refill and
+//                    prefetch.global.L2 ahead — streamed operands next to 64 KB weight stages (after_conv, aggregation);
+//                 0  general: thread (row, half chunk), scalar fallbacks for any alignment / K, softmax operand mode,
+//                    component masks and clock64 probes.
+//               The lean loops hold no state in local memory and carry no fallbacks: see the comments at their heads.
+//   one producer thread per group also issues the TMA bulk copy (cp.async.bulk + mbarrier transaction bytes) of the
+//               pre-packed weight chunk when the weight does not stay resident in shared memory;
 //   warps 8-15  epilogue, two per TMEM lane quarter on alternating 16-column blocks: tcgen05.ld -> bias / ReLU /
 //               row scale -> shared-memory staging -> 8 rows x 64 B per store instruction (+ residuals), or the
-//               weight-net contraction (kEpi == 1);
-//   warp  16    one thread issues 4 K-steps x 3 tcgen05.mma per chunk (A from TMEM, B from shared memory, M=128,
+//               weight-net contraction on warp-level f16 MMAs (kEpi == 1);
+//   warp  16    one thread issues up to 4 K-steps x 3 tcgen05.mma per chunk (A from TMEM, B from shared memory, M=128,
 //               N=N_pad) and releases ring slots with tcgen05.commit.
 // full/empty mbarriers on the ring slots and on the TMEM accumulators (two of <= 128 columns, or one of 256) keep loads,
-// MMAs and the epilogue of consecutive tiles overlapped.  Development probes: DISPU_DENSE_DBG masks pipeline components,
-// DISPU_DENSE_TRACE records clock64 traces of the three roles (tools/dense_dbg.py, tools/dense_trace.py).
+// MMAs and the epilogue of consecutive tiles overlapped.  Development probes (general loop only): DISPU_DENSE_DBG masks
+// pipeline components, DISPU_DENSE_TRACE records clock64 traces of the three roles (tools/dense_dbg.py, tools/dense_trace.py);
+// DISPU_DENSE_GENERIC=1 forces the general loop, DISPU_DENSE_REGRING=1 the register ring for streamed operands.
 #include <stdlib.h>
 
 #include "common.cuh"

@@ -273,7 +273,9 @@ int dispu_dense_tf32x3(long long M, int K, int N, const float *X, const void *pa
  *   - weight-net epilogue (wn_xyz != NULL; needs the gather front-end with gather_ns == 16): the layer output G is
  *     never written; instead Y[r/16][ch*16+t] = sum_s G[16*(r/16)+s][ch] * wn[s][t] with
  *     wn[s][t] = relu(((xyz[cloud, gather_idx[r]] - xyz[r/16]) . wn_w[:,t] + wn_b[t]) * wn_scale): conv1 of PointShuffle2
- *     fused with weight_net_hidden and the transposed product (Common/ops.py:1055-1067).  Y is (M/16, 16*N), ldy its
+ *     fused with weight_net_hidden and the transposed product (Common/ops.py:1055-1067); the 16-sample contraction runs on
+ *     f16 (hi, scaled lo) pairs with FP32 accumulation — fp32-level accuracy for |activation| < 65504, inf/NaN beyond.
+ *     Y is (M/16, 16*N), ldy its
  *     row stride (0 = dense), wn_w (3,16), wn_b (16) or NULL. */
 typedef struct dispu_dense_args {
     long long M;

@@ -677,7 +677,8 @@ def test_generator_hoisted_equals_reference_op_sequence():
 
 
 @pytest.mark.parametrize("M,K,N", [(1000, 131, 128), (300, 3, 24), (128, 482, 256), (4100, 2048, 256), (77, 64, 3), (5000, 120, 48),
-                                   (16384, 128, 128), (129, 256, 64)])
+                                   (16384, 128, 128), (129, 256, 64),
+                                   (40000, 32, 64), (777, 16, 48), (300, 8, 16), (33000, 36, 256)])  # one-chunk / two-chunk K on the lean loops
 @pytest.mark.parametrize("relu", [False, True])
 def test_dense_tf32x3(rng, M, K, N, relu):
     """tcgen05 3xTF32 dense layer vs a float64 reference: fp32-level accuracy (tolerance 1e-5 relative to the row scale)."""
