@@ -705,6 +705,16 @@ static int feature_knn_dispatch(int b, int n, int m, int c, int k, int skip, con
     auto fits = [&](int P) {
         return ((size_t)c * (32 * P + 1) + 32 * P + (size_t)kFkWarps * kFkQueriesPerWarp * c + 2 * kFkWarps * (kFkCap + 32) + 2) * sizeof(float) <= 220 * 1024;
     };
+    static const int force_p = [] { const char *e = getenv("DISPU_FK_P"); return e ? atoi(e) : 0; }();  // development switch (A/B timing)
+    if (force_p == 8) return launch_feature_knn<8>(b, n, m, c, k, skip, points, ldp, queries, ldq, dist, idx, stream, pj);
+    if (force_p == 16 && fits(16)) return launch_feature_knn<16>(b, n, m, c, k, skip, points, ldp, queries, ldq, dist, idx, stream, pj);
+    // Clouds of more than 512 points: measured at b = 32, n = 1024 (c4's second stage), one 1024-candidate chunk (one CTA of
+    // 251 registers per SM) loses to several smaller chunks with the carried list (EdgeConv block, c = 48: 398 us vs 351 us
+    // with 256-candidate chunks; c = 24: 281 vs 238 us with 512-candidate chunks)
+    if (n > 512 && force_p == 0) {
+        if (c <= 32 && fits(16)) return launch_feature_knn<16>(b, n, m, c, k, skip, points, ldp, queries, ldq, dist, idx, stream, pj);
+        return launch_feature_knn<8>(b, n, m, c, k, skip, points, ldp, queries, ldq, dist, idx, stream, pj);
+    }
     if (n > 512 && fits(32)) return launch_feature_knn<32>(b, n, m, c, k, skip, points, ldp, queries, ldq, dist, idx, stream, pj);
     if (n > 256 && fits(16)) return launch_feature_knn<16>(b, n, m, c, k, skip, points, ldp, queries, ldq, dist, idx, stream, pj);
     return launch_feature_knn<8>(b, n, m, c, k, skip, points, ldp, queries, ldq, dist, idx, stream, pj);
