@@ -555,148 +555,6 @@ static int launch_knn(int b, int n, int m, int k, const float *data, const float
 // The reference compares in double against 1e40; for float inputs that is the float order with a
 // +inf start (a finite float is always < 1e40, inf/NaN never are), and float(1e40) = +inf is what
 // it stores when fewer than three known points exist.
-// Clouds of several chunks (n > 1024, e.g. the 4096-point second stage of the 16x generator): the register-resident form
-// above applied chunk by chunk.  A warp keeps the k best (d, idx) of its query in lanes 0..k-1 between chunks; every chunk's
-// 32 distances per lane are evaluated on packed FP32 from the paired tile, thresholded — chunk 0 by the k-th smallest lane
-// minimum, later chunks by the carried k-th best, STRICTLY (a later candidate at the same distance has the higher index and
-// loses the tie) — and the few survivors are ranked together with the carried list on 64-bit (distance bits : index) keys.
-// The older kernel walks later chunks 32 candidates at a time with a ballot and a data-dependent insertion loop per step.
-template <bool kTma>
-__global__ void __launch_bounds__(kKsWarps * 32, 3)
-knn_selectn_kernel(int n, int m, int k, const float *__restrict__ data, const float *__restrict__ query,
-                   float *__restrict__ dist, int *__restrict__ idx) {
-    __shared__ float4 s_tile[kKsChunk];
-    extern __shared__ __align__(16) float s_raw[];  // kTma: two 12 KB landing buffers (cp.async.bulk)
-    __shared__ __align__(8) uint64_t s_bar[2];
-    __shared__ unsigned long long s_bk[kKsWarps][kKsCap];  // survivors: (distance bits : index) keys
-    __shared__ float s_od[kKsWarps][32];
-    __shared__ int s_oi[kKsWarps][32];
-    __shared__ float2 s_px[16 * 32], s_py[16 * 32], s_pz[16 * 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int cloud = blockIdx.y;
-    const float *pts = data + (size_t)cloud * n * 3;
-    const int q0 = (blockIdx.x * kKsWarps + warp) * kKsQueriesPerWarp;
-    const float inf = __int_as_float(0x7f800000);
-    unsigned long long *bk = s_bk[warp];
-    float ld[kKsQueriesPerWarp];  // carried list: lane j holds the j-th best so far
-    int li[kKsQueriesPerWarp];
-    bool overflow[kKsQueriesPerWarp];
-    float qx[kKsQueriesPerWarp], qy[kKsQueriesPerWarp], qz[kKsQueriesPerWarp];
-#pragma unroll
-    for (int u = 0; u < kKsQueriesPerWarp; ++u) {
-        ld[u] = inf; li[u] = 0; overflow[u] = false;
-        const int j = min(q0 + u, m - 1);
-        const float *q = query + ((size_t)cloud * m + j) * 3;
-        qx[u] = __ldg(q); qy[u] = __ldg(q + 1); qz[u] = __ldg(q + 2);
-    }
-    const int ntiles = ceil_div(n, kKsChunk);
-    ts::stage_begin<kTma>(s_raw, s_bar, pts, n, kKsChunk);
-    for (int ti = 0; ti < ntiles; ++ti) {
-        const int t0 = ti * kKsChunk;
-        const int tn = ts::stage_tile<kTma>(s_tile, s_raw, s_bar, pts, n, kKsChunk, ti, ntiles);
-        if (tn == kKsChunk) {  // paired layout of the full chunk (see knn_select1_kernel)
-            for (int e = threadIdx.x; e < 16 * 32; e += kKsWarps * 32) {
-                const int h = e >> 5, l = e & 31;
-                const float4 a = s_tile[(2 * h) * 32 + (l ^ (2 * h))], b = s_tile[(2 * h + 1) * 32 + (l ^ (2 * h + 1))];
-                s_px[e] = make_float2(a.x, b.x);
-                s_py[e] = make_float2(a.y, b.y);
-                s_pz[e] = make_float2(a.z, b.z);
-            }
-        }
-        __syncthreads();
-        if (q0 >= m) continue;
-#pragma unroll 1
-        for (int u = 0; u < kKsQueriesPerWarp; ++u) {
-            if (overflow[u] || q0 + u >= m) continue;
-            float d[32];
-            float lmin = inf;
-            if (tn == kKsChunk) {
-                const ks_f32x2 qx2 = ks_pack(qx[u], qx[u]), qy2 = ks_pack(qy[u], qy[u]), qz2 = ks_pack(qz[u], qz[u]);
-#pragma unroll
-                for (int h = 0; h < 16; ++h) {
-                    const ks_f32x2 dx = ks_sub2(qx2, *reinterpret_cast<const ks_f32x2 *>(&s_px[h * 32 + lane]));
-                    const ks_f32x2 dy = ks_sub2(qy2, *reinterpret_cast<const ks_f32x2 *>(&s_py[h * 32 + lane]));
-                    const ks_f32x2 dz = ks_sub2(qz2, *reinterpret_cast<const ks_f32x2 *>(&s_pz[h * 32 + lane]));
-                    float xx0, xx1, yy0, yy1, zz0, zz1;
-                    ks_unpack(ks_mul2(dx, dx), xx0, xx1);
-                    ks_unpack(ks_mul2(dy, dy), yy0, yy1);
-                    ks_unpack(ks_mul2(dz, dz), zz0, zz1);
-                    d[2 * h] = __fadd_rn(__fadd_rn(xx0, yy0), zz0);
-                    d[2 * h + 1] = __fadd_rn(__fadd_rn(xx1, yy1), zz1);
-                    lmin = fminf(lmin, fminf(d[2 * h], d[2 * h + 1]));
-                }
-            } else {
-#pragma unroll
-                for (int sI = 0; sI < 32; ++sI) {
-                    const int c = sI * 32 + (lane ^ sI);
-                    const float4 p = s_tile[c < tn ? c : 0];
-                    const float v = d2_ref_cpu(__fsub_rn(qx[u], p.x), __fsub_rn(qy[u], p.y), __fsub_rn(qz[u], p.z));
-                    d[sI] = c < tn ? v : inf;
-                    lmin = fminf(lmin, d[sI]);
-                }
-            }
-            unsigned mine = 0;
-            int kc = 0;  // carried entries that take part in the ranking
-            if (ti == 0) {
-                const float tau = __shfl_sync(kFull, warp_sort32_asc(lmin, lane), k - 1);
-#pragma unroll
-                for (int sI = 0; sI < 32; ++sI) mine |= (d[sI] <= tau && d[sI] < inf) ? (1u << sI) : 0u;
-            } else {
-                const float tau = __shfl_sync(kFull, ld[u], k - 1);  // the carried k-th best: only strictly closer points can enter
-#pragma unroll
-                for (int sI = 0; sI < 32; ++sI) mine |= (d[sI] < tau) ? (1u << sI) : 0u;
-                if (__ballot_sync(kFull, mine != 0) == 0) continue;  // nothing in this chunk improves the list
-                kc = k;
-            }
-            const int cnt = __popc(mine);
-            int incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(kFull, incl, o);
-                if (lane >= o) incl += v;
-            }
-            const int S = kc + __shfl_sync(kFull, incl, 31);
-            if (S > kKsCap) { overflow[u] = true; continue; }  // masses of exactly equal distances: the serial definition at the end
-            if (lane < kc) bk[lane] = ((unsigned long long)__float_as_uint(ld[u]) << 32) | (unsigned)li[u];
-            int pos = kc + incl - cnt;
-#pragma unroll
-            for (int sI = 0; sI < 32; ++sI) {
-                if (mine & (1u << sI)) {
-                    bk[pos] = ((unsigned long long)__float_as_uint(d[sI]) << 32) | (unsigned)(t0 + sI * 32 + (lane ^ sI));
-                    ++pos;
-                }
-            }
-            __syncwarp();
-            for (int e0 = 0; e0 < S; e0 += 32) {  // rank by counting; ranks < 32 become the carried list, ascending
-                const int e = e0 + lane;
-                const unsigned long long ke = e < S ? bk[e] : ~0ull;
-                int rank = 0;
-#pragma unroll 4
-                for (int f = 0; f < S; ++f) rank += bk[f] < ke;
-                if (e < S && rank < 32) {
-                    s_od[warp][rank] = __uint_as_float((unsigned)(ke >> 32));
-                    s_oi[warp][rank] = (int)(unsigned)ke;
-                }
-            }
-            __syncwarp();
-            const int have = min(S, 32);
-            ld[u] = lane < have ? s_od[warp][lane] : inf;
-            li[u] = lane < have ? s_oi[warp][lane] : 0;
-            __syncwarp();
-        }
-    }
-#pragma unroll 1
-    for (int u = 0; u < kKsQueriesPerWarp; ++u) {
-        const int j = q0 + u;
-        if (j >= m) continue;
-        if (overflow[u]) knn_insertion_scan(n, k, pts, qx[u], qy[u], qz[u], lane, ld[u], li[u]);
-        if (lane < k) {
-            const size_t o = ((size_t)cloud * m + j) * k + lane;
-            if (dist) dist[o] = ld[u];
-            idx[o] = li[u];
-        }
-    }
-}
 template <bool kTma>
 __global__ void __launch_bounds__(kKnnThreads)
 three_nn_kernel(int n, int m, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
@@ -767,17 +625,6 @@ extern "C" int dispu_knn(int b, int n, int m, int k, const float *xyz1, const fl
                 knn_select1_kernel<true><<<grid, kKsWarps * 32, (size_t)kKsChunk * 12, stream>>>(n, m, k, xyz1, xyz2, dist, idx);
             } else
                 knn_select1_kernel<false><<<grid, kKsWarps * 32, 0, stream>>>(n, m, k, xyz1, xyz2, dist, idx);
-            return finish_launch();
-        }
-        if (!generic) {  // several chunks: the register-resident form chunk by chunk
-            count_launch();
-            if (knn_use_tma(xyz1, n)) {
-                const cudaError_t e = cudaFuncSetAttribute(knn_selectn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kKsChunk * 12);
-                if (e != cudaSuccess) return (int)e;
-                knn_selectn_kernel<true><<<grid, kKsWarps * 32, landing_bytes(n, kKsChunk), stream>>>(n, m, k, xyz1, xyz2, dist, idx);
-            } else {
-                knn_selectn_kernel<false><<<grid, kKsWarps * 32, 0, stream>>>(n, m, k, xyz1, xyz2, dist, idx);
-            }
             return finish_launch();
         }
         if (knn_use_tma(xyz1, n)) {
